@@ -1,0 +1,856 @@
+// Host side of libdiff3d_b200.so: handle, weight packing, workspace, kernel sequencing of one denoiser call
+// (MODEL:249-257), the S-step DDIM loop (DIFF:263-300) with CUDA-graph replay, and the extern "C" boundary
+// declared in include/diff3d_b200.h.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/diff3d_b200.h"
+#include "kernels.cuh"
+
+using namespace d3d;
+
+namespace {
+
+std::string g_create_error;
+
+struct Lin {
+  int N = 0, K = 0;
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  float* bias = nullptr;
+  bool have_w = false;
+  CUtensorMap m_hi, m_lo;
+};
+
+struct Blk {
+  float *n1g = nullptr, *n1b = nullptr, *n2g = nullptr, *n2b = nullptr;
+  Lin qkv, proj, fc1, fc2;
+  float *tw = nullptr, *tb = nullptr;   // per-block time Linear(1024 -> 512), fp32
+  bool have_t = false;
+};
+
+struct OperandBuf {   // a GEMM A operand living in the workspace
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  CUtensorMap m_hi, m_lo;
+};
+
+}  // namespace
+
+struct d3d_handle {
+  d3d_config cfg{};
+  int F = 0, J = 0, nblk = 0, num_sms = 148;
+  int64_t tok_cap = 0;   // workspace rows (multiple of 128)
+  std::string err;
+  int64_t launches = 0;
+
+  // parameters
+  std::vector<Blk> blk;
+  float *wf_t = nullptr, *bf = nullptr, *spos = nullptr, *tpos = nullptr;
+  float *sn_g = nullptr, *sn_b = nullptr, *tn_g = nullptr, *tn_b = nullptr;
+  float *hg = nullptr, *hb = nullptr, *wh = nullptr, *bh = nullptr;
+  float *tm1w = nullptr, *tm1b = nullptr, *tm3w = nullptr, *tm3b = nullptr;
+  std::map<std::string, bool> loaded;
+
+  // workspace
+  float* X = nullptr;
+  float* QKV = nullptr;
+  OperandBuf A, ATT, H;
+  float *in_x2d = nullptr, *y = nullptr, *in_noise = nullptr;
+  int64_t in_noise_cap = 0;
+  float *t_f32 = nullptr, *e0 = nullptr, *h1 = nullptr, *h2 = nullptr;   // time-MLP scratch, max(max_clips, S) rows
+  int t_rows_cap = 0;
+  float* tv_steps = nullptr;     // [S, nblk, 512] table for the DDIM loop
+  int tv_cap = 0;
+  float* tv_general = nullptr;   // [max_clips, nblk, 512] for per-sample t
+  int32_t* perm_dev = nullptr;
+
+  // schedule
+  int S = 0;
+  std::vector<int> times;
+  std::vector<DdimStep> steps;
+  bool have_schedule = false, table_valid = false, need_noise = false;
+
+  std::map<int, cudaGraphExec_t> graphs;
+  std::map<int, int64_t> graph_launches;
+  cudaStream_t cap_stream = nullptr;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+#define CK(expr)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      char _b[512];                                                                                    \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      h->err = _b;                                                                                     \
+      return static_cast<int>(_e);                                                                     \
+    }                                                                                                  \
+  } while (0)
+// kernel launch: counted
+#define KL(expr)       \
+  do {                 \
+    CK(expr);          \
+    ++h->launches;     \
+  } while (0)
+
+int fail(d3d_handle* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+template <typename T>
+int dev_alloc(d3d_handle* h, T** p, int64_t n, bool zero = true) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, static_cast<size_t>(n) * sizeof(T)));
+  if (zero) CK(cudaMemset(q, 0, static_cast<size_t>(n) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+int alloc_operand(d3d_handle* h, OperandBuf* o, int64_t rows, int K) {
+  int r;
+  if ((r = dev_alloc(h, &o->hi, rows * K))) return r;
+  if ((r = dev_alloc(h, &o->lo, rows * K))) return r;
+  if (make_operand_map(&o->m_hi, o->hi, rows, K) || make_operand_map(&o->m_lo, o->lo, rows, K))
+    return fail(h, -20, "cuTensorMapEncodeTiled failed for a workspace operand");
+  return 0;
+}
+
+int alloc_lin(d3d_handle* h, Lin* l, int N, int K) {
+  l->N = N;
+  l->K = K;
+  int r;
+  if ((r = dev_alloc(h, &l->hi, static_cast<int64_t>(N) * K))) return r;
+  if ((r = dev_alloc(h, &l->lo, static_cast<int64_t>(N) * K))) return r;
+  if ((r = dev_alloc(h, &l->bias, N))) return r;
+  if (make_operand_map(&l->m_hi, l->hi, N, K) || make_operand_map(&l->m_lo, l->lo, N, K))
+    return fail(h, -20, "cuTensorMapEncodeTiled failed for a weight operand");
+  return 0;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+int pick_bn(const d3d_handle* h, int64_t M, int N) {
+  int bn = env_int("D3D_GEMM_BN", 0);
+  if (bn == 128 || bn == 256) return (N % bn == 0) ? bn : 128;
+  if (N % 256 != 0) return 128;
+  const int64_t tiles256 = ((M + 127) / 128) * (N / 256);
+  return tiles256 >= 2 * h->num_sms ? 256 : 128;
+}
+
+// out = epilogue(Aop . W^T + bias)
+int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int epi, const float* residual,
+             float* out_f32, __half* out_hi, __half* out_lo, int mode, cudaStream_t st) {
+  GemmParams p;
+  p.M = static_cast<int>(M);
+  p.N = w.N;
+  p.K = w.K;
+  p.bias = w.bias;
+  p.residual = residual;
+  p.out_f32 = out_f32;
+  p.out_hi = out_hi;
+  p.out_lo = out_lo;
+  if (mode == D3D_GEMM_SIMT_FP32) {
+    KL(launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, st));
+  } else {
+    GemmMaps m;
+    m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
+    KL(launch_gemm_tc(m, p, epi, mode == D3D_GEMM_TC_FP16 ? 1 : 3, pick_bn(h, M, w.N), h->num_sms, st));
+  }
+  return 0;
+}
+
+int run_attention(d3d_handle* h, const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, bool spatial,
+                  int mode, cudaStream_t st) {
+  if (spatial) {
+    if (mode == D3D_ATTN_SIMT || h->J != 17)
+      KL(launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, B * h->F, h->J, h->J, 1, 1, st));
+    else
+      KL(launch_attn_spatial(qkv, o_hi, o_lo, o_f32, static_cast<int64_t>(B) * h->F, h->J, st));
+  } else {
+    if (mode == D3D_ATTN_SIMT)
+      KL(launch_attn_temporal_simt(qkv, o_hi, o_lo, o_f32, B, h->F, h->J, st));
+    else
+      KL(launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, B, h->F, h->J, st));
+  }
+  return 0;
+}
+
+int check_weights(d3d_handle* h) {
+  static const char* per_blk[] = {"norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.proj.weight", "attn.proj.bias",
+                                  "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight",
+                                  "mlp.fc2.bias"};
+  std::vector<std::string> need = {"fusion_layer.weight", "fusion_layer.bias", "Spatial_pos_embed", "Temporal_pos_embed",
+                                   "Spatial_norm.weight", "Spatial_norm.bias", "Temporal_norm.weight", "Temporal_norm.bias",
+                                   "head.0.weight", "head.0.bias", "head.1.weight", "head.1.bias"};
+  if (h->cfg.with_time_emb) {
+    need.insert(need.end(), {"time_mlp.1.weight", "time_mlp.1.bias", "time_mlp.3.weight", "time_mlp.3.bias"});
+  }
+  for (int i = 0; i < h->cfg.depth; ++i)
+    for (const char* kind : {"STEblocks.", "TTEblocks."}) {
+      for (const char* s : per_blk) need.push_back(std::string(kind) + std::to_string(i) + "." + s);
+      if (h->cfg.with_time_emb) {
+        need.push_back(std::string(kind) + std::to_string(i) + ".time_mlp.1.weight");
+        need.push_back(std::string(kind) + std::to_string(i) + ".time_mlp.1.bias");
+      }
+    }
+  for (auto& n : need)
+    if (!h->loaded.count(n)) return fail(h, -30, "weights not loaded: missing tensor '" + n + "'");
+  return 0;
+}
+
+// [R] fp32 timesteps (device) -> table [R, nblk, 512]
+int compute_time_table(d3d_handle* h, const float* t_dev, int R, float* table, cudaStream_t st) {
+  KL(launch_sincos(t_dev, R, h->e0, st));
+  KL(launch_small_linear(h->e0, R, kC, h->tm1w, h->tm1b, 2 * kC, 0, h->h1, 2 * kC, st));
+  KL(launch_small_linear(h->h1, R, 2 * kC, h->tm3w, h->tm3b, 2 * kC, 1, h->h2, 2 * kC, st));
+  for (int b = 0; b < h->nblk; ++b)
+    KL(launch_small_linear(h->h2, R, 2 * kC, h->blk[b].tw, h->blk[b].tb, kC, 2, table + b * kC,
+                           static_cast<int64_t>(h->nblk) * kC, st));
+  return 0;
+}
+
+// One denoiser evaluation up to (excluding) the final post-norm + head: leaves the residual stream in h->X.
+int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5, const float* tv, int64_t tv_stride,
+               int B, int n_blocks, cudaStream_t st) {
+  const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  const int gm = h->cfg.gemm_mode, am = h->cfg.attn_mode;
+  int r;
+  KL(launch_lift_ln(x2d, y, x5, h->wf_t, h->bf, h->spos, tv, tv_stride, LnParams{h->blk[0].n1g, h->blk[0].n1b}, h->X,
+                    h->A.hi, h->A.lo, T, h->J, h->F * h->J, st));
+  for (int b = 0; b < n_blocks; ++b) {
+    const Blk& k = h->blk[b];
+    const bool spatial = (b % 2) == 0;
+    if ((r = run_gemm(h, h->A, k.qkv, T, EPI_F32, nullptr, h->QKV, nullptr, nullptr, gm, st))) return r;
+    if ((r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial, am, st))) return r;
+    if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, gm, st))) return r;
+    KL(launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, T, st));
+    if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, gm, st))) return r;
+    if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, gm, st))) return r;
+    if (b + 1 < n_blocks) {
+      const LnParams post = spatial ? LnParams{h->sn_g, h->sn_b} : LnParams{h->tn_g, h->tn_b};
+      const Blk& nx = h->blk[b + 1];
+      KL(launch_postnorm_add_ln(h->X, post, (b + 1 == 1) ? h->tpos : nullptr, tv ? tv + (b + 1) * kC : nullptr,
+                                tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo, T, h->J, h->F, st));
+    }
+  }
+  return 0;
+}
+
+int run_head(d3d_handle* h, const DdimStep& s, float* y, const float* noise, float* out3, float* trace_y,
+             float* trace_x0, int trace_idx, int B, cudaStream_t st) {
+  const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  KL(launch_head_ddim(h->X, LnParams{h->tn_g, h->tn_b}, LnParams{h->hg, h->hb}, h->wh, h->bh, s, y, noise, out3,
+                      trace_y, trace_x0, h->S, trace_idx, T, st));
+  return 0;
+}
+
+int ensure_table(d3d_handle* h, cudaStream_t st) {
+  if (!h->cfg.with_time_emb || h->table_valid) return 0;
+  std::vector<float> tf(h->S);
+  for (int i = 0; i < h->S; ++i) tf[i] = static_cast<float>(h->times[i]);
+  CK(cudaMemcpyAsync(h->t_f32, tf.data(), sizeof(float) * h->S, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));   // tf is a stack vector
+  int r = compute_time_table(h, h->t_f32, h->S, h->tv_steps, st);
+  if (r) return r;
+  h->table_valid = true;
+  return 0;
+}
+
+int run_sampler(d3d_handle* h, int B, float* trace_y, float* trace_x0, cudaStream_t st) {
+  const int64_t n3 = static_cast<int64_t>(B) * h->F * h->J * 3;
+  for (int s = 0; s < h->S; ++s) {
+    const float* tv = h->cfg.with_time_emb ? h->tv_steps + static_cast<int64_t>(s) * h->nblk * kC : nullptr;
+    int r = run_blocks(h, h->in_x2d, h->y, nullptr, tv, 0, B, h->nblk, st);
+    if (r) return r;
+    const float* nz = (h->need_noise && !h->steps[s].last) ? h->in_noise + static_cast<int64_t>(s) * n3 : nullptr;
+    if ((r = run_head(h, h->steps[s], h->y, nz, nullptr, trace_y, trace_x0, s, B, st))) return r;
+  }
+  return 0;
+}
+
+void drop_graphs(d3d_handle* h) {
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
+  h->graphs.clear();
+  h->graph_launches.clear();
+}
+
+int check_ready(d3d_handle* h, int B) {
+  if (!h) return -1;
+  if (B < 1 || B > h->cfg.max_clips) return fail(h, -2, "B out of range [1, max_clips]");
+  return check_weights(h);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int d3d_abi_version(void) { return D3D_ABI_VERSION; }
+
+const char* d3d_last_error(const d3d_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t d3d_launch_count(const d3d_handle* h) { return h ? h->launches : 0; }
+
+int d3d_create(const d3d_config* cfg, d3d_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return -1; }
+  *out = nullptr;
+  if (cfg->embed_dim != kC || cfg->num_heads != kHeads || cfg->mlp_hidden != kHidden) {
+    g_create_error = "unsupported shape: kernels are specialised for embed_dim 512, 8 heads, mlp hidden 1024";
+    return -3;
+  }
+  if (cfg->num_frame < 1 || cfg->num_frame > 256 || cfg->num_joints < 1 || cfg->num_joints > 32 || cfg->depth < 1 ||
+      cfg->depth > 64 || cfg->max_clips < 1) {
+    g_create_error = "unsupported shape: need 1<=F<=256, 1<=J<=32, 1<=depth<=64, max_clips>=1";
+    return -3;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+    return e != cudaSuccess ? static_cast<int>(e) : -4;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return -2; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) {
+    g_create_error = "device is not sm_100 (Blackwell B200); this library is sm_100a-only";
+    return -5;
+  }
+  DeviceGuard guard(cfg->device);
+  d3d_handle* h = new d3d_handle();
+  h->cfg = *cfg;
+  h->F = cfg->num_frame;
+  h->J = cfg->num_joints;
+  h->nblk = 2 * cfg->depth;
+  h->num_sms = prop.multiProcessorCount;
+  h->blk.resize(h->nblk);
+  const int64_t T = static_cast<int64_t>(cfg->max_clips) * h->F * h->J;
+  h->tok_cap = (T + 127) / 128 * 128;
+
+  auto body = [&]() -> int {
+    int r;
+    CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CK(configure_gemm_tc());
+    CK(configure_attention());
+    CK(configure_attention_mma());
+    for (auto& b : h->blk) {
+      if ((r = alloc_lin(h, &b.qkv, 3 * kC, kC))) return r;
+      if ((r = alloc_lin(h, &b.proj, kC, kC))) return r;
+      if ((r = alloc_lin(h, &b.fc1, kHidden, kC))) return r;
+      if ((r = alloc_lin(h, &b.fc2, kC, kHidden))) return r;
+      for (float** p : {&b.n1g, &b.n1b, &b.n2g, &b.n2b, &b.tb})
+        if ((r = dev_alloc(h, p, kC))) return r;
+      if ((r = dev_alloc(h, &b.tw, static_cast<int64_t>(kC) * 2 * kC))) return r;
+    }
+    for (float** p : {&h->bf, &h->sn_g, &h->sn_b, &h->tn_g, &h->tn_b, &h->hg, &h->hb})
+      if ((r = dev_alloc(h, p, kC))) return r;
+    if ((r = dev_alloc(h, &h->wf_t, 5 * kC))) return r;
+    if ((r = dev_alloc(h, &h->spos, static_cast<int64_t>(h->J) * kC))) return r;
+    if ((r = dev_alloc(h, &h->tpos, static_cast<int64_t>(h->F) * kC))) return r;
+    if ((r = dev_alloc(h, &h->wh, 3 * kC))) return r;
+    if ((r = dev_alloc(h, &h->bh, 4))) return r;
+    if ((r = dev_alloc(h, &h->tm1w, static_cast<int64_t>(2 * kC) * kC))) return r;
+    if ((r = dev_alloc(h, &h->tm1b, 2 * kC))) return r;
+    if ((r = dev_alloc(h, &h->tm3w, static_cast<int64_t>(2 * kC) * 2 * kC))) return r;
+    if ((r = dev_alloc(h, &h->tm3b, 2 * kC))) return r;
+    if ((r = dev_alloc(h, &h->perm_dev, 64))) return r;
+
+    if ((r = dev_alloc(h, &h->X, h->tok_cap * kC))) return r;
+    if ((r = dev_alloc(h, &h->QKV, h->tok_cap * 3 * kC))) return r;
+    if ((r = alloc_operand(h, &h->A, h->tok_cap, kC))) return r;
+    if ((r = alloc_operand(h, &h->ATT, h->tok_cap, kC))) return r;
+    if ((r = alloc_operand(h, &h->H, h->tok_cap, kHidden))) return r;
+    if ((r = dev_alloc(h, &h->in_x2d, T * 2))) return r;
+    if ((r = dev_alloc(h, &h->y, T * 3))) return r;
+    h->t_rows_cap = cfg->max_clips > 1024 ? cfg->max_clips : 1024;
+    if ((r = dev_alloc(h, &h->t_f32, h->t_rows_cap))) return r;
+    if ((r = dev_alloc(h, &h->e0, static_cast<int64_t>(h->t_rows_cap) * kC))) return r;
+    if ((r = dev_alloc(h, &h->h1, static_cast<int64_t>(h->t_rows_cap) * 2 * kC))) return r;
+    if ((r = dev_alloc(h, &h->h2, static_cast<int64_t>(h->t_rows_cap) * 2 * kC))) return r;
+    if ((r = dev_alloc(h, &h->tv_general, static_cast<int64_t>(cfg->max_clips) * h->nblk * kC))) return r;
+    CK(cudaDeviceSynchronize());
+    return 0;
+  };
+  int r = body();
+  if (r) {
+    g_create_error = h->err;
+    d3d_destroy(h);
+    return r;
+  }
+  *out = h;
+  return 0;
+}
+
+void d3d_destroy(d3d_handle* h) {
+  if (!h) return;
+  DeviceGuard guard(h->cfg.device);
+  cudaDeviceSynchronize();
+  drop_graphs(h);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  delete h;
+}
+
+int d3d_load_weights(d3d_handle* h, const d3d_tensor* tensors, int32_t n) {
+  if (!h || !tensors) return -1;
+  DeviceGuard guard(h->cfg.device);
+  drop_graphs(h);
+  h->table_valid = false;
+  float* stage = nullptr;   // device staging for tensors that need a transform
+  const int64_t stage_cap = static_cast<int64_t>(3 * kC) * kHidden;
+  CK(cudaMalloc(&stage, stage_cap * sizeof(float)));
+  struct Free { float* p; ~Free() { cudaFree(p); } } free_stage{stage};
+
+  auto copy_to = [&](float* dst, const d3d_tensor& t, int64_t expect) -> int {
+    if (t.numel != expect)
+      return fail(h, -10, std::string("tensor '") + t.name + "' has " + std::to_string(t.numel) + " elements, expected " +
+                              std::to_string(expect));
+    CK(cudaMemcpy(dst, t.data, expect * sizeof(float), t.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return 0;
+  };
+  auto load_lin_w = [&](Lin& l, const d3d_tensor& t) -> int {
+    int r = copy_to(stage, t, static_cast<int64_t>(l.N) * l.K);
+    if (r) return r;
+    CK(launch_split(stage, l.hi, l.lo, static_cast<int64_t>(l.N) * l.K, 0));
+    CK(cudaDeviceSynchronize());
+    l.have_w = true;
+    return 0;
+  };
+
+  for (int i = 0; i < n; ++i) {
+    const d3d_tensor& t = tensors[i];
+    if (!t.name || !t.data) return fail(h, -1, "null tensor name/data");
+    std::string name = t.name;
+    if (name.rfind("module.", 0) == 0) name = name.substr(7);
+    if (name.rfind("model.", 0) == 0) name = name.substr(6);
+    int r = 0;
+    if (name == "fusion_layer.weight") {           // [512,5] -> transposed [5][512]
+      std::vector<float> w(5 * kC), wt(5 * kC);
+      if (t.numel != 5 * kC) return fail(h, -10, "fusion_layer.weight must be [512,5]");
+      CK(cudaMemcpy(w.data(), t.data, sizeof(float) * 5 * kC, t.on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+      for (int c = 0; c < kC; ++c)
+        for (int k = 0; k < 5; ++k) wt[k * kC + c] = w[c * 5 + k];
+      CK(cudaMemcpy(h->wf_t, wt.data(), sizeof(float) * 5 * kC, cudaMemcpyHostToDevice));
+    } else if (name == "fusion_layer.bias") r = copy_to(h->bf, t, kC);
+    else if (name == "Spatial_pos_embed") r = copy_to(h->spos, t, static_cast<int64_t>(h->J) * kC);
+    else if (name == "Temporal_pos_embed") r = copy_to(h->tpos, t, static_cast<int64_t>(h->F) * kC);
+    else if (name == "Spatial_norm.weight") r = copy_to(h->sn_g, t, kC);
+    else if (name == "Spatial_norm.bias") r = copy_to(h->sn_b, t, kC);
+    else if (name == "Temporal_norm.weight") r = copy_to(h->tn_g, t, kC);
+    else if (name == "Temporal_norm.bias") r = copy_to(h->tn_b, t, kC);
+    else if (name == "head.0.weight") r = copy_to(h->hg, t, kC);
+    else if (name == "head.0.bias") r = copy_to(h->hb, t, kC);
+    else if (name == "head.1.weight") r = copy_to(h->wh, t, 3 * kC);
+    else if (name == "head.1.bias") r = copy_to(h->bh, t, 3);
+    else if (name == "time_mlp.1.weight") r = copy_to(h->tm1w, t, static_cast<int64_t>(2 * kC) * kC);
+    else if (name == "time_mlp.1.bias") r = copy_to(h->tm1b, t, 2 * kC);
+    else if (name == "time_mlp.3.weight") r = copy_to(h->tm3w, t, static_cast<int64_t>(2 * kC) * 2 * kC);
+    else if (name == "time_mlp.3.bias") r = copy_to(h->tm3b, t, 2 * kC);
+    else if (name.rfind("STEblocks.", 0) == 0 || name.rfind("TTEblocks.", 0) == 0) {
+      const bool spatial = name[0] == 'S';
+      const size_t dot = name.find('.', 10);
+      if (dot == std::string::npos) return fail(h, -11, "unknown tensor '" + name + "'");
+      const int idx = atoi(name.substr(10, dot - 10).c_str());
+      if (idx < 0 || idx >= h->cfg.depth) return fail(h, -11, "block index out of range in '" + name + "'");
+      Blk& b = h->blk[2 * idx + (spatial ? 0 : 1)];
+      const std::string sub = name.substr(dot + 1);
+      if (sub == "norm1.weight") r = copy_to(b.n1g, t, kC);
+      else if (sub == "norm1.bias") r = copy_to(b.n1b, t, kC);
+      else if (sub == "norm2.weight") r = copy_to(b.n2g, t, kC);
+      else if (sub == "norm2.bias") r = copy_to(b.n2b, t, kC);
+      else if (sub == "attn.qkv.weight") r = load_lin_w(b.qkv, t);
+      else if (sub == "attn.qkv.bias") r = copy_to(b.qkv.bias, t, 3 * kC);
+      else if (sub == "attn.proj.weight") r = load_lin_w(b.proj, t);
+      else if (sub == "attn.proj.bias") r = copy_to(b.proj.bias, t, kC);
+      else if (sub == "mlp.fc1.weight") r = load_lin_w(b.fc1, t);
+      else if (sub == "mlp.fc1.bias") r = copy_to(b.fc1.bias, t, kHidden);
+      else if (sub == "mlp.fc2.weight") r = load_lin_w(b.fc2, t);
+      else if (sub == "mlp.fc2.bias") r = copy_to(b.fc2.bias, t, kC);
+      else if (sub == "time_mlp.1.weight") r = copy_to(b.tw, t, static_cast<int64_t>(kC) * 2 * kC);
+      else if (sub == "time_mlp.1.bias") r = copy_to(b.tb, t, kC);
+      else return fail(h, -11, "unknown tensor '" + name + "'");
+    } else {
+      return fail(h, -11, "unknown tensor '" + name + "'");
+    }
+    if (r) return r;
+    h->loaded[name] = true;
+  }
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int d3d_set_schedule(d3d_handle* h, int32_t S, const int32_t* times, const float* ac, const float* s1m, int32_t T,
+                     float eta, int32_t clip_denoised) {
+  if (!h || !times || !ac || !s1m) return -1;
+  if (S < 1 || S > 1024) return fail(h, -2, "sampling_timesteps out of range [1,1024]");
+  DeviceGuard guard(h->cfg.device);
+  drop_graphs(h);
+  h->table_valid = false;
+  h->S = S;
+  h->times.assign(times, times + S + 1);
+  h->steps.resize(S);
+  h->need_noise = false;
+  for (int i = 0; i < S; ++i) {
+    const int t = times[i], tn = times[i + 1];
+    if (t < 0 || t >= T || tn >= T) return fail(h, -2, "time index outside the schedule buffers");
+    DdimStep s{};
+    s.clip = clip_denoised ? 1 : 0;
+    if (tn < 0) {
+      s.last = 1;                                   // DIFF:283-285
+    } else {
+      // DIFF:287-292 evaluated in fp32, one rounding per op as torch does on 0-dim fp32 tensors
+      const volatile float alpha = ac[t], alpha_next = ac[tn];
+      volatile float q = alpha / alpha_next;
+      volatile float a1 = 1.0f - q;
+      volatile float a2 = 1.0f - alpha_next;
+      volatile float a3 = a1 * a2;
+      volatile float a4 = 1.0f - alpha;
+      volatile float a5 = a3 / a4;
+      volatile float sig = eta * sqrtf(a5);
+      volatile float s2 = sig * sig;
+      volatile float c0 = a2 - s2;
+      s.sigma = sig;
+      s.c = sqrtf(c0);
+      s.alpha = alpha;
+      s.sqrt_alpha_next = sqrtf(alpha_next);
+      s.sqrt_one_minus = s1m[t];
+      if (s.sigma != 0.0f) h->need_noise = true;
+    }
+    h->steps[i] = s;
+  }
+  if (S > h->tv_cap) {
+    int r = dev_alloc(h, &h->tv_steps, static_cast<int64_t>(S) * h->nblk * kC);
+    if (r) return r;
+    h->tv_cap = S;
+  }
+  if (S > h->t_rows_cap) return fail(h, -2, "sampling_timesteps exceeds the time-MLP scratch rows");
+  h->have_schedule = true;
+  return 0;
+}
+
+int d3d_forward_denoise(d3d_handle* h, const float* x5, const int64_t* t_dev, float* out3, int32_t B, void* stream) {
+  int r = check_ready(h, B);
+  if (r) return r;
+  if (!x5 || !out3 || (h->cfg.with_time_emb && !t_dev)) return fail(h, -1, "null argument");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* tv = nullptr;
+  if (h->cfg.with_time_emb) {
+    // per-sample t: int64 -> fp32 on the host side of the stream (B values), then the general table
+    std::vector<int64_t> ti(B);
+    CK(cudaMemcpyAsync(ti.data(), t_dev, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<float> tf(B);
+    for (int i = 0; i < B; ++i) tf[i] = static_cast<float>(ti[i]);
+    CK(cudaMemcpyAsync(h->t_f32, tf.data(), sizeof(float) * B, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    if ((r = compute_time_table(h, h->t_f32, B, h->tv_general, st))) return r;
+    tv = h->tv_general;
+  }
+  if ((r = run_blocks(h, nullptr, nullptr, x5, tv, static_cast<int64_t>(h->nblk) * kC, B, h->nblk, st))) return r;
+  DdimStep s{};
+  return run_head(h, s, nullptr, nullptr, out3, nullptr, nullptr, 0, B, st);
+}
+
+int d3d_debug_forward_blocks(d3d_handle* h, const float* x5, const int64_t* t_dev, int32_t B, int32_t n_blocks,
+                             float* x_out, void* stream) {
+  int r = check_ready(h, B);
+  if (r) return r;
+  if (n_blocks < 0 || n_blocks > h->nblk) return fail(h, -2, "n_blocks out of range");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* tv = nullptr;
+  if (h->cfg.with_time_emb) {
+    std::vector<int64_t> ti(B);
+    CK(cudaMemcpyAsync(ti.data(), t_dev, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<float> tf(B);
+    for (int i = 0; i < B; ++i) tf[i] = static_cast<float>(ti[i]);
+    CK(cudaMemcpyAsync(h->t_f32, tf.data(), sizeof(float) * B, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    if ((r = compute_time_table(h, h->t_f32, B, h->tv_general, st))) return r;
+    tv = h->tv_general;
+  }
+  if ((r = run_blocks(h, nullptr, nullptr, x5, tv, static_cast<int64_t>(h->nblk) * kC, B, n_blocks, st))) return r;
+  const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  CK(cudaMemcpyAsync(x_out, h->X, sizeof(float) * T * kC, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int sample_on_device(d3d_handle* h, int B, float* trace_y, float* trace_x0, cudaStream_t st) {
+  int r = ensure_table(h, st);
+  if (r) return r;
+  const bool tracing = trace_y || trace_x0;
+  if (!h->cfg.use_graph || tracing) return run_sampler(h, B, trace_y, trace_x0, st);
+  auto it = h->graphs.find(B);
+  if (it == h->graphs.end()) {
+    const int64_t before = h->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    r = run_sampler(h, B, nullptr, nullptr, h->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    const int64_t n_kernels = h->launches - before;
+    h->launches = before;
+    if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+    CK(e);
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CK(e);
+    h->graphs[B] = exec;
+    h->graph_launches[B] = n_kernels;
+    it = h->graphs.find(B);
+  }
+  CK(cudaGraphLaunch(it->second, st));
+  h->launches += h->graph_launches[B];
+  return 0;
+}
+
+static int ensure_noise_buf(d3d_handle* h, int B) {
+  const int64_t need = static_cast<int64_t>(h->S - 1) * B * h->F * h->J * 3;
+  if (need > h->in_noise_cap) {
+    drop_graphs(h);
+    int r = dev_alloc(h, &h->in_noise, need, false);
+    if (r) return r;
+    h->in_noise_cap = need;
+  }
+  return 0;
+}
+
+int d3d_ddim_sample(d3d_handle* h, const float* x2d, const float* noise0, const float* step_noise, float* y0,
+                    float* trace_y, float* trace_x0, int32_t B, void* stream) {
+  int r = check_ready(h, B);
+  if (r) return r;
+  if (!h->have_schedule) return fail(h, -31, "d3d_set_schedule has not been called");
+  if (!x2d || !noise0 || !y0) return fail(h, -1, "null argument");
+  if (h->need_noise && !step_noise && h->S > 1) return fail(h, -1, "eta != 0 requires step_noise");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  CK(cudaMemcpyAsync(h->in_x2d, x2d, sizeof(float) * T * 2, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(h->y, noise0, sizeof(float) * T * 3, cudaMemcpyDeviceToDevice, st));
+  if (h->need_noise && h->S > 1) {
+    if ((r = ensure_noise_buf(h, B))) return r;
+    CK(cudaMemcpyAsync(h->in_noise, step_noise, sizeof(float) * T * 3 * (h->S - 1), cudaMemcpyDeviceToDevice, st));
+  }
+  if ((r = sample_on_device(h, B, trace_y, trace_x0, st))) return r;
+  CK(cudaMemcpyAsync(y0, h->y, sizeof(float) * T * 3, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int d3d_ddim_sample_host(d3d_handle* h, const float* x2d, const float* noise0, const float* step_noise, float* y0,
+                         int32_t B, void* stream) {
+  int r = check_ready(h, B);
+  if (r) return r;
+  if (!h->have_schedule) return fail(h, -31, "d3d_set_schedule has not been called");
+  if (!x2d || !noise0 || !y0) return fail(h, -1, "null argument");
+  if (h->need_noise && !step_noise && h->S > 1) return fail(h, -1, "eta != 0 requires step_noise");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  CK(cudaMemcpyAsync(h->in_x2d, x2d, sizeof(float) * T * 2, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->y, noise0, sizeof(float) * T * 3, cudaMemcpyHostToDevice, st));
+  if (h->need_noise && h->S > 1) {
+    if ((r = ensure_noise_buf(h, B))) return r;
+    CK(cudaMemcpyAsync(h->in_noise, step_noise, sizeof(float) * T * 3 * (h->S - 1), cudaMemcpyHostToDevice, st));
+  }
+  if ((r = sample_on_device(h, B, nullptr, nullptr, st))) return r;
+  CK(cudaMemcpyAsync(y0, h->y, sizeof(float) * T * 3, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int d3d_tta_merge(d3d_handle* h, const float* y, const float* yf, const int32_t* left, const int32_t* right,
+                  int32_t n_lr, float scale, float* out, int64_t n_frames, void* stream) {
+  if (!h || !y || !yf || !out) return -1;
+  if (n_lr < 0 || n_lr > 16 || (n_lr > 0 && (!left || !right))) return fail(h, -2, "bad joint lists");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int32_t perm[64];
+  for (int j = 0; j < 64; ++j) perm[j] = j;
+  for (int i = 0; i < n_lr; ++i) {
+    if (left[i] < 0 || left[i] >= h->J || right[i] < 0 || right[i] >= h->J) return fail(h, -2, "joint index out of range");
+    perm[left[i]] = right[i];      // new[left] = old[right]  (RUN:584-585)
+    perm[right[i]] = left[i];
+  }
+  CK(cudaMemcpyAsync(h->perm_dev, perm, sizeof(perm), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  KL(launch_tta_merge(y, yf, h->perm_dev, scale, out, n_frames, h->J, st));
+  return 0;
+}
+
+int d3d_mpjpe_accumulate(d3d_handle* h, const float* pred, const float* gt, const uint8_t* mask, int64_t n_frames,
+                         double* acc, void* stream) {
+  if (!h || !pred || !gt || !acc) return -1;
+  DeviceGuard guard(h->cfg.device);
+  KL(launch_mpjpe(pred, gt, mask, n_frames, h->J, acc, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ kernel-level entry points
+int d3d_op_layernorm(d3d_handle* h, const float* x, const float* gamma, const float* beta, float eps, float* out,
+                     int64_t rows, void* stream) {
+  if (!h || !x || !gamma || !beta || !out) return -1;
+  DeviceGuard guard(h->cfg.device);
+  KL(launch_ln_f32(x, LnParams{gamma, beta}, eps, out, rows, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int d3d_op_attention(d3d_handle* h, const float* qkv, float* out, int32_t B, int32_t spatial, int32_t attn_mode,
+                     void* stream) {
+  if (!h || !qkv || !out) return -1;
+  if (B < 1) return fail(h, -2, "B < 1");
+  DeviceGuard guard(h->cfg.device);
+  return run_attention(h, qkv, nullptr, nullptr, out, B, spatial != 0, attn_mode, static_cast<cudaStream_t>(stream));
+}
+
+int d3d_op_time_table(d3d_handle* h, const float* t_host, int32_t R, float* out, void* stream) {
+  if (!h || !t_host || !out) return -1;
+  if (!h->cfg.with_time_emb) return fail(h, -3, "handle was created with with_time_emb = 0");
+  if (R < 1 || R > h->t_rows_cap) return fail(h, -2, "R out of range");
+  int r = check_weights(h);
+  if (r) return r;
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaMemcpyAsync(h->t_f32, t_host, sizeof(float) * R, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  return compute_time_table(h, h->t_f32, R, out, st);
+}
+
+}  // extern "C"
+
+namespace {
+struct OpLinearBufs {
+  OperandBuf a;
+  Lin w;
+  __half *o_hi = nullptr, *o_lo = nullptr;
+  std::vector<void*> mine;
+  ~OpLinearBufs() { for (void* p : mine) cudaFree(p); }
+};
+template <typename T>
+cudaError_t tmp_alloc(OpLinearBufs& b, T** p, int64_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, static_cast<size_t>(n) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(q, 0, static_cast<size_t>(n) * sizeof(T));
+  b.mine.push_back(q);
+  *p = static_cast<T*>(q);
+  return e;
+}
+int prep_op_linear(d3d_handle* h, OpLinearBufs& b, int64_t M, int N, int K, int act) {
+  const int64_t Mp = (M + 127) / 128 * 128;
+  CK(tmp_alloc(b, &b.a.hi, Mp * K));
+  CK(tmp_alloc(b, &b.a.lo, Mp * K));
+  CK(tmp_alloc(b, &b.w.hi, static_cast<int64_t>(N) * K));
+  CK(tmp_alloc(b, &b.w.lo, static_cast<int64_t>(N) * K));
+  b.w.N = N;
+  b.w.K = K;
+  if (act) {
+    CK(tmp_alloc(b, &b.o_hi, M * N));
+    CK(tmp_alloc(b, &b.o_lo, M * N));
+  }
+  if (make_operand_map(&b.a.m_hi, b.a.hi, Mp, K) || make_operand_map(&b.a.m_lo, b.a.lo, Mp, K) ||
+      make_operand_map(&b.w.m_hi, b.w.hi, N, K) || make_operand_map(&b.w.m_lo, b.w.lo, N, K))
+    return fail(h, -20, "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int d3d_op_linear(d3d_handle* h, const float* a, const float* w, const float* bias, const float* residual, float* out,
+                  int64_t M, int32_t N, int32_t K, int32_t act, int32_t gemm_mode, void* stream) {
+  if (!h || !a || !w || !bias || !out) return -1;
+  if (M < 1 || N % 128 != 0 || K % 64 != 0 || N < 128 || K < 64) return fail(h, -2, "need M>=1, N%128==0, K%64==0");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  OpLinearBufs b;
+  int r = prep_op_linear(h, b, M, N, K, act);
+  if (r) return r;
+  b.w.bias = const_cast<float*>(bias);
+  KL(launch_split(a, b.a.hi, b.a.lo, M * K, st));
+  KL(launch_split(w, b.w.hi, b.w.lo, static_cast<int64_t>(N) * K, st));
+  if (act) {
+    if ((r = run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, gemm_mode, st))) return r;
+    KL(launch_merge(b.o_hi, b.o_lo, out, M * N, st));
+  } else {
+    if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, out, nullptr, nullptr, gemm_mode, st))) return r;
+  }
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int d3d_op_linear_bench(d3d_handle* h, int64_t M, int32_t N, int32_t K, int32_t act, int32_t gemm_mode, int32_t iters,
+                        float* ms_per_launch) {
+  if (!h || !ms_per_launch || iters < 1) return -1;
+  if (M < 1 || N % 128 != 0 || K % 64 != 0) return fail(h, -2, "need M>=1, N%128==0, K%64==0");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = h->cap_stream;
+  OpLinearBufs b;
+  int r = prep_op_linear(h, b, M, N, K, act);
+  if (r) return r;
+  float *fa = nullptr, *fo = nullptr, *fb = nullptr;
+  CK(tmp_alloc(b, &fa, M * K > static_cast<int64_t>(N) * K ? M * K : static_cast<int64_t>(N) * K));
+  CK(tmp_alloc(b, &fo, M * N));
+  CK(tmp_alloc(b, &fb, N));
+  b.w.bias = fb;
+  // deterministic non-trivial operands: a 0.01-step ramp pattern split into halves
+  std::vector<float> host(1 << 20);
+  for (size_t i = 0; i < host.size(); ++i) host[i] = static_cast<float>(static_cast<int>((i * 2654435761u) >> 20 & 1023) - 512) * (1.0f / 512.0f);
+  const int64_t na = M * K;
+  for (int64_t off = 0; off < na; off += static_cast<int64_t>(host.size()))
+    CK(cudaMemcpy(fa + off, host.data(), sizeof(float) * static_cast<size_t>(std::min<int64_t>(host.size(), na - off)), cudaMemcpyHostToDevice));
+  CK(launch_split(fa, b.a.hi, b.a.lo, na, st));
+  CK(launch_split(fa, b.w.hi, b.w.lo, static_cast<int64_t>(N) * K, st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  auto once = [&]() -> int {
+    if (act) return run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, gemm_mode, st);
+    return run_gemm(h, b.a, b.w, M, EPI_F32, nullptr, fo, nullptr, nullptr, gemm_mode, st);
+  };
+  for (int i = 0; i < 3; ++i)
+    if ((r = once())) return r;
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i)
+    if ((r = once())) return r;
+  CK(cudaEventRecord(e1, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / iters;
+  return 0;
+}
+
+}  // extern "C"

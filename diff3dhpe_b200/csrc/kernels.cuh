@@ -1,0 +1,103 @@
+// Launcher declarations shared by the engine and the kernel translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace d3d {
+
+constexpr int kC = 512;        // embed_dim the kernels are specialised for
+constexpr int kHeads = 8;      // heads
+constexpr int kHd = 64;        // head_dim
+constexpr int kHidden = 1024;  // mlp hidden
+
+// ------------------------------------------------------------------ GEMM
+enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1 };
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;      // [N] (never null)
+  const float* residual;  // [M,N] or null; may alias out_f32
+  float* out_f32;         // EPI_F32
+  __half* out_hi;         // EPI_GELU_SPLIT
+  __half* out_lo;
+};
+
+// A: [M,K] fp16 (hi, lo), W: [N,K] fp16 (hi, lo); K-major.  Tensor maps use a {64, 128} box, SWIZZLE_128B.
+struct GemmMaps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+// passes: 3 (split) or 1 (fp16).  bn: 128 or 256 (N % bn == 0).
+cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int num_sms,
+                           cudaStream_t st);
+cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
+                             const GemmParams& p, int epi, cudaStream_t st);
+// One-time per-device kernel attribute setup (dynamic shared memory opt-in); call outside graph capture.
+cudaError_t configure_gemm_tc();
+cudaError_t configure_attention();
+cudaError_t configure_attention_mma();
+// Build a K-major fp16 operand map for a [rows, K] row-major matrix.
+int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t K);
+
+// ------------------------------------------------------------------ row-wise (one warp per 512-wide token row)
+struct LnParams {
+  const float* gamma;
+  const float* beta;
+};
+
+// fp32 -> fp16 hi/lo split of a flat array (weights at load time, op-level tests).
+cudaError_t launch_split(const float* in, __half* hi, __half* lo, int64_t n, cudaStream_t st);
+cudaError_t launch_merge(const __half* hi, const __half* lo, float* out, int64_t n, cudaStream_t st);
+
+// X = [x2d,y] . Wf^T + bf + spos[j] (+ tvec[sample]);  A = LN(X; ln1)  (MODEL:250, 230-233, 113-116, 127)
+cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, const float* wf_t /*[5][512]*/,
+                           const float* bf, const float* spos /*[J][512]*/, const float* tvec, int64_t tvec_stride,
+                           LnParams ln1, float* X, __half* a_hi, __half* a_lo, int64_t T, int J, int tokens_per_clip,
+                           cudaStream_t st);
+// X = LN(X; post) (+ tpos[f]) (+ tvec[sample]);  A = LN(X; ln1)   (MODEL:236/245, 239-242, 113-116, 127)
+cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos /*[F][512] or null*/,
+                                   const float* tvec, int64_t tvec_stride, LnParams ln1, __half* a_hi,
+                                   __half* a_lo, int64_t T, int J, int F, cudaStream_t st);
+// A = LN(X; ln)  (MODEL:128 norm2)
+cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int64_t T,
+                            cudaStream_t st);
+// out = LN(x) fp32 (stand-alone exhibit / op test)
+cudaError_t launch_ln_f32(const float* x, LnParams ln, float eps, float* out, int64_t T, cudaStream_t st);
+
+struct DdimStep {      // DIFF:287-297 scalars; last != 0 -> y_next = x0 (DIFF:283-285)
+  float sqrt_alpha_next, c, alpha, sqrt_one_minus, sigma;
+  int last, clip;
+};
+// x0 = head(LN(LN(X; post, 1e-6); head.0, 1e-5)); clamp; DDIM update.  (MODEL:245,255; DIFF:256,287-297)
+// If out3 != null only x0 is written there (forward_denoise); else y is updated in place.
+cudaError_t launch_head_ddim(const float* X, LnParams post, LnParams head_ln, const float* wh /*[3][512]*/,
+                             const float* bh, DdimStep s, float* y, const float* noise, float* out3,
+                             float* trace_y, float* trace_x0, int trace_stride, int trace_idx, int64_t T,
+                             cudaStream_t st);
+
+cudaError_t launch_tta_merge(const float* y, const float* yf, const int32_t* perm /*[J] device*/, float scale,
+                             float* out, int64_t n_frames, int J, cudaStream_t st);
+cudaError_t launch_mpjpe(const float* pred, const float* gt, const uint8_t* mask, int64_t n_frames, int J,
+                         double* acc, cudaStream_t st);
+
+// ------------------------------------------------------------------ attention
+cudaError_t launch_attn_spatial(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int64_t n_groups,
+                                int J, cudaStream_t st);
+cudaError_t launch_attn_temporal_simt(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F,
+                                      int J, cudaStream_t st);
+cudaError_t launch_attn_temporal_mma(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F,
+                                     int J, cudaStream_t st);
+cudaError_t launch_attn_generic_simt(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int n_seq,
+                                     int N, int64_t seq_stride_tokens_outer, int inner, int64_t tok_stride,
+                                     cudaStream_t st);
+
+// ------------------------------------------------------------------ time embedding
+// e[r, 0:256] = sin(t_r * f_i), e[r, 256:512] = cos(t_r * f_i)   (MODEL:29-36)
+cudaError_t launch_sincos(const float* t, int R, float* out, cudaStream_t st);
+// out[r, n] = act_in(in[r, :]) . W[n, :] + b[n];  act_in: 0 none, 1 gelu(erf), 2 silu.  out row stride given.
+cudaError_t launch_small_linear(const float* in, int R, int K, const float* W, const float* b, int N, int act_in,
+                                float* out, int64_t out_row_stride, cudaStream_t st);
+
+}  // namespace d3d

@@ -1,0 +1,213 @@
+"""`Engine`: a thin Python owner of one d3d_handle.  PyTorch is used here only for device memory and
+streams; every computation is a call through the C ABI (include/diff3d_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _check_dev(t: torch.Tensor, device: torch.device, shape=None, dtype=torch.float32, name="tensor"):
+    if not t.is_cuda or t.device != device:
+        raise ValueError(f"{name} must live on {device}, got {t.device}")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+class Engine:
+    """One handle = one device, one (F, J, depth, with_time_emb) model, workspace for `max_clips` clips."""
+
+    def __init__(self, num_frame: int, num_joints: int = 17, embed_dim: int = 512, depth: int = 8, num_heads: int = 8,
+                 mlp_hidden: int = 1024, with_time_emb: bool = True, max_clips: int = 1, device=None,
+                 gemm_mode: int = _lib.GEMM_TC_SPLIT3, attn_mode: int = _lib.ATTN_DEFAULT, use_graph: bool = True):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("diff3dhpe_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.F, self.J, self.C, self.depth = num_frame, num_joints, embed_dim, depth
+        self.with_time_emb = bool(with_time_emb)
+        self.max_clips = max_clips
+        self.S = 0
+        cfg = _lib.Config(num_frame, num_joints, embed_dim, depth, num_heads, mlp_hidden, int(with_time_emb), max_clips,
+                          gemm_mode, attn_mode, self.device.index, int(use_graph))
+        h = C.c_void_p()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            rc = self.lib.d3d_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"d3d_create failed (code {rc}): {_lib.last_error(None)}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.d3d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ weights / schedule
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """Accepts the reference's keys, with or without 'module.' / 'model.' prefixes; schedule buffers
+        (top-level keys such as 'alphas_cumprod') are skipped as RUN:226-235 does."""
+        keep, descs = [], []
+        for k, v in sd.items():
+            name = k
+            if name.startswith("module."):
+                name = name[7:]
+            if name.startswith("model."):
+                name = name[6:]
+            elif "." not in name and name not in ("Spatial_pos_embed", "Temporal_pos_embed"):
+                continue                      # GaussianDiffusion buffers
+            t = v.detach().to(dtype=torch.float32).contiguous()
+            keep.append((name.encode(), t))
+        arr = (_lib.TensorDesc * len(keep))()
+        for i, (name, t) in enumerate(keep):
+            arr[i].name = name
+            arr[i].data = t.data_ptr()
+            arr[i].numel = t.numel()
+            arr[i].on_device = 1 if (t.is_cuda and t.device == self.device) else 0
+            if t.is_cuda and t.device != self.device:
+                keep[i] = (name, t.cpu())
+                arr[i].data = keep[i][1].data_ptr()
+        if any(t.is_cuda for _, t in keep):
+            torch.cuda.synchronize(self.device)
+        _lib.check(self.lib.d3d_load_weights(self.h, arr, len(keep)), self.h, "d3d_load_weights")
+
+    def set_schedule(self, times: Sequence[int], alphas_cumprod: torch.Tensor, sqrt_one_minus: torch.Tensor,
+                     eta: float, clip_denoised: bool):
+        S = len(times) - 1
+        ac = alphas_cumprod.detach().to("cpu", torch.float32).contiguous()
+        s1m = sqrt_one_minus.detach().to("cpu", torch.float32).contiguous()
+        tarr = (C.c_int32 * (S + 1))(*[int(t) for t in times])
+        _lib.check(self.lib.d3d_set_schedule(self.h, S, tarr, C.cast(ac.data_ptr(), C.POINTER(C.c_float)),
+                                             C.cast(s1m.data_ptr(), C.POINTER(C.c_float)), ac.numel(), float(eta),
+                                             int(bool(clip_denoised))), self.h, "d3d_set_schedule")
+        self.S = S
+
+    # ------------------------------------------------------------------ hot path
+    def forward_denoise(self, x5: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        B = x5.shape[0]
+        _check_dev(x5, self.device, (B, self.F, self.J, 5), name="x")
+        t = t.to(device=self.device, dtype=torch.int64).contiguous()
+        if t.numel() != B:
+            raise ValueError("time must have one entry per clip")
+        out = torch.empty((B, self.F, self.J, 3), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.d3d_forward_denoise(self.h, _ptr(x5), _ptr(t), _ptr(out), B, self._stream()), self.h,
+                   "d3d_forward_denoise")
+        return out
+
+    def ddim_sample(self, x2d: torch.Tensor, noise0: torch.Tensor, step_noise: Optional[torch.Tensor] = None,
+                    trace: bool = False):
+        B = x2d.shape[0]
+        _check_dev(x2d, self.device, (B, self.F, self.J, 2), name="x2d")
+        _check_dev(noise0, self.device, (B, self.F, self.J, 3), name="noise0")
+        if step_noise is not None:
+            _check_dev(step_noise, self.device, (self.S - 1, B, self.F, self.J, 3), name="step_noise")
+        y0 = torch.empty_like(noise0)
+        ty = tx = None
+        if trace:
+            ty = torch.empty((B, self.F, self.J, 3, self.S), device=self.device, dtype=torch.float32)
+            tx = torch.empty_like(ty)
+        _lib.check(self.lib.d3d_ddim_sample(self.h, _ptr(x2d), _ptr(noise0), _ptr(step_noise), _ptr(y0), _ptr(ty),
+                                            _ptr(tx), B, self._stream()), self.h, "d3d_ddim_sample")
+        return (y0, ty, tx) if trace else y0
+
+    def ddim_sample_host(self, x2d: torch.Tensor, noise0: torch.Tensor, step_noise: Optional[torch.Tensor],
+                         y0: torch.Tensor):
+        """Host (pinned) buffers in, host buffer out; synchronises the stream.  The e2e entry point."""
+        B = x2d.shape[0]
+        for name, t in (("x2d", x2d), ("noise0", noise0), ("y0", y0)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous fp32 host tensor")
+        _lib.check(self.lib.d3d_ddim_sample_host(self.h, _ptr(x2d), _ptr(noise0), _ptr(step_noise), _ptr(y0), B,
+                                                 self._stream()), self.h, "d3d_ddim_sample_host")
+        return y0
+
+    def tta_merge(self, y: torch.Tensor, y_flip: torch.Tensor, joints_left, joints_right, scale: float = 1.0):
+        _check_dev(y, self.device, name="y")
+        _check_dev(y_flip, self.device, tuple(y.shape), name="y_flip")
+        n = len(joints_left)
+        la = (C.c_int32 * n)(*joints_left)
+        ra = (C.c_int32 * n)(*joints_right)
+        out = torch.empty_like(y)
+        _lib.check(self.lib.d3d_tta_merge(self.h, _ptr(y), _ptr(y_flip), la, ra, n, float(scale), _ptr(out),
+                                          y.shape[0] * y.shape[1], self._stream()), self.h, "d3d_tta_merge")
+        return out
+
+    def mpjpe_accumulate(self, pred: torch.Tensor, gt: torch.Tensor, acc: torch.Tensor,
+                         frame_mask: Optional[torch.Tensor] = None):
+        """acc: fp64[2] on the device: (sum of joint errors, joint count)."""
+        _check_dev(pred, self.device, name="pred")
+        _check_dev(gt, self.device, tuple(pred.shape), name="gt")
+        _check_dev(acc, self.device, (2,), torch.float64, "acc")
+        n_frames = pred.numel() // (self.J * 3)
+        if frame_mask is not None:
+            _check_dev(frame_mask, self.device, dtype=torch.uint8, name="frame_mask")
+        _lib.check(self.lib.d3d_mpjpe_accumulate(self.h, _ptr(pred), _ptr(gt), _ptr(frame_mask), n_frames, _ptr(acc),
+                                                 self._stream()), self.h, "d3d_mpjpe_accumulate")
+        return acc
+
+    def launch_count(self) -> int:
+        return int(self.lib.d3d_launch_count(self.h))
+
+    # ------------------------------------------------------------------ kernel-level entry points (tests / bench)
+    def op_linear(self, a, w, bias, residual=None, act=0, gemm_mode=_lib.GEMM_TC_SPLIT3):
+        M, K = a.shape
+        N = w.shape[0]
+        out = torch.empty((M, N), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.d3d_op_linear(self.h, _ptr(a), _ptr(w), _ptr(bias), _ptr(residual), _ptr(out), M, N, K,
+                                          act, gemm_mode, self._stream()), self.h, "d3d_op_linear")
+        return out
+
+    def op_linear_bench(self, M, N, K, act=0, gemm_mode=_lib.GEMM_TC_SPLIT3, iters=10) -> float:
+        ms = C.c_float()
+        _lib.check(self.lib.d3d_op_linear_bench(self.h, M, N, K, act, gemm_mode, iters, C.byref(ms)), self.h,
+                   "d3d_op_linear_bench")
+        return float(ms.value)
+
+    def op_layernorm(self, x, gamma, beta, eps):
+        out = torch.empty_like(x)
+        _lib.check(self.lib.d3d_op_layernorm(self.h, _ptr(x), _ptr(gamma), _ptr(beta), eps, _ptr(out),
+                                             x.numel() // self.C, self._stream()), self.h, "d3d_op_layernorm")
+        return out
+
+    def op_attention(self, qkv, B, spatial, attn_mode=_lib.ATTN_DEFAULT):
+        out = torch.empty((qkv.shape[0], self.C), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.d3d_op_attention(self.h, _ptr(qkv), _ptr(out), B, int(spatial), attn_mode, self._stream()),
+                   self.h, "d3d_op_attention")
+        return out
+
+    def op_time_table(self, t_host: Sequence[float]):
+        R = len(t_host)
+        arr = (C.c_float * R)(*[float(v) for v in t_host])
+        out = torch.empty((R, 2 * self.depth, self.C), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.d3d_op_time_table(self.h, arr, R, _ptr(out), self._stream()), self.h, "d3d_op_time_table")
+        return out
+
+    def debug_forward_blocks(self, x5, t, n_blocks):
+        B = x5.shape[0]
+        t = t.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty((B * self.F * self.J, self.C), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.d3d_debug_forward_blocks(self.h, _ptr(x5), _ptr(t), B, n_blocks, _ptr(out), self._stream()),
+                   self.h, "d3d_debug_forward_blocks")
+        return out

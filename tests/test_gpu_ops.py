@@ -1,0 +1,121 @@
+"""GPU (-m gpu): kernel-level parity through the C ABI against the CPU oracle / fp64 torch on the same inputs."""
+import numpy as np
+import pytest
+import torch
+
+from diff3dhpe_b200 import _lib, synthetic
+from diff3dhpe_b200.engine import Engine
+from oracle import diff3d_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng27():
+    e = Engine(27, max_clips=4)
+    yield e
+    e.close()
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+@pytest.mark.parametrize("mode,tol", [(_lib.GEMM_SIMT_FP32, 3e-6), (_lib.GEMM_TC_SPLIT3, 3e-6), (_lib.GEMM_TC_FP16, 2e-3)])
+@pytest.mark.parametrize("M,N,K", [(128, 1536, 512), (200, 512, 512), (1000, 1024, 512), (459, 512, 1024),
+                                   (37 * 128 + 5, 256, 64)])
+def test_linear_parity(eng27, mode, tol, M, N, K):
+    a, w, b = _rand((M, K), 1), _rand((N, K), 2, 0.05), _rand((N,), 3, 0.1)
+    res = _rand((M, N), 4)
+    ref = (a.double() @ w.double().T + b.double() + res.double())
+    out = eng27.op_linear(a.cuda(), w.cuda(), b.cuda(), residual=res.cuda(), act=0, gemm_mode=mode).cpu()
+    scale = (a.double().abs() @ w.double().abs().T).max().item()       # error bound scales with sum |a||w|
+    err = (out.double() - ref).abs().max().item() / scale
+    assert err < tol, f"relative error {err:.3e}"
+
+
+@pytest.mark.parametrize("mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3])
+def test_linear_gelu_split_epilogue(eng27, mode):
+    M, N, K = 300, 1024, 512
+    a, w, b = _rand((M, K), 5), _rand((N, K), 6, 0.05), _rand((N,), 7, 0.1)
+    ref = torch.nn.functional.gelu(a.double() @ w.double().T + b.double())
+    out = eng27.op_linear(a.cuda(), w.cuda(), b.cuda(), act=1, gemm_mode=mode).cpu()
+    assert (out.double() - ref).abs().max().item() < 2e-5
+
+
+def test_tc_matches_simt_elementwise(eng27):
+    """Same split operands in, so tensor-core and CUDA-core results differ only by accumulation order and the
+    dropped lo*lo term (2^-22 relative)."""
+    M, N, K = 777, 1536, 512
+    a, w, b = _rand((M, K), 8).cuda(), _rand((N, K), 9, 0.05).cuda(), _rand((N,), 10).cuda()
+    x = eng27.op_linear(a, w, b, gemm_mode=_lib.GEMM_TC_SPLIT3)
+    y = eng27.op_linear(a, w, b, gemm_mode=_lib.GEMM_SIMT_FP32)
+    assert (x - y).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("eps", [1e-6, 1e-5])
+def test_layernorm(eng27, eps):
+    x, g, b = _rand((1000, 512), 11, 3.0) + 0.5, _rand((512,), 12) + 1, _rand((512,), 13)
+    ref = torch.nn.functional.layer_norm(x, (512,), g, b, eps)
+    out = eng27.op_layernorm(x.cuda(), g.cuda(), b.cuda(), eps).cpu()
+    assert (out - ref).abs().max().item() < 5e-6
+
+
+@pytest.mark.parametrize("F", [27, 81, 243, 9, 100])
+@pytest.mark.parametrize("mode", [_lib.ATTN_DEFAULT, _lib.ATTN_SIMT])
+@pytest.mark.parametrize("spatial", [True, False])
+def test_attention_core(F, mode, spatial):
+    B, J, C = 2, 17, 512
+    eng = Engine(F, max_clips=B)
+    qkv = _rand((B * F * J, 3 * C), 20 + F, 1.5)
+    x = qkv.view(B, F, J, 3 * C)
+    seqs = x.reshape(B * F, J, 3 * C) if spatial else x.permute(0, 2, 1, 3).reshape(B * J, F, 3 * C)
+    ref = oracle.attention_core(seqs, 8)
+    ref = ref.reshape(B, F, J, C) if spatial else ref.reshape(B, J, F, C).permute(0, 2, 1, 3)
+    out = eng.op_attention(qkv.cuda(), B, spatial, mode).cpu().view(B, F, J, C)
+    eng.close()
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+def test_time_table_golden(golden):
+    g = golden("denoise_f27_b3")
+    eng = Engine(27, max_clips=3)
+    eng.load_state_dict(synthetic.make_model(27).state_dict())
+    tab = eng.op_time_table([float(t) for t in g["t"]]).cpu().numpy()
+    eng.close()
+    assert np.abs(tab - g["time_table"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3])
+def test_residual_stream_after_blocks_golden(golden, gemm_mode):
+    """Residual stream after STE block 0 and TTE block 0 (sub-sampled) against the imported reference."""
+    g = golden("denoise_f27_b3")
+    eng = Engine(27, max_clips=3, gemm_mode=gemm_mode)
+    eng.load_state_dict(synthetic.make_model(27).state_dict())
+    x2d, _ = synthetic.make_inputs(3, 27)
+    y_T, _ = synthetic.make_noise(3, 27, 1)
+    x5 = torch.cat([x2d, y_T], -1).cuda()
+    t = torch.tensor(g["t"], dtype=torch.long).cuda()
+    x1 = eng.debug_forward_blocks(x5, t, 1).cpu().numpy()[::8]
+    x2 = eng.debug_forward_blocks(x5, t, 2).cpu().numpy()[::8]
+    eng.close()
+    assert np.abs(x1 - g["x_after_1"]).max() < 5e-5
+    assert np.abs(x2 - g["x_after_2"]).max() < 1e-4
+
+
+def test_tta_merge_and_mpjpe_golden(eng27, golden):
+    g = golden("tta_tail")
+    y, yf, gt = (torch.from_numpy(g[k]).cuda() for k in ("y", "yf", "gt"))
+    merged = eng27.tta_merge(y, yf, synthetic.H36M_JOINTS_LEFT, synthetic.H36M_JOINTS_RIGHT, float(g["scale"]))
+    assert np.array_equal(merged.cpu().numpy(), g["merged"])           # bit-exact: same fp32 op order
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    eng27.mpjpe_accumulate(merged, gt, acc)
+    assert acc[1].item() == 3 * 9 * 17
+    assert abs(acc[0].item() / acc[1].item() - float(g["mpjpe"])) < 1e-6
+    mask = torch.zeros(27, dtype=torch.uint8, device="cuda")
+    mask[::2] = 1
+    acc.zero_()
+    eng27.mpjpe_accumulate(merged, gt, acc, mask)
+    ref = torch.norm(merged - gt, dim=-1).reshape(27, 17)[mask.bool()].double()
+    assert acc[1].item() == ref.numel() and abs(acc[0].item() - ref.sum().item()) < 1e-4

@@ -1,0 +1,115 @@
+"""CPU: the oracle against the committed golden vectors (generated from the imported, unmodified reference by
+tools/make_golden.py) and against the known answers of SURVEY.md section 4."""
+import numpy as np
+import pytest
+import torch
+
+from diff3dhpe_b200 import synthetic
+from oracle import diff3d_oracle as oracle
+
+# fp32 CPU GEMM blocking differs between hosts (AVX2 / AVX-512 code paths), so cross-machine agreement with the
+# golden vectors is to rounding, not bit-exact (it IS bit-exact on the machine that generated them).
+TOL = 2e-5
+
+
+def _sd(F, with_time_emb=True):
+    m = synthetic.make_model(F, with_time_emb=with_time_emb)
+    return {k: v.detach() for k, v in m.state_dict().items()}
+
+
+def test_schedule_known_answers():
+    assert oracle.ddim_times(1000, 9) == [999, 887, 776, 665, 554, 443, 332, 221, 110, -1]
+    assert oracle.ddim_times(1000, 1) == [999, -1]
+    assert oracle.ddim_times(1000, 1000)[:3] == [999, 998, 997]
+    b = oracle.schedule_buffers(1000)
+    ac = b["alphas_cumprod"]
+    assert ac.dtype == torch.float32 and ac.shape == (1000,)
+    assert torch.all(ac[1:] < ac[:-1]) and 0.99 < ac[0] < 1 and ac[-1] < 1e-4
+    co = oracle.ddim_coefficients(b, oracle.ddim_times(1000, 9), 0.0)
+    assert co[-1] is None and all(c["sigma"] == 0 for c in co[:-1])
+    # eta = 0: c = sqrt(1 - alpha_next)
+    assert torch.equal(co[0]["c"], (1 - ac[887]).sqrt())
+
+
+def test_weights_match_reference_seeded_init(golden):
+    g = golden("weights_checksum")
+    for F, n in ((27, 43646467), (81, 43674115), (243, 43757059)):
+        sd = synthetic.make_model(F).state_dict()
+        assert sum(v.numel() for v in sd.values()) == n == int(g[f"F{F}_n"])
+        s = np.array([v.double().sum().item() for v in sd.values()])
+        a = np.array([v.double().abs().sum().item() for v in sd.values()])
+        np.testing.assert_allclose(s, g[f"F{F}_sum"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(a, g[f"F{F}_abs"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["denoise_f27_b3", "denoise_f27_b2_notime"])
+def test_forward_denoise_golden(golden, name):
+    g = golden(name)
+    F, B = int(g["F"]), int(g["B"])
+    wt = "notime" not in name
+    sd = _sd(F, wt)
+    x2d, _ = synthetic.make_inputs(B, F)
+    y_T, _ = synthetic.make_noise(B, F, 1)
+    with torch.no_grad():
+        out = oracle.forward_denoise(sd, torch.cat([x2d, y_T], -1), torch.tensor(g["t"], dtype=torch.long))
+    assert np.abs(out.numpy() - g["out"]).max() < TOL
+
+
+@pytest.mark.parametrize("name", ["sampler_f27_b2_s3_clip", "sampler_f27_b2_s3_eta", "sampler_f27_b2_s2_notime",
+                                  "sampler_f9_b2_s9_clip"])
+def test_sampler_golden(golden, name):
+    g = golden(name)
+    F, B, S = int(g["F"]), int(g["B"]), int(g["S"])
+    sd = _sd(F, bool(g["with_time_emb"]))
+    x2d, _ = synthetic.make_inputs(B, F)
+    y_T, steps = synthetic.make_noise(B, F, S)
+    with torch.no_grad():
+        out = oracle.ddim_sample_loop(sd, x2d, y_T, steps, sampling_timesteps=S, eta=float(g["eta"]),
+                                      clip_denoised=bool(g["clip"]), trace="rev" in g)
+    if "rev" in g:
+        out, rev, x0s = out
+        assert np.abs(rev.numpy() - g["rev"]).max() < 5e-5
+        assert np.abs(x0s.numpy() - g["x0s"]).max() < 5e-5
+    assert np.abs(out.numpy() - g["pred"]).max() < 5e-5
+
+
+def test_tta_tail_golden(golden):
+    g = golden("tta_tail")
+    merged = oracle.tta_merge(torch.from_numpy(g["y"]), torch.from_numpy(g["yf"]), float(g["scale"]))
+    assert np.array_equal(merged.numpy(), g["merged"])
+    e = oracle.mpjpe(merged, torch.from_numpy(g["gt"]))
+    assert abs(e.item() - float(g["mpjpe"])) < 1e-6
+
+
+def test_draw_order_matches_reference_count():
+    y_T, steps = oracle.draw_noise((2, 9, 17, 3), 9, torch.Generator().manual_seed(3))
+    assert y_T.shape == (2, 9, 17, 3) and steps.shape == (8, 2, 9, 17, 3)
+    g = torch.Generator().manual_seed(3)
+    assert torch.equal(y_T, torch.randn(2, 9, 17, 3, generator=g))
+    assert torch.equal(steps[0], torch.randn(2, 9, 17, 3, generator=g))
+
+
+def test_grand_identity_and_flip_batching():
+    """(P - I) V == P V - V, and orig||flip as one 2B batch equals two separate calls."""
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(4, 8, 17, 17, generator=g).softmax(-1)
+    v = torch.randn(4, 8, 17, 64, generator=g)
+    eye = torch.eye(17).view(1, 1, 17, 17)
+    assert ((p - eye) @ v - (p @ v - v)).abs().max() < 2e-6
+    sd = _sd(9)
+    x2d, _ = synthetic.make_inputs(2, 9)
+    xf = oracle.flip_2d(x2d)
+    y_T, _ = synthetic.make_noise(4, 9, 1)
+    kw = dict(sampling_timesteps=1)
+    with torch.no_grad():
+        both = oracle.ddim_sample_loop(sd, torch.cat([x2d, xf]), y_T, None, **kw)
+        a = oracle.ddim_sample_loop(sd, x2d, y_T[:2], None, **kw)
+        b = oracle.ddim_sample_loop(sd, xf, y_T[2:], None, **kw)
+    assert (both - torch.cat([a, b])).abs().max() < 1e-5
+
+
+def test_flip_is_involution_and_uses_h36m_lists():
+    x, _ = synthetic.make_inputs(2, 3)
+    assert torch.equal(oracle.flip_2d(oracle.flip_2d(x)), x)
+    assert oracle.H36M_JOINTS_LEFT == [4, 5, 6, 11, 12, 13] and oracle.H36M_JOINTS_RIGHT == [1, 2, 3, 14, 15, 16]
+    assert torch.equal(oracle.flip_2d(x), synthetic.flip_2d(x))
