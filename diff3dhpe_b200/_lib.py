@@ -14,6 +14,7 @@ LIB_PATH = Path(os.environ.get("D3D_LIB", _PKG / "libdiff3d_b200.so"))
 
 GEMM_TC_SPLIT3, GEMM_TC_FP16, GEMM_SIMT_FP32 = 0, 1, 2
 ATTN_DEFAULT, ATTN_SIMT = 0, 1
+PROF_CLASSES = ("gemm", "attn_spatial", "attn_temporal", "ln", "lift", "head_ddim")
 
 
 class Config(C.Structure):
@@ -45,6 +46,8 @@ PROTOTYPES = {
     "d3d_mpjpe_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_void_p]),
     "d3d_launch_count": (C.c_int64, [C.c_void_p]),
+    "d3d_profile_begin": (C.c_int, [C.c_void_p]),
+    "d3d_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "d3d_op_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "d3d_op_linear_bench": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -122,7 +122,7 @@ attn_generic_kernel(const float* __restrict__ qkv, __half* __restrict__ o_hi, __
                     float* __restrict__ o_f32, int N, int64_t outer, int inner, int64_t tok_stride) {
   extern __shared__ float sm[];
   float* Ks = sm;                       // [N][65]
-  float* Vs = Ks + N * KPAD;            // [N][64]
+  float* Vs = Ks + ((N * KPAD + 3) & ~3);   // [N][64], 16-byte aligned
   float* Ps = Vs + N * kHd;             // [8][N]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y;
@@ -212,7 +212,7 @@ cudaError_t configure_attention() {
   cudaError_t e = cudaFuncSetAttribute(attn_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpatialSmem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(attn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (256 * KPAD + 256 * kHd + 8 * 256) * static_cast<int>(sizeof(float)));
+                              (((256 * KPAD + 3) & ~3) + 256 * kHd + 8 * 256) * static_cast<int>(sizeof(float)));
 }
 
 cudaError_t launch_attn_spatial(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int64_t n_groups,
@@ -228,7 +228,7 @@ cudaError_t launch_attn_generic_simt(const float* qkv, __half* o_hi, __half* o_l
                                      int64_t outer, int inner, int64_t tok_stride, cudaStream_t st) {
   if (n_seq <= 0) return cudaSuccess;
   if (N < 1 || N > 256) return cudaErrorInvalidValue;
-  const int smem = (N * KPAD + N * kHd + 8 * N) * static_cast<int>(sizeof(float));
+  const int smem = (((N * KPAD + 3) & ~3) + N * kHd + 8 * N) * static_cast<int>(sizeof(float));
   dim3 grid(static_cast<unsigned>(n_seq), kHeads);
   attn_generic_kernel<<<grid, 256, smem, st>>>(qkv, o_hi, o_lo, o_f32, N, outer, inner, tok_stride);
   return cudaGetLastError();

@@ -79,6 +79,13 @@ struct d3d_handle {
   std::vector<DdimStep> steps;
   bool have_schedule = false, table_valid = false, need_noise = false;
 
+  // per-kernel-class device timing (d3d_profile_*): events bracket every launch of the un-graphed sampler
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_pool;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  size_t prof_next = 0;
+
   std::map<int, cudaGraphExec_t> graphs;
   std::map<int, int64_t> graph_launches;
   cudaStream_t cap_stream = nullptr;
@@ -103,6 +110,31 @@ namespace {
     CK(expr);          \
     ++h->launches;     \
   } while (0)
+
+// kernel launch of class `cls` (D3D_PROF_*): counted, and bracketed by events when profiling is on
+#define KLP(cls, st, expr)                                          \
+  do {                                                              \
+    cudaEvent_t _a = nullptr, _b = nullptr;                         \
+    if (h->prof) {                                                  \
+      _a = prof_event(h);                                           \
+      _b = prof_event(h);                                           \
+      if (_a && _b) CK(cudaEventRecord(_a, st));                    \
+    }                                                               \
+    KL(expr);                                                       \
+    if (h->prof && _a && _b) {                                      \
+      CK(cudaEventRecord(_b, st));                                  \
+      h->prof_recs.push_back(d3d_handle::ProfRec{cls, _a, _b});     \
+    }                                                               \
+  } while (0)
+
+cudaEvent_t prof_event(d3d_handle* h) {
+  if (h->prof_next == h->prof_pool.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    h->prof_pool.push_back(e);
+  }
+  return h->prof_pool[h->prof_next++];
+}
 
 int fail(d3d_handle* h, int code, const std::string& msg) {
   h->err = msg;
@@ -166,11 +198,11 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   p.out_hi = out_hi;
   p.out_lo = out_lo;
   if (mode == D3D_GEMM_SIMT_FP32) {
-    KL(launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, st));
+    KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, st));
   } else {
     GemmMaps m;
     m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
-    KL(launch_gemm_tc(m, p, epi, mode == D3D_GEMM_TC_FP16 ? 1 : 3, pick_bn(h, M, w.N), h->num_sms, st));
+    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, mode == D3D_GEMM_TC_FP16 ? 1 : 3, pick_bn(h, M, w.N), h->num_sms, st));
   }
   return 0;
 }
@@ -179,14 +211,14 @@ int run_attention(d3d_handle* h, const float* qkv, __half* o_hi, __half* o_lo, f
                   int mode, cudaStream_t st) {
   if (spatial) {
     if (mode == D3D_ATTN_SIMT || h->J != 17)
-      KL(launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, B * h->F, h->J, h->J, 1, 1, st));
+      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, B * h->F, h->J, h->J, 1, 1, st));
     else
-      KL(launch_attn_spatial(qkv, o_hi, o_lo, o_f32, static_cast<int64_t>(B) * h->F, h->J, st));
+      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial(qkv, o_hi, o_lo, o_f32, static_cast<int64_t>(B) * h->F, h->J, st));
   } else {
     if (mode == D3D_ATTN_SIMT)
-      KL(launch_attn_temporal_simt(qkv, o_hi, o_lo, o_f32, B, h->F, h->J, st));
+      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_simt(qkv, o_hi, o_lo, o_f32, B, h->F, h->J, st));
     else
-      KL(launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, B, h->F, h->J, st));
+      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, B, h->F, h->J, st));
   }
   return 0;
 }
@@ -231,22 +263,24 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
   const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
   const int gm = h->cfg.gemm_mode, am = h->cfg.attn_mode;
   int r;
-  KL(launch_lift_ln(x2d, y, x5, h->wf_t, h->bf, h->spos, tv, tv_stride, LnParams{h->blk[0].n1g, h->blk[0].n1b}, h->X,
-                    h->A.hi, h->A.lo, T, h->J, h->F * h->J, st));
+  KLP(D3D_PROF_LIFT, st, launch_lift_ln(x2d, y, x5, h->wf_t, h->bf, h->spos, tv, tv_stride,
+                                        LnParams{h->blk[0].n1g, h->blk[0].n1b}, h->X, h->A.hi, h->A.lo, T, h->J,
+                                        h->F * h->J, st));
   for (int b = 0; b < n_blocks; ++b) {
     const Blk& k = h->blk[b];
     const bool spatial = (b % 2) == 0;
     if ((r = run_gemm(h, h->A, k.qkv, T, EPI_F32, nullptr, h->QKV, nullptr, nullptr, gm, st))) return r;
     if ((r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial, am, st))) return r;
     if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, gm, st))) return r;
-    KL(launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, T, st));
+    KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, T, st));
     if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, gm, st))) return r;
     if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, gm, st))) return r;
     if (b + 1 < n_blocks) {
       const LnParams post = spatial ? LnParams{h->sn_g, h->sn_b} : LnParams{h->tn_g, h->tn_b};
       const Blk& nx = h->blk[b + 1];
-      KL(launch_postnorm_add_ln(h->X, post, (b + 1 == 1) ? h->tpos : nullptr, tv ? tv + (b + 1) * kC : nullptr,
-                                tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo, T, h->J, h->F, st));
+      KLP(D3D_PROF_LN, st,
+          launch_postnorm_add_ln(h->X, post, (b + 1 == 1) ? h->tpos : nullptr, tv ? tv + (b + 1) * kC : nullptr,
+                                 tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo, T, h->J, h->F, st));
     }
   }
   return 0;
@@ -255,8 +289,8 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
 int run_head(d3d_handle* h, const DdimStep& s, float* y, const float* noise, float* out3, float* trace_y,
              float* trace_x0, int trace_idx, int B, cudaStream_t st) {
   const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
-  KL(launch_head_ddim(h->X, LnParams{h->tn_g, h->tn_b}, LnParams{h->hg, h->hb}, h->wh, h->bh, s, y, noise, out3,
-                      trace_y, trace_x0, h->S, trace_idx, T, st));
+  KLP(D3D_PROF_HEAD, st, launch_head_ddim(h->X, LnParams{h->tn_g, h->tn_b}, LnParams{h->hg, h->hb}, h->wh, h->bh, s,
+                                          y, noise, out3, trace_y, trace_x0, h->S, trace_idx, T, st));
   return 0;
 }
 
@@ -416,6 +450,7 @@ void d3d_destroy(d3d_handle* h) {
   cudaDeviceSynchronize();
   drop_graphs(h);
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
@@ -610,7 +645,7 @@ static int sample_on_device(d3d_handle* h, int B, float* trace_y, float* trace_x
   int r = ensure_table(h, st);
   if (r) return r;
   const bool tracing = trace_y || trace_x0;
-  if (!h->cfg.use_graph || tracing) return run_sampler(h, B, trace_y, trace_x0, st);
+  if (!h->cfg.use_graph || tracing || h->prof) return run_sampler(h, B, trace_y, trace_x0, st);
   auto it = h->graphs.find(B);
   if (it == h->graphs.end()) {
     const int64_t before = h->launches;
@@ -713,6 +748,31 @@ int d3d_mpjpe_accumulate(d3d_handle* h, const float* pred, const float* gt, cons
   if (!h || !pred || !gt || !acc) return -1;
   DeviceGuard guard(h->cfg.device);
   KL(launch_mpjpe(pred, gt, mask, n_frames, h->J, acc, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int d3d_profile_begin(d3d_handle* h) {
+  if (!h) return -1;
+  h->prof = true;
+  h->prof_recs.clear();
+  h->prof_next = 0;
+  return 0;
+}
+
+int d3d_profile_end(d3d_handle* h, double* ms_per_class, int64_t* launches_per_class) {
+  if (!h || !ms_per_class || !launches_per_class) return -1;
+  DeviceGuard guard(h->cfg.device);
+  h->prof = false;
+  CK(cudaDeviceSynchronize());
+  for (int c = 0; c < D3D_PROF_NUM_CLASSES; ++c) { ms_per_class[c] = 0.0; launches_per_class[c] = 0; }
+  for (auto& r : h->prof_recs) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_per_class[r.cls] += ms;
+    launches_per_class[r.cls] += 1;
+  }
+  h->prof_recs.clear();
+  h->prof_next = 0;
   return 0;
 }
 

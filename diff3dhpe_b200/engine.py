@@ -167,6 +167,16 @@ class Engine:
                                                  self._stream()), self.h, "d3d_mpjpe_accumulate")
         return acc
 
+    def profile_begin(self):
+        _lib.check(self.lib.d3d_profile_begin(self.h), self.h, "d3d_profile_begin")
+
+    def profile_end(self):
+        """Returns {class: (total_ms, launches)} for the kernels launched since profile_begin()."""
+        n = len(_lib.PROF_CLASSES)
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(self.lib.d3d_profile_end(self.h, ms, cnt), self.h, "d3d_profile_end")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.PROF_CLASSES)}
+
     def launch_count(self) -> int:
         return int(self.lib.d3d_launch_count(self.h))
 

@@ -131,6 +131,21 @@ D3D_API int d3d_mpjpe_accumulate(d3d_handle* h, const float* pred_dev, const flo
 /* Number of kernels launched (or replayed through graphs) by this handle since creation. */
 D3D_API int64_t d3d_launch_count(const d3d_handle* h);
 
+/* Per-kernel-class device timing.  Between d3d_profile_begin and d3d_profile_end every kernel of the sampler /
+ * denoiser is launched un-graphed and bracketed by CUDA events on the launch stream; d3d_profile_end
+ * synchronises and returns the summed durations (ms) and launch counts per class. */
+enum {
+  D3D_PROF_GEMM = 0,          /* qkv / proj / fc1 / fc2 tcgen05 GEMMs          */
+  D3D_PROF_ATTN_SPATIAL = 1,  /* 17-joint attention                             */
+  D3D_PROF_ATTN_TEMPORAL = 2, /* F-frame attention                              */
+  D3D_PROF_LN = 3,            /* post-norm + add + norm1, norm2 (row-wise)      */
+  D3D_PROF_LIFT = 4,          /* input lift + pos-embed + time vector + norm1   */
+  D3D_PROF_HEAD = 5,          /* Temporal_norm + head + clamp + DDIM update     */
+  D3D_PROF_NUM_CLASSES = 6
+};
+D3D_API int d3d_profile_begin(d3d_handle* h);
+D3D_API int d3d_profile_end(d3d_handle* h, double* ms_per_class, int64_t* launches_per_class);
+
 /* ---- kernel-level entry points (parity tests, microbenchmarks, ncu exhibits) ------------------------ */
 
 /* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias[N]) with the handle's (or the given) GEMM mode.
