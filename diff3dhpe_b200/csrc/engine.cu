@@ -72,6 +72,8 @@ struct d3d_handle {
   int tv_cap = 0;
   float* tv_general = nullptr;   // [max_clips, nblk, 512] for per-sample t
   int32_t* perm_dev = nullptr;
+  int32_t perm_host[64];
+  bool perm_valid = false;
 
   // schedule
   int S = 0;
@@ -737,8 +739,12 @@ int d3d_tta_merge(d3d_handle* h, const float* y, const float* yf, const int32_t*
     perm[left[i]] = right[i];      // new[left] = old[right]  (RUN:584-585)
     perm[right[i]] = left[i];
   }
-  CK(cudaMemcpyAsync(h->perm_dev, perm, sizeof(perm), cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));
+  if (!h->perm_valid || memcmp(perm, h->perm_host, sizeof(perm)) != 0) {      // upload only when the lists change
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(h->perm_dev, perm, sizeof(perm), cudaMemcpyHostToDevice));
+    memcpy(h->perm_host, perm, sizeof(perm));
+    h->perm_valid = true;
+  }
   KL(launch_tta_merge(y, yf, h->perm_dev, scale, out, n_frames, h->J, st));
   return 0;
 }
