@@ -1,124 +1,27 @@
-// GRAND attention cores (MODEL:76-83):  O = (softmax(Q K^T * hd^-0.5) - I) V  on the packed qkv tensor
-// [T, 3*512] written by the qkv GEMM (channel = which*512 + head*64 + d; token = (b*F + f)*J + j).
+// CUDA-core (fp32 arithmetic) GRAND attention used ONLY to validate the tensor-core kernels of attention_mma.cu:
+// same packed fp16 input (row = q | k | v_hi | v_lo, see EPI_QKV16), same output formats, no tensor cores.
 //
-//   attn_spatial_kernel   G-sattn: the 17 joints of one frame.  One warp per (frame, head); K and V live in
-//                         shared memory, each of the first 17 lanes owns one query row in registers, so the
-//                         17x17 softmax needs no shuffles and P never leaves registers.
-//   attn_generic_kernel   CUDA-core validation kernel for any sequence (temporal: the F frames of one joint,
-//                         addressed with stride J tokens -- no transposes, MODEL:119-121,130-133 eliminated).
-//   (the tensor-core temporal kernel lives in attention_mma.cu)
+//     O = (softmax(Q K^T * hd^-0.5) - I) V        (MODEL:76-83)
 //
-// Output is written token-major [T, 512] (heads merged, MODEL:83) either as the split-fp16 A operand of the
-// proj GEMM or as fp32 (op-level tests).
+// One CTA per (sequence, head).  Token of position n in sequence s:  (s / inner) * outer + (s % inner) + n * tok_stride
+//   spatial : inner = 1, outer = J, tok_stride = 1, N = J      (s = b*F + f)
+//   temporal: inner = J, outer = F*J, tok_stride = J, N = F    (s = b*J + j)   -- no transposes (MODEL:119-121,130-133)
+// Also: pack_qkv16_kernel, fp32 [T,1536] -> the packed fp16 layout (op-level test entry point only; in the
+// sampler the qkv GEMM epilogue writes the packed layout directly).
 #include "kernels.cuh"
 
 namespace d3d {
 namespace {
 
 constexpr float kScale = 0.125f;   // head_dim ** -0.5, MODEL:65
+constexpr int KPAD = kHd + 1;
 
 __device__ __forceinline__ uint32_t pack2(__half a, __half b) {
   return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
 }
 
-// ------------------------------------------------------------------------------------------ spatial, J = 17
-constexpr int SJ = 17;
-
 __global__ void __launch_bounds__(256)
-attn_spatial_kernel(const float* __restrict__ qkv, __half* __restrict__ o_hi, __half* __restrict__ o_lo,
-                    float* __restrict__ o_f32, int64_t n_groups) {
-  extern __shared__ float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = warp;                                    // 8 warps = 8 heads of one frame
-  const int64_t g = blockIdx.x;
-  if (g >= n_groups) return;
-  float* Ks = sm + warp * (2 * SJ * kHd);
-  float* Vs = Ks + SJ * kHd;
-  const float* base = qkv + g * SJ * (3 * kC) + head * kHd;
-
-  // K, V rows -> smem (17 rows x 16 float4 each)
-  for (int i = lane; i < SJ * 16; i += 32) {
-    const int r = i >> 4, c4 = i & 15;
-    const float4 kk = *reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * (3 * kC) + kC + 4 * c4);
-    const float4 vv = *reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * (3 * kC) + 2 * kC + 4 * c4);
-    *reinterpret_cast<float4*>(Ks + r * kHd + 4 * c4) = kk;
-    *reinterpret_cast<float4*>(Vs + r * kHd + 4 * c4) = vv;
-  }
-  // own query row -> registers
-  const int qi = lane < SJ ? lane : SJ - 1;                 // idle lanes shadow row 16 (results discarded)
-  float q[kHd];
-#pragma unroll
-  for (int c4 = 0; c4 < 16; ++c4) {
-    const float4 t = *reinterpret_cast<const float4*>(base + static_cast<size_t>(qi) * (3 * kC) + 4 * c4);
-    q[4 * c4] = t.x; q[4 * c4 + 1] = t.y; q[4 * c4 + 2] = t.z; q[4 * c4 + 3] = t.w;
-  }
-  __syncwarp();
-
-  float s[SJ];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < SJ; ++j) {
-    float a = 0.f;
-#pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      const float4 kk = *reinterpret_cast<const float4*>(Ks + j * kHd + 4 * c4);
-      a = fmaf(q[4 * c4], kk.x, a); a = fmaf(q[4 * c4 + 1], kk.y, a);
-      a = fmaf(q[4 * c4 + 2], kk.z, a); a = fmaf(q[4 * c4 + 3], kk.w, a);
-    }
-    s[j] = a * kScale;
-    mx = fmaxf(mx, s[j]);
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < SJ; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
-  const float inv = 1.0f / sum;
-#pragma unroll
-  for (int j = 0; j < SJ; ++j) s[j] = s[j] * inv - (j == qi ? 1.0f : 0.0f);      // P - I  (MODEL:82-83)
-
-  float o[kHd];
-#pragma unroll
-  for (int d = 0; d < kHd; ++d) o[d] = 0.f;
-#pragma unroll
-  for (int j = 0; j < SJ; ++j) {
-#pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      const float4 vv = *reinterpret_cast<const float4*>(Vs + j * kHd + 4 * c4);
-      o[4 * c4] = fmaf(s[j], vv.x, o[4 * c4]); o[4 * c4 + 1] = fmaf(s[j], vv.y, o[4 * c4 + 1]);
-      o[4 * c4 + 2] = fmaf(s[j], vv.z, o[4 * c4 + 2]); o[4 * c4 + 3] = fmaf(s[j], vv.w, o[4 * c4 + 3]);
-    }
-  }
-  if (lane < SJ) {
-    const size_t off = static_cast<size_t>(g * SJ + lane) * kC + head * kHd;
-    if (o_f32) {
-#pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4)
-        *reinterpret_cast<float4*>(o_f32 + off + 4 * c4) = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
-    } else {
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float v0 = o[8 * c8 + 2 * e], v1 = o[8 * c8 + 2 * e + 1];
-          const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-          hw[e] = pack2(h0, h1);
-          lw[e] = pack2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
-        }
-        *reinterpret_cast<uint4*>(o_hi + off + 8 * c8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(o_lo + off + 8 * c8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------ generic (validation)
-// One CTA per (sequence, head).  Token of position n in sequence s:  (s / inner) * outer + (s % inner) + n * tok_stride
-//   spatial : inner = 1, outer = J, tok_stride = 1, N = J      (s = b*F + f)
-//   temporal: inner = J, outer = F*J, tok_stride = J, N = F    (s = b*J + j)
-constexpr int KPAD = kHd + 1;
-
-__global__ void __launch_bounds__(256)
-attn_generic_kernel(const float* __restrict__ qkv, __half* __restrict__ o_hi, __half* __restrict__ o_lo,
+attn_generic_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_hi, __half* __restrict__ o_lo,
                     float* __restrict__ o_f32, int N, int64_t outer, int inner, int64_t tok_stride) {
   extern __shared__ float sm[];
   float* Ks = sm;                       // [N][65]
@@ -128,28 +31,22 @@ attn_generic_kernel(const float* __restrict__ qkv, __half* __restrict__ o_hi, __
   const int head = blockIdx.y;
   const int64_t s = blockIdx.x;
   const int64_t tok0 = (s / inner) * outer + (s % inner);
-  const float* base = qkv + head * kHd;
+  const __half* base = qkv + head * kHd;
 
-  for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
-    const int r = i >> 4, c4 = i & 15;
-    const size_t row = static_cast<size_t>(tok0 + r * tok_stride) * (3 * kC);
-    const float4 kk = *reinterpret_cast<const float4*>(base + row + kC + 4 * c4);
-    const float4 vv = *reinterpret_cast<const float4*>(base + row + 2 * kC + 4 * c4);
-    float* kd = Ks + r * KPAD + 4 * c4;
-    kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
-    *reinterpret_cast<float4*>(Vs + r * kHd + 4 * c4) = vv;
+  for (int i = threadIdx.x; i < N * kHd; i += blockDim.x) {
+    const int r = i >> 6, d = i & 63;
+    const size_t row = static_cast<size_t>(tok0 + r * tok_stride) * kQkvRow;
+    Ks[r * KPAD + d] = __half2float(base[row + kC + d]);
+    Vs[r * kHd + d] = __half2float(base[row + 2 * kC + d]) + __half2float(base[row + 3 * kC + d]);
   }
   __syncthreads();
 
   float* P = Ps + warp * N;
   for (int i = warp; i < N; i += 8) {
     float q[kHd];
-    const float* qrow = base + static_cast<size_t>(tok0 + i * tok_stride) * (3 * kC);
+    const __half* qrow = base + static_cast<size_t>(tok0 + i * tok_stride) * kQkvRow;
 #pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(qrow + 4 * c4));
-      q[4 * c4] = t.x; q[4 * c4 + 1] = t.y; q[4 * c4 + 2] = t.z; q[4 * c4 + 3] = t.w;
-    }
+    for (int d = 0; d < kHd; ++d) q[d] = __half2float(qrow[d]);
     float sc[8];
     float mx = -INFINITY;
 #pragma unroll
@@ -204,27 +101,27 @@ attn_generic_kernel(const float* __restrict__ qkv, __half* __restrict__ o_hi, __
   }
 }
 
-constexpr int kSpatialSmem = 8 * 2 * SJ * kHd * sizeof(float);   // 69632 B
+__global__ void pack_qkv16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t T) {
+  const int64_t n = T * (3 * kC);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / (3 * kC);
+    const int c = static_cast<int>(i - t * (3 * kC));
+    const float v = in[i];
+    const __half h = __float2half_rn(v);
+    out[t * kQkvRow + c] = h;
+    if (c >= 2 * kC) out[t * kQkvRow + c + kC] = __float2half_rn(v - __half2float(h));
+  }
+}
 
 }  // namespace
 
 cudaError_t configure_attention() {
-  cudaError_t e = cudaFuncSetAttribute(attn_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpatialSmem);
-  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(attn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (((256 * KPAD + 3) & ~3) + 256 * kHd + 8 * 256) * static_cast<int>(sizeof(float)));
 }
 
-cudaError_t launch_attn_spatial(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int64_t n_groups,
-                                int J, cudaStream_t st) {
-  if (n_groups <= 0) return cudaSuccess;
-  if (J != SJ) return cudaErrorInvalidValue;
-  const int smem = kSpatialSmem;
-  attn_spatial_kernel<<<static_cast<unsigned>(n_groups), 256, smem, st>>>(qkv, o_hi, o_lo, o_f32, n_groups);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_attn_generic_simt(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int n_seq, int N,
+cudaError_t launch_attn_generic_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int n_seq, int N,
                                      int64_t outer, int inner, int64_t tok_stride, cudaStream_t st) {
   if (n_seq <= 0) return cudaSuccess;
   if (N < 1 || N > 256) return cudaErrorInvalidValue;
@@ -234,9 +131,17 @@ cudaError_t launch_attn_generic_simt(const float* qkv, __half* o_hi, __half* o_l
   return cudaGetLastError();
 }
 
-cudaError_t launch_attn_temporal_simt(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F, int J,
+cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F, int J,
                                       cudaStream_t st) {
   return launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, B * J, F, static_cast<int64_t>(F) * J, J, J, st);
+}
+
+cudaError_t launch_pack_qkv16(const float* qkv_f32, __half* out, int64_t T, cudaStream_t st) {
+  if (T <= 0) return cudaSuccess;
+  int64_t g = (T * 3 * kC + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  pack_qkv16_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(qkv_f32, out, T);
+  return cudaGetLastError();
 }
 
 }  // namespace d3d

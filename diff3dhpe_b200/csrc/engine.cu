@@ -62,7 +62,7 @@ struct d3d_handle {
 
   // workspace
   float* X = nullptr;
-  float* QKV = nullptr;
+  __half* QKV = nullptr;     // packed fp16 q | k | v_hi | v_lo, [tok_cap, 2048]
   OperandBuf A, ATT, H;
   float *in_x2d = nullptr, *y = nullptr, *in_noise = nullptr;
   int64_t in_noise_cap = 0;
@@ -179,6 +179,11 @@ int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
+int pick_cg(int N) {
+  const int cg = env_int("D3D_GEMM_CG", 2);
+  return (cg == 2 && N % 256 == 0) ? 2 : 1;
+}
+
 int pick_bn(const d3d_handle* h, int64_t M, int N) {
   int bn = env_int("D3D_GEMM_BN", 0);
   if (bn == 128 || bn == 256) return (N % bn == 0) ? bn : 128;
@@ -189,7 +194,7 @@ int pick_bn(const d3d_handle* h, int64_t M, int N) {
 
 // out = epilogue(Aop . W^T + bias)
 int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int epi, const float* residual,
-             float* out_f32, __half* out_hi, __half* out_lo, int mode, cudaStream_t st) {
+             float* out_f32, __half* out_hi, __half* out_lo, __half* out_qkv, int mode, cudaStream_t st) {
   GemmParams p;
   p.M = static_cast<int>(M);
   p.N = w.N;
@@ -199,17 +204,18 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   p.out_f32 = out_f32;
   p.out_hi = out_hi;
   p.out_lo = out_lo;
+  p.out_qkv = out_qkv;
   if (mode == D3D_GEMM_SIMT_FP32) {
     KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, st));
   } else {
     GemmMaps m;
     m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
-    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, mode == D3D_GEMM_TC_FP16 ? 1 : 3, pick_bn(h, M, w.N), h->num_sms, st));
+    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, mode == D3D_GEMM_TC_FP16 ? 1 : 3, pick_bn(h, M, w.N), pick_cg(w.N), h->num_sms, st));
   }
   return 0;
 }
 
-int run_attention(d3d_handle* h, const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, bool spatial,
+int run_attention(d3d_handle* h, const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, bool spatial,
                   int mode, cudaStream_t st) {
   if (spatial) {
     if (mode == D3D_ATTN_SIMT || h->J != 17)
@@ -271,12 +277,12 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
   for (int b = 0; b < n_blocks; ++b) {
     const Blk& k = h->blk[b];
     const bool spatial = (b % 2) == 0;
-    if ((r = run_gemm(h, h->A, k.qkv, T, EPI_F32, nullptr, h->QKV, nullptr, nullptr, gm, st))) return r;
+    if ((r = run_gemm(h, h->A, k.qkv, T, EPI_QKV16, nullptr, nullptr, nullptr, nullptr, h->QKV, gm, st))) return r;
     if ((r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial, am, st))) return r;
-    if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, gm, st))) return r;
+    if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
     KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, T, st));
-    if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, gm, st))) return r;
-    if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, gm, st))) return r;
+    if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, nullptr, gm, st))) return r;
+    if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
     if (b + 1 < n_blocks) {
       const LnParams post = spatial ? LnParams{h->sn_g, h->sn_b} : LnParams{h->tn_g, h->tn_b};
       const Blk& nx = h->blk[b + 1];
@@ -390,7 +396,7 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   h->blk.resize(h->nblk);
   const int64_t T = static_cast<int64_t>(cfg->max_clips) * h->F * h->J;
-  h->tok_cap = (T + 127) / 128 * 128;
+  h->tok_cap = (T + 255) / 256 * 256;
 
   auto body = [&]() -> int {
     int r;
@@ -421,7 +427,7 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
     if ((r = dev_alloc(h, &h->perm_dev, 64))) return r;
 
     if ((r = dev_alloc(h, &h->X, h->tok_cap * kC))) return r;
-    if ((r = dev_alloc(h, &h->QKV, h->tok_cap * 3 * kC))) return r;
+    if ((r = dev_alloc(h, &h->QKV, h->tok_cap * kQkvRow))) return r;
     if ((r = alloc_operand(h, &h->A, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->ATT, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->H, h->tok_cap, kHidden))) return r;
@@ -794,9 +800,12 @@ int d3d_op_layernorm(d3d_handle* h, const float* x, const float* gamma, const fl
 int d3d_op_attention(d3d_handle* h, const float* qkv, float* out, int32_t B, int32_t spatial, int32_t attn_mode,
                      void* stream) {
   if (!h || !qkv || !out) return -1;
-  if (B < 1) return fail(h, -2, "B < 1");
+  if (B < 1 || B > h->cfg.max_clips) return fail(h, -2, "B out of range [1, max_clips]");
   DeviceGuard guard(h->cfg.device);
-  return run_attention(h, qkv, nullptr, nullptr, out, B, spatial != 0, attn_mode, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the hot path receives q | k | v_hi | v_lo fp16 rows from the qkv GEMM epilogue; here they are packed from fp32
+  KL(launch_pack_qkv16(qkv, h->QKV, static_cast<int64_t>(B) * h->F * h->J, st));
+  return run_attention(h, h->QKV, nullptr, nullptr, out, B, spatial != 0, attn_mode, st);
 }
 
 int d3d_op_time_table(d3d_handle* h, const float* t_host, int32_t R, float* out, void* stream) {
@@ -833,7 +842,7 @@ cudaError_t tmp_alloc(OpLinearBufs& b, T** p, int64_t n) {
   return e;
 }
 int prep_op_linear(d3d_handle* h, OpLinearBufs& b, int64_t M, int N, int K, int act) {
-  const int64_t Mp = (M + 127) / 128 * 128;
+  const int64_t Mp = (M + 255) / 256 * 256;
   CK(tmp_alloc(b, &b.a.hi, Mp * K));
   CK(tmp_alloc(b, &b.a.lo, Mp * K));
   CK(tmp_alloc(b, &b.w.hi, static_cast<int64_t>(N) * K));
@@ -866,10 +875,10 @@ int d3d_op_linear(d3d_handle* h, const float* a, const float* w, const float* bi
   KL(launch_split(a, b.a.hi, b.a.lo, M * K, st));
   KL(launch_split(w, b.w.hi, b.w.lo, static_cast<int64_t>(N) * K, st));
   if (act) {
-    if ((r = run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, gemm_mode, st))) return r;
+    if ((r = run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st))) return r;
     KL(launch_merge(b.o_hi, b.o_lo, out, M * N, st));
   } else {
-    if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, out, nullptr, nullptr, gemm_mode, st))) return r;
+    if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, out, nullptr, nullptr, nullptr, gemm_mode, st))) return r;
   }
   CK(cudaStreamSynchronize(st));
   return 0;
@@ -901,8 +910,8 @@ int d3d_op_linear_bench(d3d_handle* h, int64_t M, int32_t N, int32_t K, int32_t 
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   auto once = [&]() -> int {
-    if (act) return run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, gemm_mode, st);
-    return run_gemm(h, b.a, b.w, M, EPI_F32, nullptr, fo, nullptr, nullptr, gemm_mode, st);
+    if (act) return run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st);
+    return run_gemm(h, b.a, b.w, M, EPI_F32, nullptr, fo, nullptr, nullptr, nullptr, gemm_mode, st);
   };
   for (int i = 0; i < 3; ++i)
     if ((r = once())) return r;

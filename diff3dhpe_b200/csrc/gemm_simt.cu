@@ -57,11 +57,16 @@ gemm_simt_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_l
       if (EPI == EPI_F32) {
         if (p.residual) v += p.residual[o];
         p.out_f32[o] = v;
-      } else {
+      } else if (EPI == EPI_GELU_SPLIT) {
         v = gelu_erf(v);
         const __half h = __float2half_rn(v);
         p.out_hi[o] = h;
         p.out_lo[o] = __float2half_rn(v - __half2float(h));
+      } else {   // EPI_QKV16
+        const size_t oq = static_cast<size_t>(gm) * kQkvRow + gn;
+        const __half h = __float2half_rn(v);
+        p.out_qkv[oq] = h;
+        if (gn >= 2 * kC) p.out_qkv[oq + kC] = __float2half_rn(v - __half2float(h));
       }
     }
   }
@@ -76,8 +81,10 @@ cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const __hal
   dim3 grid((p.M + TM - 1) / TM, p.N / TN);
   if (epi == EPI_F32)
     gemm_simt_kernel<EPI_F32><<<grid, 256, 0, st>>>(a_hi, a_lo, b_hi, b_lo, p);
-  else
+  else if (epi == EPI_GELU_SPLIT)
     gemm_simt_kernel<EPI_GELU_SPLIT><<<grid, 256, 0, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+  else
+    gemm_simt_kernel<EPI_QKV16><<<grid, 256, 0, st>>>(a_hi, a_lo, b_hi, b_lo, p);
   return cudaGetLastError();
 }
 

@@ -13,7 +13,13 @@ constexpr int kHd = 64;        // head_dim
 constexpr int kHidden = 1024;  // mlp hidden
 
 // ------------------------------------------------------------------ GEMM
-enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1 };
+// EPI_F32        out_f32[M,N] = acc + bias (+ residual)
+// EPI_GELU_SPLIT out_hi/out_lo[M,N] = split_fp16(gelu_erf(acc + bias))            (fc1 -> A operand of fc2)
+// EPI_QKV16      N == 1536: out_qkv[M, 2048] fp16 rows = q(512) | k(512) | v_hi(512) | v_lo(512)
+//                (q, k rounded to fp16; v kept as a hi/lo pair so that the GRAND "- V" term stays exact)
+enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_QKV16 = 2 };
+
+constexpr int kQkvRow = 4 * kC;   // halves per token row of the packed q|k|v_hi|v_lo tensor
 
 struct GemmParams {
   int M, N, K;
@@ -22,6 +28,7 @@ struct GemmParams {
   float* out_f32;         // EPI_F32
   __half* out_hi;         // EPI_GELU_SPLIT
   __half* out_lo;
+  __half* out_qkv;        // EPI_QKV16
 };
 
 // A: [M,K] fp16 (hi, lo), W: [N,K] fp16 (hi, lo); K-major.  Tensor maps use a {64, 128} box, SWIZZLE_128B.
@@ -29,9 +36,10 @@ struct GemmMaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-// passes: 3 (split) or 1 (fp16).  bn: 128 or 256 (N % bn == 0).
-cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int num_sms,
-                           cudaStream_t st);
+// passes: 3 (split) or 1 (fp16).  cta_group 1: one CTA per 128 x bn tile (bn 128 or 256, N % bn == 0);
+// cta_group 2: a CTA pair per 256 x 256 tile (tcgen05.mma.cta_group::2, N % 256 == 0, bn ignored).
+cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
+                           int num_sms, cudaStream_t st);
 cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
                              const GemmParams& p, int epi, cudaStream_t st);
 // One-time per-device kernel attribute setup (dynamic shared memory opt-in); call outside graph capture.
@@ -83,15 +91,19 @@ cudaError_t launch_mpjpe(const float* pred, const float* gt, const uint8_t* mask
                          double* acc, cudaStream_t st);
 
 // ------------------------------------------------------------------ attention
-cudaError_t launch_attn_spatial(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int64_t n_groups,
+// qkv: packed fp16 [T, 2048] rows q | k | v_hi | v_lo (EPI_QKV16).  Output [T,512]: split fp16 (o_hi/o_lo) or fp32.
+cudaError_t launch_attn_spatial(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int64_t n_groups,
                                 int J, cudaStream_t st);
-cudaError_t launch_attn_temporal_simt(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F,
-                                      int J, cudaStream_t st);
-cudaError_t launch_attn_temporal_mma(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F,
+cudaError_t launch_attn_temporal_mma(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F,
                                      int J, cudaStream_t st);
-cudaError_t launch_attn_generic_simt(const float* qkv, __half* o_hi, __half* o_lo, float* o_f32, int n_seq,
+// CUDA-core validation kernels (fp32 arithmetic on the same packed input)
+cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F,
+                                      int J, cudaStream_t st);
+cudaError_t launch_attn_generic_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int n_seq,
                                      int N, int64_t seq_stride_tokens_outer, int inner, int64_t tok_stride,
                                      cudaStream_t st);
+// fp32 [T,1536] -> packed fp16 [T,2048] (op-level test entry point)
+cudaError_t launch_pack_qkv16(const float* qkv_f32, __half* out, int64_t T, cudaStream_t st);
 
 // ------------------------------------------------------------------ time embedding
 // e[r, 0:256] = sin(t_r * f_i), e[r, 256:512] = cos(t_r * f_i)   (MODEL:29-36)

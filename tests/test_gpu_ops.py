@@ -22,10 +22,20 @@ def _rand(shape, seed, scale=1.0):
     return torch.randn(*shape, generator=g) * scale
 
 
-@pytest.mark.parametrize("mode,tol", [(_lib.GEMM_SIMT_FP32, 3e-6), (_lib.GEMM_TC_SPLIT3, 3e-6), (_lib.GEMM_TC_FP16, 2e-3)])
+@pytest.fixture(autouse=True)
+def _default_cta_group(monkeypatch):
+    monkeypatch.delenv("D3D_GEMM_CG", raising=False)
+    monkeypatch.delenv("D3D_GEMM_BN", raising=False)
+
+
+@pytest.mark.parametrize("mode,tol,cg", [(_lib.GEMM_SIMT_FP32, 3e-6, 2), (_lib.GEMM_TC_SPLIT3, 3e-6, 2),
+                                         (_lib.GEMM_TC_SPLIT3, 3e-6, 1), (_lib.GEMM_TC_FP16, 2e-3, 2),
+                                         (_lib.GEMM_TC_FP16, 2e-3, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 1536, 512), (200, 512, 512), (1000, 1024, 512), (459, 512, 1024),
-                                   (37 * 128 + 5, 256, 64)])
-def test_linear_parity(eng27, mode, tol, M, N, K):
+                                   (37 * 128 + 5, 256, 64), (1, 512, 512), (74 * 256 * 3 + 77, 512, 512)])
+def test_linear_parity(eng27, monkeypatch, mode, tol, cg, M, N, K):
+    """cg = tcgen05 cta_group: 2 = CTA-pair 256x256 tiles (the product path), 1 = single-CTA 128xBN tiles."""
+    monkeypatch.setenv("D3D_GEMM_CG", str(cg))
     a, w, b = _rand((M, K), 1), _rand((N, K), 2, 0.05), _rand((N,), 3, 0.1)
     res = _rand((M, N), 4)
     ref = (a.double() @ w.double().T + b.double() + res.double())
@@ -62,20 +72,25 @@ def test_layernorm(eng27, eps):
     assert (out - ref).abs().max().item() < 5e-6
 
 
-@pytest.mark.parametrize("F", [27, 81, 243, 9, 100])
-@pytest.mark.parametrize("mode", [_lib.ATTN_DEFAULT, _lib.ATTN_SIMT])
+@pytest.mark.parametrize("F", [27, 81, 243, 9, 100, 1, 256])
+@pytest.mark.parametrize("mode,tol", [(_lib.ATTN_DEFAULT, 4e-3), (_lib.ATTN_SIMT, 3e-5)])
 @pytest.mark.parametrize("spatial", [True, False])
-def test_attention_core(F, mode, spatial):
+def test_attention_core(F, mode, tol, spatial):
+    """The kernels read q, k as fp16 and v as an fp16 hi/lo pair (what the qkv GEMM epilogue writes), so the
+    reference gets the same fp16-rounded q, k.  SIMT mode (fp32 arithmetic) then matches to rounding; the
+    tensor-core mode additionally rounds P and the V operand of P.V to fp16 (single pass), tolerance 4e-3 on
+    outputs of magnitude ~4 -- the sampler-level effect is bounded by the golden tests."""
     B, J, C = 2, 17, 512
     eng = Engine(F, max_clips=B)
     qkv = _rand((B * F * J, 3 * C), 20 + F, 1.5)
+    qkv[:, :2 * C] = qkv[:, :2 * C].half().float()
     x = qkv.view(B, F, J, 3 * C)
     seqs = x.reshape(B * F, J, 3 * C) if spatial else x.permute(0, 2, 1, 3).reshape(B * J, F, 3 * C)
     ref = oracle.attention_core(seqs, 8)
     ref = ref.reshape(B, F, J, C) if spatial else ref.reshape(B, J, F, C).permute(0, 2, 1, 3)
     out = eng.op_attention(qkv.cuda(), B, spatial, mode).cpu().view(B, F, J, C)
     eng.close()
-    assert (out - ref).abs().max().item() < 2e-5
+    assert (out - ref).abs().max().item() < tol
 
 
 def test_time_table_golden(golden):
@@ -100,8 +115,9 @@ def test_residual_stream_after_blocks_golden(golden, gemm_mode):
     x1 = eng.debug_forward_blocks(x5, t, 1).cpu().numpy()[::8]
     x2 = eng.debug_forward_blocks(x5, t, 2).cpu().numpy()[::8]
     eng.close()
-    assert np.abs(x1 - g["x_after_1"]).max() < 5e-5
-    assert np.abs(x2 - g["x_after_2"]).max() < 1e-4
+    # q, k (and P, V inside P.V) are fp16 in the attention kernels: 1e-3-level effect on a stream of magnitude ~5
+    assert np.abs(x1 - g["x_after_1"]).max() < 4e-3
+    assert np.abs(x2 - g["x_after_2"]).max() < 4e-3
 
 
 def test_tta_merge_and_mpjpe_golden(eng27, golden):

@@ -2,7 +2,9 @@
 the golden vectors of the imported reference and the CPU oracle run live on the same seeded inputs.
 
 Tolerances (north star): per-joint max-abs error <= 1e-2 (pose scale 1) and MPJPE delta <= 0.1 mm = 1e-4.  The
-default 3-pass split-fp16 GEMM mode is asserted against a 10x tighter bound."""
+default mode (3-pass split-fp16 linears, single-pass fp16 attention with an exact "- V" term) is asserted against
+a 4x tighter bound; the CPU precision emulation (tools/precision_probe.py) predicts max-abs 6e-4 / 8e-4 / 1.5e-3
+at F = 27 / 81 / 243 with 9 steps."""
 import numpy as np
 import pytest
 import torch
@@ -13,6 +15,7 @@ from oracle import diff3d_oracle as oracle
 pytestmark = pytest.mark.gpu
 
 MAXABS_BAR, MPJPE_BAR = 1e-2, 1e-4
+MARGIN = 4.0
 
 
 def _diffusion(F, S, eta=0.0, clip=True, with_time_emb=True, gemm_mode=_lib.GEMM_TC_SPLIT3, attn_mode=_lib.ATTN_DEFAULT,
@@ -35,7 +38,7 @@ def test_forward_denoise_golden(golden, name, gemm_mode):
     x2d, _ = synthetic.make_inputs(B, F)
     y_T, _ = synthetic.make_noise(B, F, 1)
     out = diff.model.forward_denoise(torch.cat([x2d, y_T], -1).cuda(), torch.tensor(g["t"]).cuda()).cpu().numpy()
-    assert np.abs(out - g["out"]).max() < 1e-3
+    assert np.abs(out - g["out"]).max() < MAXABS_BAR / MARGIN
 
 
 @pytest.mark.parametrize("name", ["sampler_f27_b2_s3_clip", "sampler_f27_b2_s3_eta", "sampler_f27_b2_s2_notime",
@@ -51,16 +54,16 @@ def test_sampler_golden(golden, name, use_graph):
     trace = "rev" in g
     if trace:
         pred, rev, x0s = diff.ddim_sample_loop_ouput_reverse_diffusion(x2d.cuda(), [B, F, 17, 3], noise=noise)
-        assert np.abs(rev.cpu().numpy() - g["rev"]).max() < 1e-3
-        assert np.abs(x0s.cpu().numpy() - g["x0s"]).max() < 1e-3
+        assert np.abs(rev.cpu().numpy() - g["rev"]).max() < MAXABS_BAR / MARGIN
+        assert np.abs(x0s.cpu().numpy() - g["x0s"]).max() < MAXABS_BAR / MARGIN
     else:
         pred = diff.ddim_sample_loop(x2d.cuda(), [B, F, 17, 3], noise=noise)
         pred2 = diff.ddim_sample_loop(x2d.cuda(), [B, F, 17, 3], noise=noise)      # graph replay / determinism
         assert torch.equal(pred, pred2)
     pred = pred.cpu()
     ref = torch.from_numpy(g["pred"])
-    assert (pred - ref).abs().max().item() < MAXABS_BAR / 10
-    assert _mpjpe_delta(pred, ref, gt) < MPJPE_BAR / 10
+    assert (pred - ref).abs().max().item() < MAXABS_BAR / MARGIN
+    assert _mpjpe_delta(pred, ref, gt) < MPJPE_BAR / MARGIN
 
 
 def test_fp16_fast_mode_is_within_maxabs_bar(golden):
@@ -85,8 +88,8 @@ def test_forward_api_flip_tta_against_oracle():
     sd = {k: v.detach().cpu() for k, v in diff.model.state_dict().items()}
     with torch.no_grad():
         ref = oracle.sample_tta(sd, x2d, n1, n2, sampling_timesteps=S)
-    assert (merged - ref).abs().max().item() < MAXABS_BAR / 10
-    assert _mpjpe_delta(merged, ref, gt) < MPJPE_BAR / 10
+    assert (merged - ref).abs().max().item() < MAXABS_BAR / MARGIN
+    assert _mpjpe_delta(merged, ref, gt) < MPJPE_BAR / MARGIN
     # forward(): same signature / return convention as DIFF:421-449, and it consumes S normal draws in order
     torch.manual_seed(77)
     loss, pred = diff(clean_3d_pose=gt.cuda(), noisy_2d_pose=x2d.cuda(), output_loss=False)

@@ -22,16 +22,21 @@ def _imports():
     return torch, _lib, synthetic, Engine
 
 
-def _gemm(mode, M, N, K, bn, act=0):
+def _gemm(mode, M, N, K, bn, act=0, cg=2, residual=False):
     torch, _lib, synthetic, Engine = _imports()
     os.environ["D3D_GEMM_BN"] = str(bn)
+    os.environ["D3D_GEMM_CG"] = str(cg)
     eng = Engine(27, max_clips=1)
     g = torch.Generator().manual_seed(1)
     a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05, torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g) if residual else None
     ref = a.double() @ w.double().T + b.double()
+    if residual:
+        ref = ref + res.double()
     if act:
         ref = torch.nn.functional.gelu(ref)
-    out = eng.op_linear(a.cuda(), w.cuda(), b.cuda(), act=act, gemm_mode=mode).cpu().double()
+    out = eng.op_linear(a.cuda(), w.cuda(), b.cuda(), residual=res.cuda() if residual else None, act=act,
+                        gemm_mode=mode).cpu().double()
     err = (out - ref).abs()
     bad = (err > 1e-2).nonzero()
     return {"max_err": err.max().item(), "mean_err": err.mean().item(), "n_bad": int(bad.shape[0]),
@@ -44,33 +49,43 @@ def gemm_simt():
 
 
 @stage
-def gemm_tc_fp16_bn128():
-    return _gemm(1, 300, 512, 512, 128)
+def gemm_cg1_split3_bn256():
+    return _gemm(0, 5000, 1536, 512, 256, cg=1)
 
 
 @stage
-def gemm_tc_split3_bn128():
-    return _gemm(0, 300, 512, 512, 128)
+def gemm_cg1_residual_bn128():
+    return _gemm(0, 300, 512, 512, 128, cg=1, residual=True)
 
 
 @stage
-def gemm_tc_split3_bn256():
-    return _gemm(0, 5000, 1536, 512, 256)
+def gemm_cg2_split3_one_tile():
+    return _gemm(0, 256, 256, 64, 256, cg=2)
 
 
 @stage
-def gemm_tc_fp16_bn256_k1024():
-    return _gemm(1, 5000, 512, 1024, 256)
+def gemm_cg2_split3_small():
+    return _gemm(0, 300, 512, 512, 256, cg=2)
 
 
 @stage
-def gemm_tc_gelu_bn256():
-    return _gemm(0, 5000, 1024, 512, 256, act=1)
+def gemm_cg2_split3_residual():
+    return _gemm(0, 5000, 512, 1024, 256, cg=2, residual=True)
 
 
 @stage
-def gemm_tc_many_tiles():
-    return _gemm(0, 70000, 1536, 512, 256)
+def gemm_cg2_gelu():
+    return _gemm(0, 5000, 1024, 512, 256, act=1, cg=2)
+
+
+@stage
+def gemm_cg2_fp16():
+    return _gemm(1, 5000, 1536, 512, 256, cg=2)
+
+
+@stage
+def gemm_cg2_many_tiles():
+    return _gemm(0, 70001, 1536, 512, 256, cg=2, residual=True)
 
 
 def _attn(F, spatial, mode):
@@ -81,22 +96,24 @@ def _attn(F, spatial, mode):
     eng = Engine(F, max_clips=B)
     g = torch.Generator().manual_seed(5)
     qkv = torch.randn(B * F * J, 3 * C, generator=g) * 1.5
+    qkv[:, :2 * C] = qkv[:, :2 * C].half().float()      # the packed layout keeps q, k as fp16
     x = qkv.view(B, F, J, 3 * C)
     seqs = x.reshape(B * F, J, 3 * C) if spatial else x.permute(0, 2, 1, 3).reshape(B * J, F, 3 * C)
     ref = oracle.attention_core(seqs, 8)
     ref = ref.reshape(B, F, J, C) if spatial else ref.reshape(B, J, F, C).permute(0, 2, 1, 3)
     out = eng.op_attention(qkv.cuda(), B, spatial, mode).cpu().view(B, F, J, C)
-    return {"max_err": (out - ref).abs().max().item()}
-
-
-@stage
-def attn_spatial():
-    return _attn(27, True, 0)
+    err = (out - ref).abs()
+    return {"max_err": err.max().item(), "mean_err": err.mean().item(), "argmax": list(map(int, (err == err.max()).nonzero()[0]))}
 
 
 @stage
 def attn_spatial_simt():
     return _attn(27, True, 1)
+
+
+@stage
+def attn_spatial_mma():
+    return _attn(27, True, 0)
 
 
 @stage
@@ -114,9 +131,10 @@ def attn_temporal_mma_f243():
     return _attn(243, False, 0)
 
 
-def _sampler(gemm_mode, attn_mode, use_graph, name="sampler_f27_b2_s3_clip"):
+def _sampler(gemm_mode, attn_mode, use_graph, name="sampler_f27_b2_s3_clip", cg=2):
     torch, _lib, synthetic, Engine = _imports()
     import numpy as np
+    os.environ["D3D_GEMM_CG"] = str(cg)
     g = dict(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz")))
     F, B, S = int(g["F"]), int(g["B"]), int(g["S"])
     m = synthetic.make_model(F).cuda()
@@ -134,12 +152,17 @@ def sampler_simt_simt():
 
 
 @stage
-def sampler_tc_simtattn():
-    return _sampler(0, 1, False)
+def sampler_cg1_simtattn():
+    return _sampler(0, 1, False, cg=1)
 
 
 @stage
-def sampler_tc_default_graph():
+def sampler_cg2_simtattn():
+    return _sampler(0, 1, False, cg=2)
+
+
+@stage
+def sampler_default_graph():
     return _sampler(0, 0, True)
 
 
@@ -148,13 +171,58 @@ def sampler_f243():
     return _sampler(0, 0, True, "sampler_f243_b1_s1_clip")
 
 
+@stage
+def sampler_f9_s9():
+    return _sampler(0, 0, True, "sampler_f9_b2_s9_clip")
+
+
+@stage
+def bench_gemm():
+    """ms / launch of the GEMM kernel alone at the cfg3 half-batch size (M = 1 057 536 tokens)."""
+    torch, _lib, synthetic, Engine = _imports()
+    eng = Engine(27, max_clips=1)
+    out = {}
+    M = 1057536
+    for cg in (1, 2):
+        os.environ["D3D_GEMM_CG"] = str(cg)
+        os.environ["D3D_GEMM_BN"] = "256"
+        for mode, name, passes in ((_lib.GEMM_TC_SPLIT3, "split3", 3), (_lib.GEMM_TC_FP16, "fp16", 1)):
+            for N, K, act in ((1536, 512, 0), (512, 512, 0), (1024, 512, 1), (512, 1024, 0)):
+                ms = eng.op_linear_bench(M, N, K, act, mode, iters=5)
+                tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+                out[f"cg{cg}_{name}_N{N}_K{K}"] = [round(ms, 3), round(tf, 1), round(tf * passes, 1)]
+    return out
+
+
+@stage
+def bench_attention():
+    """ms / launch of the attention kernels at 128 clips x 243 frames (529 k tokens)."""
+    torch, _lib, synthetic, Engine = _imports()
+    B, F = 128, 243
+    eng = Engine(F, max_clips=B)
+    qkv = torch.randn(B * F * 17, 1536, device="cuda")
+    out = {}
+    for spatial in (True, False):
+        for _ in range(2):
+            eng.op_attention(qkv, B, spatial, 0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            eng.op_attention(qkv, B, spatial, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        out["spatial" if spatial else "temporal"] = round(e0.elapsed_time(e1) / 5, 3)    # includes the fp32->fp16 pack kernel
+    return out
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         print("RESULT " + json.dumps(STAGES[sys.argv[1]]()), flush=True)
         sys.exit(0)
     for name in STAGES:
         try:
-            p = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=300)
+            p = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=400)
             res = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             tail = (p.stderr.strip().splitlines() or [""])[-1][:300]
             print(f"{name:32s} rc={p.returncode} {res[0][7:] if res else 'NO RESULT: ' + tail}", flush=True)

@@ -1,0 +1,108 @@
+"""Predict the parity of a GEMM / attention operand-precision policy WITHOUT a GPU (SURVEY.md 7.4 recipe).
+
+A TorchFunctionMode intercepts F.linear (K >= 64) and torch.matmul while the CPU oracle's DDIM sampler runs,
+replaces the operands by their rounded / split versions and accumulates in fp32, then compares the result with
+the plain fp32 run on the same weights, inputs and noise.
+
+    python tools/precision_probe.py F B [S]
+
+Linear modes:
+  fp16      a_hi.b_hi                                             (1 fp16 pass)
+  split3    a_hi.b_hi + a_hi.b_lo + a_lo.b_hi                     (3 fp16 passes)
+  f8corr    a_hi.b_hi + 2^-16 (e4m3(a).e4m3(2^16 b_lo) + e4m3(2^12 a_lo).e4m3(2^4 b))   (1 fp16 + 2 fp8 passes)
+Attention modes: fp32 | fp16 | split3 | qk3pv1 (QK^T split3, PV single fp16 pass)
+"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+from torch.overrides import TorchFunctionMode
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from diff3dhpe_b200 import synthetic  # noqa: E402
+from oracle import diff3d_oracle as oracle  # noqa: E402
+
+
+def h16(x):
+    return x.to(torch.float16).float()
+
+
+def split16(x):
+    hi = h16(x)
+    return hi, h16(x - hi)
+
+
+def e4m3(x):
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+
+
+def mm_mode(a, bt, mode):
+    """a [.., M, K] @ bt [.., K, N] with operand rounding per mode, fp32 accumulate."""
+    if mode == "fp32":
+        return torch.matmul(a, bt)
+    ah, al = split16(a)
+    bh, bl = split16(bt)
+    if mode == "fp16":
+        return torch.matmul(ah, bh)
+    if mode == "split3":
+        return torch.matmul(ah, bh) + torch.matmul(ah, bl) + torch.matmul(al, bh)
+    if mode == "split2a":           # activations exact-ish, weights rounded
+        return torch.matmul(ah, bh) + torch.matmul(al, bh)
+    if mode == "f8corr":
+        corr = torch.matmul(e4m3(a), e4m3(bl * 65536.0)) + torch.matmul(e4m3(al * 4096.0), e4m3(bt * 16.0))
+        return torch.matmul(ah, bh) + corr * (1.0 / 65536.0)
+    raise ValueError(mode)
+
+
+class Policy(TorchFunctionMode):
+    def __init__(self, lin, attn):
+        super().__init__()
+        self.lin, self.attn = lin, attn
+        self.n_qk = 0
+
+    def __torch_function__(self, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func is F.linear and args[1].shape[1] >= 64 and self.lin != "fp32":
+            x, w = args[0], args[1]
+            b = args[2] if len(args) > 2 else kwargs.get("bias")
+            with torch._C.DisableTorchFunction():
+                out = mm_mode(x, w.t(), self.lin)
+                return out + b if b is not None else out
+        if func in (torch.matmul, torch.Tensor.matmul, torch.Tensor.__matmul__) and self.attn != "fp32":
+            a, b = args
+            with torch._C.DisableTorchFunction():
+                # oracle.attention_core: first matmul is q @ k^T, second is (p - I) @ v
+                is_qk = (self.n_qk % 2) == 0
+                self.n_qk += 1
+                if self.attn == "qk3pv1":
+                    return mm_mode(a, b, "split3" if is_qk else "fp16")
+                return mm_mode(a, b, self.attn)
+        return func(*args, **kwargs)
+
+
+def main():
+    Fr = int(sys.argv[1]) if len(sys.argv) > 1 else 27
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    S = int(sys.argv[3]) if len(sys.argv) > 3 else 9
+    torch.set_num_threads(os.cpu_count())
+    m = synthetic.make_model(Fr)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    x2d, gt = synthetic.make_inputs(B, Fr)
+    y_T, steps = synthetic.make_noise(B, Fr, S)
+    for clip in (False, True):
+        with torch.no_grad():
+            ref = oracle.ddim_sample_loop(sd, x2d, y_T, steps, sampling_timesteps=S, clip_denoised=clip)
+        print(f"F={Fr} B={B} S={S} clip_denoised={clip}  |ref|max={ref.abs().max():.3f}", flush=True)
+        for lin, attn in (("fp16", "fp16"), ("split3", "fp16"), ("split3", "split3"), ("f8corr", "fp16"),
+                          ("f8corr", "split3"), ("f8corr", "qk3pv1"), ("split2a", "split3")):
+            with torch.no_grad(), Policy(lin, attn):
+                out = oracle.ddim_sample_loop(sd, x2d, y_T, steps, sampling_timesteps=S, clip_denoised=clip)
+            err = (out - ref).abs()
+            dm = abs(oracle.mpjpe(out, gt).item() - oracle.mpjpe(ref, gt).item())
+            print(f"  linear={lin:8s} attn={attn:7s} max-abs {err.max():.3e}  mean-joint-L2 "
+                  f"{torch.norm(out - ref, dim=-1).mean():.3e}  |dMPJPE| {dm:.3e}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
