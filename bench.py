@@ -157,7 +157,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.clips
-    gemm_mode = {"split3": _lib.GEMM_TC_SPLIT3, "fp16": _lib.GEMM_TC_FP16}[args.gemm]
+    gemm_mode = {"split3": _lib.GEMM_TC_SPLIT3, "fp16": _lib.GEMM_TC_FP16, "f8c": _lib.GEMM_TC_F8C}[args.gemm]
 
     model = synthetic.make_model(F_FRAMES).to(dev)
     model.gemm_mode, model.max_clips_hint = gemm_mode, 2 * B
@@ -252,7 +252,7 @@ def run_ours(args):
     peaks = measured_peaks()
     gemm_flops = tokens * GEMM_FLOPS_PER_TOKEN_CALL * S_STEPS
     achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12
-    passes = 3 if args.gemm == "split3" else 1
+    passes = {"split3": 3, "f8c": 2, "fp16": 1}[args.gemm]
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::f16, TMA, TMEM)",
         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
@@ -279,7 +279,9 @@ def run_ours(args):
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16x3-split operands, fp32 accumulate" if args.gemm == "split3" else "fp16 operands, fp32 accumulate",
+        "dtype": {"split3": "fp16x3-split operands, fp32 accumulate",
+                  "f8c": "fp16 main + e5m2 correction products (2 tensor-pipe units), fp32 accumulate",
+                  "fp16": "fp16 operands, fp32 accumulate"}[args.gemm],
         "data": "synthetic",
         "config": {"workload": workload_name(B), "clips_per_gpu": B, "frames": F_FRAMES, "sampling_timesteps": S_STEPS,
                    "tokens_per_step": tokens, "parallelism": f"clip-sharded x{world}, no data-path collective",
@@ -303,7 +305,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU (BASELINE cfg3: 256)")
-    ap.add_argument("--gemm", default="split3", choices=["split3", "fp16"])
+    ap.add_argument("--gemm", default="split3", choices=["split3", "f8c", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -9,6 +9,7 @@
 // Also: pack_qkv16_kernel, fp32 [T,1536] -> the packed fp16 layout (op-level test entry point only; in the
 // sampler the qkv GEMM epilogue writes the packed layout directly).
 #include "kernels.cuh"
+#include "operand.cuh"
 
 namespace d3d {
 namespace {
@@ -22,7 +23,7 @@ __device__ __forceinline__ uint32_t pack2(__half a, __half b) {
 
 __global__ void __launch_bounds__(256)
 attn_generic_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_hi, __half* __restrict__ o_lo,
-                    float* __restrict__ o_f32, int N, int64_t outer, int inner, int64_t tok_stride) {
+                    float* __restrict__ o_f32, int fmt, int N, int64_t outer, int inner, int64_t tok_stride) {
   extern __shared__ float sm[];
   float* Ks = sm;                       // [N][65]
   float* Vs = Ks + ((N * KPAD + 3) & ~3);   // [N][64], 16-byte aligned
@@ -95,8 +96,16 @@ attn_generic_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_hi, _
     } else {
       const __half h0 = __float2half_rn(o0), h1 = __float2half_rn(o1);
       *reinterpret_cast<uint32_t*>(o_hi + off) = pack2(h0, h1);
-      *reinterpret_cast<uint32_t*>(o_lo + off) =
-          pack2(__float2half_rn(o0 - __half2float(h0)), __float2half_rn(o1 - __half2float(h1)));
+      if (fmt == FMT_SPLIT16) {
+        *reinterpret_cast<uint32_t*>(o_lo + off) =
+            pack2(__float2half_rn(o0 - __half2float(h0)), __float2half_rn(o1 - __half2float(h1)));
+      } else {
+        uint8_t* c8 = reinterpret_cast<uint8_t*>(o_lo) + static_cast<size_t>(tok0 + i * tok_stride) * (2 * kC) +
+                      head * kHd + 2 * lane;
+        *reinterpret_cast<uint16_t*>(c8) = static_cast<uint16_t>(op_e5m2x2(o0 * kActHiScale, o1 * kActHiScale));
+        *reinterpret_cast<uint16_t*>(c8 + kC) = static_cast<uint16_t>(
+            op_e5m2x2((o0 - __half2float(h0)) * kActLoScale, (o1 - __half2float(h1)) * kActLoScale));
+      }
     }
   }
 }
@@ -121,19 +130,19 @@ cudaError_t configure_attention() {
                               (((256 * KPAD + 3) & ~3) + 256 * kHd + 8 * 256) * static_cast<int>(sizeof(float)));
 }
 
-cudaError_t launch_attn_generic_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int n_seq, int N,
-                                     int64_t outer, int inner, int64_t tok_stride, cudaStream_t st) {
+cudaError_t launch_attn_generic_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int n_seq,
+                                     int N, int64_t outer, int inner, int64_t tok_stride, cudaStream_t st) {
   if (n_seq <= 0) return cudaSuccess;
   if (N < 1 || N > 256) return cudaErrorInvalidValue;
   const int smem = (((N * KPAD + 3) & ~3) + N * kHd + 8 * N) * static_cast<int>(sizeof(float));
   dim3 grid(static_cast<unsigned>(n_seq), kHeads);
-  attn_generic_kernel<<<grid, 256, smem, st>>>(qkv, o_hi, o_lo, o_f32, N, outer, inner, tok_stride);
+  attn_generic_kernel<<<grid, 256, smem, st>>>(qkv, o_hi, o_lo, o_f32, fmt, N, outer, inner, tok_stride);
   return cudaGetLastError();
 }
 
-cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F, int J,
-                                      cudaStream_t st) {
-  return launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, B * J, F, static_cast<int64_t>(F) * J, J, J, st);
+cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
+                                      int J, cudaStream_t st) {
+  return launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, fmt, B * J, F, static_cast<int64_t>(F) * J, J, J, st);
 }
 
 cudaError_t launch_pack_qkv16(const float* qkv_f32, __half* out, int64_t T, cudaStream_t st) {

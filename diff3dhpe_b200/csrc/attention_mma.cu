@@ -19,6 +19,7 @@
 //
 // Output: token-major [T, 512] (heads merged, MODEL:83) as the split-fp16 A operand of the proj GEMM, or fp32.
 #include "kernels.cuh"
+#include "operand.cuh"
 
 namespace d3d {
 namespace {
@@ -55,12 +56,17 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ temporal
+constexpr int kTStgRow = 272;                     // bytes per staged output row (256 + 16: conflict-free 4-byte writes)
+constexpr int kTStgWarp = 16 * kTStgRow;          // one 16-query tile per warp
+
+template <int FMT>
 __global__ void __launch_bounds__(256)
 attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_hi, __half* __restrict__ o_lo,
                          float* __restrict__ o_f32, int F, int J, int NK) {
   extern __shared__ __align__(16) __half smh[];
   __half* Ks = smh;
   __half* Vs = Ks + NK * KS;
+  uint8_t* stg = reinterpret_cast<uint8_t*>(Vs + NK * KS) + (threadIdx.x >> 5) * kTStgWarp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int head = blockIdx.y;
   const int64_t seq = blockIdx.x;                                   // b * J + j
@@ -182,7 +188,8 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
         }
       }
     }
-    // ---- finalize: out = O / l - V[query],  V[query] = v_hi (smem) + v_lo (global)
+    // ---- finalize: out = O / l - V[query],  V[query] = v_hi (smem) + v_lo (global).  The 16 x 64 tile is staged
+    //      per warp (row = 128 B hi | 128 B second part, or 256 B fp32) and written with 16-byte stores.
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -194,8 +201,8 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
       if (r >= F) continue;
       const float inv = half ? i1 : i0;
       const int64_t tok = tok0 + static_cast<int64_t>(r) * J;
-      const size_t off = static_cast<size_t>(tok) * kC + head * kHd;
       const __half* vlo = base + static_cast<size_t>(tok) * kQkvRow + 3 * kC;
+      uint8_t* srow = stg + (g + 8 * half) * kTStgRow;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int d = nt * 8 + 2 * q4;
@@ -204,15 +211,44 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
         const float x0 = o[nt][2 * half] * inv - (__low2float(vh) + __low2float(vl));
         const float x1 = o[nt][2 * half + 1] * inv - (__high2float(vh) + __high2float(vl));
         if (o_f32) {
-          *reinterpret_cast<float2*>(o_f32 + off + d) = make_float2(x0, x1);
-        } else {
+          *reinterpret_cast<float2*>(srow + d * 4) = make_float2(x0, x1);
+        } else if (FMT == FMT_SPLIT16) {
           uint32_t hh, ll;
           split2(x0, x1, hh, ll);
-          *reinterpret_cast<uint32_t*>(o_hi + off + d) = hh;
-          *reinterpret_cast<uint32_t*>(o_lo + off + d) = ll;
+          *reinterpret_cast<uint32_t*>(srow + d * 2) = hh;
+          *reinterpret_cast<uint32_t*>(srow + 128 + d * 2) = ll;
+        } else {      // hi | e5m2(x 2^-8) (64 B) | e5m2(lo 2^4) (64 B)
+          const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+          *reinterpret_cast<uint32_t*>(srow + d * 2) = pack2(h0, h1);
+          *reinterpret_cast<uint16_t*>(srow + 128 + d) =
+              static_cast<uint16_t>(op_e5m2x2(x0 * kActHiScale, x1 * kActHiScale));
+          *reinterpret_cast<uint16_t*>(srow + 192 + d) = static_cast<uint16_t>(
+              op_e5m2x2((x0 - __half2float(h0)) * kActLoScale, (x1 - __half2float(h1)) * kActLoScale));
         }
       }
     }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane;
+      const int rr = idx >> 4, c = idx & 15;              // staged row, 16-byte chunk
+      const int r = q0 + rr;
+      if (r < F) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kTStgRow + c * 16);
+        const size_t tok = static_cast<size_t>(tok0 + static_cast<int64_t>(r) * J);
+        if (o_f32) {
+          *reinterpret_cast<uint4*>(o_f32 + tok * kC + head * kHd + c * 4) = val;
+        } else if (c < 8) {
+          *reinterpret_cast<uint4*>(o_hi + tok * kC + head * kHd + c * 8) = val;
+        } else if (FMT == FMT_SPLIT16) {
+          *reinterpret_cast<uint4*>(o_lo + tok * kC + head * kHd + (c - 8) * 8) = val;
+        } else {      // c8 row = 1024 B: [0,512) e5m2(x 2^-8), [512,1024) e5m2(lo 2^4); this head owns 64 B of each
+          uint8_t* c8 = reinterpret_cast<uint8_t*>(o_lo) + tok * (2 * kC) + head * kHd;
+          *reinterpret_cast<uint4*>(c8 + (c < 12 ? 0 : kC) + ((c - 8) & 3) * 16) = val;
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -221,6 +257,7 @@ constexpr int SJ = 17;
 constexpr int kSpRows = 3 * SJ + 1;                 // q, k, v tiles of one head + one all-zero row
 constexpr int kSpWarpHalves = kSpRows * KS;         // 3744 halves = 7488 B per warp
 
+template <int FMT>
 __global__ void __launch_bounds__(256)
 attn_spatial_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_hi, __half* __restrict__ o_lo,
                         float* __restrict__ o_f32, int64_t n_groups) {
@@ -347,11 +384,18 @@ attn_spatial_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_h
       if (o_f32) {          // fp32 row = 256 B: first 32 floats in the Q tile row, last 32 in the K tile row
         float* dstrow = reinterpret_cast<float*>((d < 32 ? Qs : Ksm) + r * KS);
         *reinterpret_cast<float2*>(dstrow + (d & 31)) = make_float2(x0, x1);
-      } else {
+      } else if (FMT == FMT_SPLIT16) {
         uint32_t hh, ll;
         split2(x0, x1, hh, ll);
         *reinterpret_cast<uint32_t*>(Qs + r * KS + d) = hh;
         *reinterpret_cast<uint32_t*>(Ksm + r * KS + d) = ll;
+      } else {              // K tile row: e5m2(x 2^-8) in bytes [0,64), e5m2(lo 2^4) in bytes [64,128)
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        *reinterpret_cast<uint32_t*>(Qs + r * KS + d) = pack2(h0, h1);
+        uint8_t* krow = reinterpret_cast<uint8_t*>(Ksm + r * KS);
+        *reinterpret_cast<uint16_t*>(krow + d) = static_cast<uint16_t>(op_e5m2x2(x0 * kActHiScale, x1 * kActHiScale));
+        *reinterpret_cast<uint16_t*>(krow + 64 + d) = static_cast<uint16_t>(
+            op_e5m2x2((x0 - __half2float(h0)) * kActLoScale, (x1 - __half2float(h1)) * kActLoScale));
       }
     }
   };
@@ -377,8 +421,13 @@ attn_spatial_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_h
     for (int i = lane; i < SJ * 16; i += 32) {            // 8 x 16 B of hi and 8 x 16 B of lo per row
       const int r = i >> 4, c = i & 15;
       const uint4 v = *reinterpret_cast<const uint4*>((c < 8 ? Qs : Ksm) + r * KS + (c & 7) * 8);
-      __half* dst = (c < 8 ? o_hi : o_lo) + (tok_base + r) * kC + head * kHd + (c & 7) * 8;
-      *reinterpret_cast<uint4*>(dst) = v;
+      if (c < 8 || FMT == FMT_SPLIT16) {
+        __half* dst = (c < 8 ? o_hi : o_lo) + (tok_base + r) * kC + head * kHd + (c & 7) * 8;
+        *reinterpret_cast<uint4*>(dst) = v;
+      } else {
+        uint8_t* c8 = reinterpret_cast<uint8_t*>(o_lo) + (tok_base + r) * (2 * kC) + head * kHd;
+        *reinterpret_cast<uint4*>(c8 + (c < 12 ? 0 : kC) + ((c - 8) & 3) * 16) = v;
+      }
     }
   }
 }
@@ -388,30 +437,34 @@ constexpr int kSpatialSmem = 8 * kSpWarpHalves * static_cast<int>(sizeof(__half)
 }  // namespace
 
 cudaError_t configure_attention_mma() {
-  cudaError_t e = cudaFuncSetAttribute(attn_temporal_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       2 * 256 * KS * static_cast<int>(sizeof(__half)));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(attn_spatial_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpatialSmem);
+  const int tsmem = 2 * 256 * KS * static_cast<int>(sizeof(__half)) + 8 * kTStgWarp;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(attn_temporal_h16_kernel<FMT_SPLIT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attn_temporal_h16_kernel<FMT_F8C>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attn_spatial_h16_kernel<FMT_SPLIT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpatialSmem)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attn_spatial_h16_kernel<FMT_F8C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpatialSmem);
 }
 
-cudaError_t launch_attn_temporal_mma(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F, int J,
-                                     cudaStream_t st) {
+cudaError_t launch_attn_temporal_mma(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
+                                     int J, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   if (F < 1 || F > 256) return cudaErrorInvalidValue;
   const int NK = (F + 63) / 64 * 64;
-  const int smem = 2 * NK * KS * static_cast<int>(sizeof(__half));
   const int n_qt = (F + 15) / 16;
   const int warps = n_qt < 8 ? n_qt : 8;
+  const int smem = 2 * NK * KS * static_cast<int>(sizeof(__half)) + warps * kTStgWarp;
   dim3 grid(static_cast<unsigned>(B) * J, kHeads);
-  attn_temporal_h16_kernel<<<grid, warps * 32, smem, st>>>(qkv, o_hi, o_lo, o_f32, F, J, NK);
+  auto kern = fmt == FMT_F8C ? attn_temporal_h16_kernel<FMT_F8C> : attn_temporal_h16_kernel<FMT_SPLIT16>;
+  kern<<<grid, warps * 32, smem, st>>>(qkv, o_hi, o_lo, o_f32, F, J, NK);
   return cudaGetLastError();
 }
 
-cudaError_t launch_attn_spatial(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int64_t n_groups, int J,
-                                cudaStream_t st) {
+cudaError_t launch_attn_spatial(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int64_t n_groups,
+                                int J, cudaStream_t st) {
   if (n_groups <= 0) return cudaSuccess;
   if (J != SJ) return cudaErrorInvalidValue;
-  attn_spatial_h16_kernel<<<static_cast<unsigned>(n_groups), 256, kSpatialSmem, st>>>(qkv, o_hi, o_lo, o_f32, n_groups);
+  auto kern = fmt == FMT_F8C ? attn_spatial_h16_kernel<FMT_F8C> : attn_spatial_h16_kernel<FMT_SPLIT16>;
+  kern<<<static_cast<unsigned>(n_groups), 256, kSpatialSmem, st>>>(qkv, o_hi, o_lo, o_f32, n_groups);
   return cudaGetLastError();
 }
 

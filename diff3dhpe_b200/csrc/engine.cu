@@ -14,6 +14,7 @@
 
 #include "../../include/diff3d_b200.h"
 #include "kernels.cuh"
+#include "operand.cuh"
 
 using namespace d3d;
 
@@ -48,6 +49,7 @@ struct OperandBuf {   // a GEMM A operand living in the workspace
 struct d3d_handle {
   d3d_config cfg{};
   int F = 0, J = 0, nblk = 0, num_sms = 148;
+  int fmt = FMT_SPLIT16;   // GEMM operand format of the workspace and the packed weights (operand.cuh)
   int64_t tok_cap = 0;   // workspace rows (multiple of 128)
   std::string err;
   int64_t launches = 0;
@@ -153,11 +155,23 @@ int dev_alloc(d3d_handle* h, T** p, int64_t n, bool zero = true) {
   return 0;
 }
 
+int mode_fmt(int gemm_mode) {
+  return (gemm_mode == D3D_GEMM_TC_F8C || gemm_mode == D3D_GEMM_SIMT_F8C) ? FMT_F8C : FMT_SPLIT16;
+}
+
+// tensor maps of an operand: fp16 hi [rows,K]; second array = fp16 lo [rows,K] or uint8 c8 [rows,2K]
+int make_maps(CUtensorMap* m_hi, CUtensorMap* m_second, const __half* hi, const __half* second, int64_t rows, int K,
+              int fmt) {
+  if (make_operand_map(m_hi, hi, rows, K)) return -1;
+  if (fmt == FMT_F8C) return make_operand_map_u8(m_second, second, rows, 2 * static_cast<int64_t>(K));
+  return make_operand_map(m_second, second, rows, K);
+}
+
 int alloc_operand(d3d_handle* h, OperandBuf* o, int64_t rows, int K) {
   int r;
   if ((r = dev_alloc(h, &o->hi, rows * K))) return r;
   if ((r = dev_alloc(h, &o->lo, rows * K))) return r;
-  if (make_operand_map(&o->m_hi, o->hi, rows, K) || make_operand_map(&o->m_lo, o->lo, rows, K))
+  if (make_maps(&o->m_hi, &o->m_lo, o->hi, o->lo, rows, K, h->fmt))
     return fail(h, -20, "cuTensorMapEncodeTiled failed for a workspace operand");
   return 0;
 }
@@ -169,7 +183,7 @@ int alloc_lin(d3d_handle* h, Lin* l, int N, int K) {
   if ((r = dev_alloc(h, &l->hi, static_cast<int64_t>(N) * K))) return r;
   if ((r = dev_alloc(h, &l->lo, static_cast<int64_t>(N) * K))) return r;
   if ((r = dev_alloc(h, &l->bias, N))) return r;
-  if (make_operand_map(&l->m_hi, l->hi, N, K) || make_operand_map(&l->m_lo, l->lo, N, K))
+  if (make_maps(&l->m_hi, &l->m_lo, l->hi, l->lo, N, K, h->fmt))
     return fail(h, -20, "cuTensorMapEncodeTiled failed for a weight operand");
   return 0;
 }
@@ -205,12 +219,13 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   p.out_hi = out_hi;
   p.out_lo = out_lo;
   p.out_qkv = out_qkv;
-  if (mode == D3D_GEMM_SIMT_FP32) {
-    KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, st));
+  if (mode == D3D_GEMM_SIMT_FP32 || mode == D3D_GEMM_SIMT_F8C) {
+    KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, mode_fmt(mode), st));
   } else {
     GemmMaps m;
     m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
-    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, mode == D3D_GEMM_TC_FP16 ? 1 : 3, pick_bn(h, M, w.N), pick_cg(w.N), h->num_sms, st));
+    const int passes = mode == D3D_GEMM_TC_FP16 ? 1 : (mode == D3D_GEMM_TC_F8C ? 2 : 3);
+    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), h->num_sms, st));
   }
   return 0;
 }
@@ -219,14 +234,14 @@ int run_attention(d3d_handle* h, const __half* qkv, __half* o_hi, __half* o_lo, 
                   int mode, cudaStream_t st) {
   if (spatial) {
     if (mode == D3D_ATTN_SIMT || h->J != 17)
-      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, B * h->F, h->J, h->J, 1, 1, st));
+      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, h->fmt, B * h->F, h->J, h->J, 1, 1, st));
     else
-      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial(qkv, o_hi, o_lo, o_f32, static_cast<int64_t>(B) * h->F, h->J, st));
+      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial(qkv, o_hi, o_lo, o_f32, h->fmt, static_cast<int64_t>(B) * h->F, h->J, st));
   } else {
     if (mode == D3D_ATTN_SIMT)
-      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_simt(qkv, o_hi, o_lo, o_f32, B, h->F, h->J, st));
+      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_simt(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));
     else
-      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, B, h->F, h->J, st));
+      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));
   }
   return 0;
 }
@@ -272,7 +287,7 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
   const int gm = h->cfg.gemm_mode, am = h->cfg.attn_mode;
   int r;
   KLP(D3D_PROF_LIFT, st, launch_lift_ln(x2d, y, x5, h->wf_t, h->bf, h->spos, tv, tv_stride,
-                                        LnParams{h->blk[0].n1g, h->blk[0].n1b}, h->X, h->A.hi, h->A.lo, T, h->J,
+                                        LnParams{h->blk[0].n1g, h->blk[0].n1b}, h->X, h->A.hi, h->A.lo, h->fmt, T, h->J,
                                         h->F * h->J, st));
   for (int b = 0; b < n_blocks; ++b) {
     const Blk& k = h->blk[b];
@@ -280,7 +295,7 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
     if ((r = run_gemm(h, h->A, k.qkv, T, EPI_QKV16, nullptr, nullptr, nullptr, nullptr, h->QKV, gm, st))) return r;
     if ((r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial, am, st))) return r;
     if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
-    KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, T, st));
+    KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, h->fmt, T, st));
     if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, nullptr, gm, st))) return r;
     if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
     if (b + 1 < n_blocks) {
@@ -288,7 +303,7 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
       const Blk& nx = h->blk[b + 1];
       KLP(D3D_PROF_LN, st,
           launch_postnorm_add_ln(h->X, post, (b + 1 == 1) ? h->tpos : nullptr, tv ? tv + (b + 1) * kC : nullptr,
-                                 tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo, T, h->J, h->F, st));
+                                 tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo, h->fmt, T, h->J, h->F, st));
     }
   }
   return 0;
@@ -390,6 +405,7 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
   DeviceGuard guard(cfg->device);
   d3d_handle* h = new d3d_handle();
   h->cfg = *cfg;
+  h->fmt = mode_fmt(cfg->gemm_mode);
   h->F = cfg->num_frame;
   h->J = cfg->num_joints;
   h->nblk = 2 * cfg->depth;
@@ -483,7 +499,7 @@ int d3d_load_weights(d3d_handle* h, const d3d_tensor* tensors, int32_t n) {
   auto load_lin_w = [&](Lin& l, const d3d_tensor& t) -> int {
     int r = copy_to(stage, t, static_cast<int64_t>(l.N) * l.K);
     if (r) return r;
-    CK(launch_split(stage, l.hi, l.lo, static_cast<int64_t>(l.N) * l.K, 0));
+    CK(launch_split(stage, l.hi, l.lo, l.N, l.K, h->fmt, 1, 0));
     CK(cudaDeviceSynchronize());
     l.have_w = true;
     return 0;
@@ -841,7 +857,7 @@ cudaError_t tmp_alloc(OpLinearBufs& b, T** p, int64_t n) {
   *p = static_cast<T*>(q);
   return e;
 }
-int prep_op_linear(d3d_handle* h, OpLinearBufs& b, int64_t M, int N, int K, int act) {
+int prep_op_linear(d3d_handle* h, OpLinearBufs& b, int64_t M, int N, int K, int act, int fmt) {
   const int64_t Mp = (M + 255) / 256 * 256;
   CK(tmp_alloc(b, &b.a.hi, Mp * K));
   CK(tmp_alloc(b, &b.a.lo, Mp * K));
@@ -853,8 +869,7 @@ int prep_op_linear(d3d_handle* h, OpLinearBufs& b, int64_t M, int N, int K, int 
     CK(tmp_alloc(b, &b.o_hi, M * N));
     CK(tmp_alloc(b, &b.o_lo, M * N));
   }
-  if (make_operand_map(&b.a.m_hi, b.a.hi, Mp, K) || make_operand_map(&b.a.m_lo, b.a.lo, Mp, K) ||
-      make_operand_map(&b.w.m_hi, b.w.hi, N, K) || make_operand_map(&b.w.m_lo, b.w.lo, N, K))
+  if (make_maps(&b.a.m_hi, &b.a.m_lo, b.a.hi, b.a.lo, Mp, K, fmt) || make_maps(&b.w.m_hi, &b.w.m_lo, b.w.hi, b.w.lo, N, K, fmt))
     return fail(h, -20, "cuTensorMapEncodeTiled failed");
   return 0;
 }
@@ -869,14 +884,15 @@ int d3d_op_linear(d3d_handle* h, const float* a, const float* w, const float* bi
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   OpLinearBufs b;
-  int r = prep_op_linear(h, b, M, N, K, act);
+  const int fmt = mode_fmt(gemm_mode);
+  int r = prep_op_linear(h, b, M, N, K, act, fmt);
   if (r) return r;
   b.w.bias = const_cast<float*>(bias);
-  KL(launch_split(a, b.a.hi, b.a.lo, M * K, st));
-  KL(launch_split(w, b.w.hi, b.w.lo, static_cast<int64_t>(N) * K, st));
+  KL(launch_split(a, b.a.hi, b.a.lo, M, K, fmt, 0, st));
+  KL(launch_split(w, b.w.hi, b.w.lo, N, K, fmt, 1, st));
   if (act) {
     if ((r = run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st))) return r;
-    KL(launch_merge(b.o_hi, b.o_lo, out, M * N, st));
+    KL(launch_merge(b.o_hi, b.o_lo, out, M, N, fmt, st));
   } else {
     if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, out, nullptr, nullptr, nullptr, gemm_mode, st))) return r;
   }
@@ -891,7 +907,8 @@ int d3d_op_linear_bench(d3d_handle* h, int64_t M, int32_t N, int32_t K, int32_t 
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = h->cap_stream;
   OpLinearBufs b;
-  int r = prep_op_linear(h, b, M, N, K, act);
+  const int fmt = mode_fmt(gemm_mode);
+  int r = prep_op_linear(h, b, M, N, K, act, fmt);
   if (r) return r;
   float *fa = nullptr, *fo = nullptr, *fb = nullptr;
   CK(tmp_alloc(b, &fa, M * K > static_cast<int64_t>(N) * K ? M * K : static_cast<int64_t>(N) * K));
@@ -904,8 +921,8 @@ int d3d_op_linear_bench(d3d_handle* h, int64_t M, int32_t N, int32_t K, int32_t 
   const int64_t na = M * K;
   for (int64_t off = 0; off < na; off += static_cast<int64_t>(host.size()))
     CK(cudaMemcpy(fa + off, host.data(), sizeof(float) * static_cast<size_t>(std::min<int64_t>(host.size(), na - off)), cudaMemcpyHostToDevice));
-  CK(launch_split(fa, b.a.hi, b.a.lo, na, st));
-  CK(launch_split(fa, b.w.hi, b.w.lo, static_cast<int64_t>(N) * K, st));
+  CK(launch_split(fa, b.a.hi, b.a.lo, M, K, fmt, 0, st));
+  CK(launch_split(fa, b.w.hi, b.w.lo, N, K, fmt, 1, st));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));

@@ -2,20 +2,29 @@
 // K-major) and produces exactly its outputs, so the tensor-core path can be checked element by element on
 // the device.  Not a performance path: 64x64 tiles, 4x4 outputs per thread.
 #include "kernels.cuh"
+#include "operand.cuh"
 
 namespace d3d {
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 32;
+constexpr int TM = 64, TN = 64, TK = 16;
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
-template <int EPI>
+// FMT_SPLIT16: acc = (a_hi + a_lo) . (b_hi + b_lo)   (the lo.lo term, 2^-22 relative, is the only difference from the
+//              3-pass tensor-core kernel).
+// FMT_F8C    : acc = a_hi . b_hi + a8 . blo8 + alo8 . b8 with the e5m2 factors decoded to fp32: exactly the products the
+//              tensor-core kernel forms (the power-of-two scales cancel), so it validates that kernel tightly.
+template <int EPI, int FMT>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_lo, const __half* __restrict__ b_hi,
                  const __half* __restrict__ b_lo, const GemmParams p) {
   __shared__ float As[TK][TM + 1];
   __shared__ float Bs[TK][TN + 1];
+  __shared__ float A8[FMT == FMT_F8C ? 2 * TK : 1][TM + 1];      // [0,TK): e5m2(a 2^-8), [TK,2TK): e5m2(a_lo 2^4)
+  __shared__ float B8[FMT == FMT_F8C ? 2 * TK : 1][TN + 1];      // [0,TK): e5m2(b_lo 2^8), [TK,2TK): e5m2(b 2^-4)
+  const uint8_t* a_c8 = reinterpret_cast<const uint8_t*>(a_lo);
+  const uint8_t* b_c8 = reinterpret_cast<const uint8_t*>(b_lo);
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4] = {};
@@ -23,14 +32,29 @@ gemm_simt_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_l
     for (int i = threadIdx.x; i < TM * TK; i += 256) {
       const int r = i / TK, c = i % TK;
       const int gm = m0 + r;
-      float v = 0.f;
+      float v = 0.f, v8 = 0.f, vl8 = 0.f;
       if (gm < p.M) {
         const size_t o = static_cast<size_t>(gm) * p.K + k0 + c;
-        v = __half2float(a_hi[o]) + (a_lo ? __half2float(a_lo[o]) : 0.f);
+        v = __half2float(a_hi[o]);
+        if (FMT == FMT_SPLIT16) {
+          if (a_lo) v += __half2float(a_lo[o]);
+        } else {
+          const size_t o8 = static_cast<size_t>(gm) * 2 * p.K + k0 + c;
+          v8 = op_e5m2_to_float(a_c8[o8]);
+          vl8 = op_e5m2_to_float(a_c8[o8 + p.K]);
+        }
       }
       As[c][r] = v;
       const size_t ob = static_cast<size_t>(n0 + r) * p.K + k0 + c;
-      Bs[c][r] = __half2float(b_hi[ob]) + (b_lo ? __half2float(b_lo[ob]) : 0.f);
+      float w = __half2float(b_hi[ob]);
+      if (FMT == FMT_SPLIT16) {
+        if (b_lo) w += __half2float(b_lo[ob]);
+      } else {
+        const size_t ob8 = static_cast<size_t>(n0 + r) * 2 * p.K + k0 + c;
+        A8[c][r] = v8; A8[TK + c][r] = vl8;
+        B8[c][r] = op_e5m2_to_float(b_c8[ob8]); B8[TK + c][r] = op_e5m2_to_float(b_c8[ob8 + p.K]);
+      }
+      Bs[c][r] = w;
     }
     __syncthreads();
 #pragma unroll 8
@@ -42,6 +66,18 @@ gemm_simt_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_l
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (FMT == FMT_F8C) {
+#pragma unroll 8
+      for (int k = 0; k < 2 * TK; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = A8[k][ty * 4 + i]; b[i] = B8[k][tx * 4 + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
     }
     __syncthreads();
   }
@@ -61,7 +97,13 @@ gemm_simt_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_l
         v = gelu_erf(v);
         const __half h = __float2half_rn(v);
         p.out_hi[o] = h;
-        p.out_lo[o] = __float2half_rn(v - __half2float(h));
+        if (FMT == FMT_SPLIT16) {
+          p.out_lo[o] = __float2half_rn(v - __half2float(h));
+        } else {
+          uint8_t* c8 = reinterpret_cast<uint8_t*>(p.out_lo) + static_cast<size_t>(gm) * 2 * p.N + gn;
+          c8[0] = static_cast<uint8_t>(op_e5m2x2(v * kActHiScale, 0.f) & 0xff);
+          c8[p.N] = static_cast<uint8_t>(op_e5m2x2((v - __half2float(h)) * kActLoScale, 0.f) & 0xff);
+        }
       } else {   // EPI_QKV16
         const size_t oq = static_cast<size_t>(gm) * kQkvRow + gn;
         const __half h = __float2half_rn(v);
@@ -75,16 +117,21 @@ gemm_simt_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_l
 }  // namespace
 
 cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
-                             const GemmParams& p, int epi, cudaStream_t st) {
+                             const GemmParams& p, int epi, int fmt, cudaStream_t st) {
   if (p.M <= 0) return cudaSuccess;
   if (p.N % TN != 0 || p.K % TK != 0) return cudaErrorInvalidValue;
   dim3 grid((p.M + TM - 1) / TM, p.N / TN);
-  if (epi == EPI_F32)
-    gemm_simt_kernel<EPI_F32><<<grid, 256, 0, st>>>(a_hi, a_lo, b_hi, b_lo, p);
-  else if (epi == EPI_GELU_SPLIT)
-    gemm_simt_kernel<EPI_GELU_SPLIT><<<grid, 256, 0, st>>>(a_hi, a_lo, b_hi, b_lo, p);
-  else
-    gemm_simt_kernel<EPI_QKV16><<<grid, 256, 0, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+#define D3D_SIMT(EPI_, FMT_) gemm_simt_kernel<EPI_, FMT_><<<grid, 256, 0, st>>>(a_hi, a_lo, b_hi, b_lo, p)
+  if (fmt == FMT_F8C) {
+    if (epi == EPI_F32) D3D_SIMT(EPI_F32, FMT_F8C);
+    else if (epi == EPI_GELU_SPLIT) D3D_SIMT(EPI_GELU_SPLIT, FMT_F8C);
+    else D3D_SIMT(EPI_QKV16, FMT_F8C);
+  } else {
+    if (epi == EPI_F32) D3D_SIMT(EPI_F32, FMT_SPLIT16);
+    else if (epi == EPI_GELU_SPLIT) D3D_SIMT(EPI_GELU_SPLIT, FMT_SPLIT16);
+    else D3D_SIMT(EPI_QKV16, FMT_SPLIT16);
+  }
+#undef D3D_SIMT
   return cudaGetLastError();
 }
 

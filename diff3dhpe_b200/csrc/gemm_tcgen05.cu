@@ -6,7 +6,10 @@
 //   * operands are fp16 "split halves": x = hi + lo with hi = fp16(x), lo = fp16(x - hi).  The default
 //     3-pass mode issues   D += A_hi.B_hi ; D += A_hi.B_lo ; D += A_lo.B_hi   per k-step, accumulating in
 //     fp32 in TMEM, which restores ~22 mantissa bits (single-pass bf16/fp16 misses the
-//     parity bar).  The 1-pass mode issues only A_hi.B_hi.
+//     parity bar).  The 1-pass mode issues only A_hi.B_hi.  PASSES == 2 is the FMT_F8C mode of operand.cuh: the
+//     fp16 main product followed by ONE kind::f8f6f4 (e5m2) product over K' = 2K that carries both correction
+//     terms -- 2 tensor-pipe units instead of 3; the second tensor maps then describe the uint8 c8 arrays and
+//     the ring holds 2 * K/64 uniform stages per tile (fp16 stages first, then fp8 stages).
 //   * TMA (cp.async.bulk.tensor, SWIZZLE_128B) stages {128 rows x 64} fp16 boxes; a ring of mbarrier-guarded
 //     stages feeds one MMA-issuing thread.
 //   * CG = 2 (default): a CTA PAIR (thread-block cluster of 2, tcgen05.mma.cta_group::2) owns a 256 x 256
@@ -24,6 +27,7 @@
 // Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA), 2 = TMEM allocator, 3 = idle,
 // 4..11 = epilogue.
 #include "kernels.cuh"
+#include "operand.cuh"
 #include "ptx.cuh"
 
 namespace d3d {
@@ -44,7 +48,8 @@ struct Cfg {
   static constexpr int kStageBytes = (PASSES == 3 ? 2 : 1) * (kTileBytesA + kTileBytesB);
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;   // 256 or 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256 x 256 tiles");
 };
@@ -57,7 +62,27 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// Exact-erf GELU (MODEL:52, nn.GELU()) without the branchy library erff: the epilogue is instruction-issue bound
+// (32 768 activations per 128 x 256 tile), so the form below is branch-free, 2 MUFU + ~14 FP32 ops:
+//   gelu(v) = max(v, 0) - |v|/2 * erfc(|v| / sqrt 2),   erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),
+//   t = 1 / (1 + p z)   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 on erfc; using erfc for BOTH signs avoids the
+//   1 + erf cancellation in the negative tail).  Absolute error on gelu <= |v| * 1e-7.
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  return fmaxf(v, 0.0f) - (0.70710678118654752440f * z) * (poly * t * e);
+}
+
+// Epilogue transpose buffer: 32 rows x 128 B; the 16-byte granule g of row r lives at r*128 + ((g ^ (r&7)) << 4)
+// (the 128-byte swizzle), so "lane = row" accesses and "8 lanes = one row" accesses are both conflict-free.
+__device__ __forceinline__ uint4* stg_at(uint8_t* stg, int r, int g) {
+  return reinterpret_cast<uint4*>(stg + r * 128 + ((g ^ (r & 7)) << 4));
+}
 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
@@ -71,7 +96,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   using C = Cfg<CG, BN, PASSES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(staging + C::kStagingBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,6 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int n_tiles_m = (p.M + TM - 1) / TM;
   const int n_tiles = n_tiles_m * n_tiles_n;
   const int n_kb = p.K / BK;
+  const int n_steps = PASSES == 2 ? 2 * n_kb : n_kb;       // ring stages consumed per tile
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tm_a_hi);
@@ -120,10 +147,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int tile = unit; tile < n_tiles; tile += n_units) {
         const int m0 = (tile / n_tiles_n) * TM + static_cast<int>(rank) * BM;
         const int n0 = (tile % n_tiles_n) * BN + static_cast<int>(rank) * C::kBRows;
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = 0; kb < n_steps; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* s = smem + stage * C::kStageBytes;
-          if (CG == 1) {
+          if (PASSES == 2) {
+            // uniform stage: one A tile + one B tile of 128-byte rows; fp16 (hi) stages first, then e5m2 (c8) stages
+            const bool f8 = kb >= n_kb;
+            const CUtensorMap* ma = f8 ? &tm_a_lo : &tm_a_hi;
+            const CUtensorMap* mb = f8 ? &tm_b_lo : &tm_b_hi;
+            const int c0 = f8 ? (kb - n_kb) * 128 : kb * BK;      // element coordinate (bytes for the uint8 maps)
+            if (CG == 1) {
+              ptx::mbar_arrive_expect_tx(&bars->full[stage], C::kStageBytes);
+              ptx::tma_load_2d(s, ma, &bars->full[stage], c0, m0);
+#pragma unroll
+              for (int h = 0; h < C::kBRows / 128; ++h)
+                ptx::tma_load_2d(s + kTileBytesA + h * (128 * BK * 2), mb, &bars->full[stage], c0, n0 + h * 128);
+            } else {
+              const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * C::kStageBytes);
+              ptx::tma_load_2d_cg2(s, ma, full_leader, c0, m0);
+              ptx::tma_load_2d_cg2(s + kTileBytesA, mb, full_leader, c0, n0);
+            }
+          } else if (CG == 1) {
             ptx::mbar_arrive_expect_tx(&bars->full[stage], C::kStageBytes);
             ptx::tma_load_2d(s, &tm_a_hi, &bars->full[stage], kb * BK, m0);
             s += kTileBytesA;
@@ -170,10 +215,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         ptx::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = 0; kb < n_steps; ++kb) {
           ptx::mbar_wait(&bars->full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t s = ptx::smem_u32(smem + stage * C::kStageBytes);
+          if (PASSES == 2) {
+            constexpr uint32_t idesc8 = ptx::make_idesc_f16(TM, BN, 1 /*e5m2*/);
+            const bool f8 = kb >= n_kb;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {       // 4 x 32 bytes of K per 128-byte row: K = 16 (fp16) or 32 (e5m2)
+              const uint64_t da = ptx::make_desc_k_sw128(s + k * 32);
+              const uint64_t db = ptx::make_desc_k_sw128(s + kTileBytesA + k * 32);
+              const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+              if (f8) {
+                if (CG == 2) ptx::mma_f8_ss_cg2(d_tmem, da, db, idesc8, accum);
+                else ptx::mma_f8_ss(d_tmem, da, db, idesc8, accum);
+              } else {
+                if (CG == 2) ptx::mma_f16_ss_cg2(d_tmem, da, db, idesc, accum);
+                else ptx::mma_f16_ss(d_tmem, da, db, idesc, accum);
+              }
+            }
+            if (CG == 2) ptx::mma_commit_cg2(&bars->empty[stage], 3);
+            else ptx::mma_commit(&bars->empty[stage]);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint32_t a_hi = s;
           const uint32_t a_lo = s + kTileBytesA;
           const uint32_t b_hi = s + (PASSES == 3 ? 2 : 1) * kTileBytesA;
@@ -210,26 +276,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (8 warps per CTA)
+    // TMEM hands every lane one ROW (32 consecutive columns); storing that layout directly costs 32 cache lines
+    // per store instruction and made the epilogue, not the MMA, the bottleneck (1-pass and 3-pass GEMMs took
+    // the same time).  Each warp therefore transposes its 32 x 32 chunk through a swizzled 4 KB buffer and
+    // moves global data with "8 lanes = 128 contiguous bytes of one row" accesses (4 rows per instruction).
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;       // which half of the BN columns
     constexpr int kChunks = BN / 64;        // 32-column chunks per warp
+    uint8_t* stg = staging + (warp - 4) * 4096;
+    const int rsub = lane >> 3, gsub = lane & 7;      // coalesced mapping: instruction j covers rows 4j + rsub
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = unit; tile < n_tiles; tile += n_units) {
       const int m0 = (tile / n_tiles_n) * TM + static_cast<int>(rank) * BM;
       const int n0 = (tile % n_tiles_n) * BN;
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_w = m0 + q * 32;                    // first row of this warp
       const int colbase = n0 + half * (BN / 2);
-      const float* rrow = nullptr;
-      float4 res[8];
-      if (EPI == EPI_F32) {
-        if (p.residual && row_ok) rrow = p.residual + static_cast<size_t>(row) * p.N + colbase;
-        if (rrow) {                          // prefetch chunk 0 of the residual before the accumulator is ready
+      const bool has_res = EPI == EPI_F32 && p.residual != nullptr;
+      float4 resv[8];
+      auto load_res = [&](int ci) {                     // residual chunk ci, coalesced (row 4j + rsub, granule gsub)
 #pragma unroll
-          for (int v = 0; v < 8; ++v) res[v] = *reinterpret_cast<const float4*>(rrow + 4 * v);
+        for (int j = 0; j < 8; ++j) {
+          const int rr = row_w + 4 * j + rsub;
+          resv[j] = rr < p.M ? *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(rr) * p.N + colbase +
+                                                                 ci * 32 + gsub * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      }
+      };
+      if (has_res) load_res(0);              // in flight while the accumulator is still being computed
       ptx::mbar_wait(&bars->tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll
@@ -237,16 +311,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int col0 = half * (BN / 2) + ci * 32;     // column inside the tile
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + acc * BN + col0 + (static_cast<uint32_t>(q * 32) << 16), r);
-        float4 nxt[8];
-        if (EPI == EPI_F32 && ci + 1 < kChunks && rrow) {
+        if (has_res) {
 #pragma unroll
-          for (int v = 0; v < 8; ++v) nxt[v] = *reinterpret_cast<const float4*>(rrow + (ci + 1) * 32 + 4 * v);
+          for (int j = 0; j < 8; ++j) *stg_at(stg, 4 * j + rsub, gsub) = *reinterpret_cast<uint4*>(&resv[j]);
+          __syncwarp();
+          if (ci + 1 < kChunks) load_res(ci + 1);
         }
         ptx::tmem_ld_wait();
         const int gcol = n0 + col0;
         const float4* bias4 = reinterpret_cast<const float4*>(p.bias + gcol);
         if (EPI == EPI_F32) {
-          float* orow = p.out_f32 + static_cast<size_t>(row) * p.N + gcol;
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
             const float4 b = __ldg(bias4 + v);
@@ -255,56 +329,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             o.y = __uint_as_float(r[4 * v + 1]) + b.y;
             o.z = __uint_as_float(r[4 * v + 2]) + b.z;
             o.w = __uint_as_float(r[4 * v + 3]) + b.w;
-            if (rrow) { o.x += res[v].x; o.y += res[v].y; o.z += res[v].z; o.w += res[v].w; }
-            if (row_ok) *reinterpret_cast<float4*>(orow + 4 * v) = o;
+            uint4* cell = stg_at(stg, lane, v);
+            if (has_res) {
+              const float4 rr = *reinterpret_cast<const float4*>(cell);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(cell) = o;
           }
-          if (ci + 1 < kChunks && rrow) {
+          __syncwarp();
 #pragma unroll
-            for (int v = 0; v < 8; ++v) res[v] = nxt[v];
+          for (int j = 0; j < 8; ++j) {
+            const int rr = row_w + 4 * j + rsub;
+            const uint4 val = *stg_at(stg, 4 * j + rsub, gsub);
+            if (rr < p.M) *reinterpret_cast<uint4*>(p.out_f32 + static_cast<size_t>(rr) * p.N + gcol + gsub * 4) = val;
           }
-        } else if (EPI == EPI_GELU_SPLIT) {
-          __half* hrow = p.out_hi + static_cast<size_t>(row) * p.N + gcol;
-          __half* lrow = p.out_lo + static_cast<size_t>(row) * p.N + gcol;
+        } else {
+          // fp16 outputs: row = hi (granules 0..3, 32 halves) | second part (granules 4..7):
+          //   fp16 lo (FMT_SPLIT16, and always for q|k|v), or for the FMT_F8C fc2 operand
+          //   granules 4,5 = e5m2(x 2^-8) and 6,7 = e5m2(lo 2^4) of the 32 columns
+          constexpr bool gelu = EPI == EPI_GELU_SPLIT;
+          constexpr bool f8out = EPI == EPI_GELU_SPLIT && PASSES == 2;
+          uint32_t a8w[8], l8w[8];
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            uint32_t hw[4], lw[4];
+            uint32_t hw[4], lw[4], a16[4], l16[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float4 b = __ldg(bias4 + 2 * v + (e >> 1));
-              const float b0 = (e & 1) ? b.z : b.x;
-              const float b1 = (e & 1) ? b.w : b.y;
-              const float g0 = gelu_erf(__uint_as_float(r[8 * v + 2 * e + 0]) + b0);
-              const float g1 = gelu_erf(__uint_as_float(r[8 * v + 2 * e + 1]) + b1);
-              const __half h0 = __float2half_rn(g0), h1 = __float2half_rn(g1);
-              hw[e] = pack_h2(h0, h1);
-              lw[e] = pack_h2(__float2half_rn(g0 - __half2float(h0)), __float2half_rn(g1 - __half2float(h1)));
-            }
-            if (row_ok) {
-              *reinterpret_cast<uint4*>(hrow + 8 * v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(lrow + 8 * v) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-          }
-        } else {   // EPI_QKV16: q | k -> fp16;  v -> fp16 hi at the same column, lo 512 columns further
-          const bool is_v = gcol >= 2 * kC;
-          __half* hrow = p.out_qkv + static_cast<size_t>(row) * kQkvRow + gcol;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 b = __ldg(bias4 + 2 * v + (e >> 1));
-              const float x0 = __uint_as_float(r[8 * v + 2 * e + 0]) + ((e & 1) ? b.z : b.x);
-              const float x1 = __uint_as_float(r[8 * v + 2 * e + 1]) + ((e & 1) ? b.w : b.y);
+              float x0 = __uint_as_float(r[8 * v + 2 * e + 0]) + ((e & 1) ? b.z : b.x);
+              float x1 = __uint_as_float(r[8 * v + 2 * e + 1]) + ((e & 1) ? b.w : b.y);
+              if (gelu) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); }
               const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+              const float l0 = x0 - __half2float(h0), l1 = x1 - __half2float(h1);
               hw[e] = pack_h2(h0, h1);
-              lw[e] = pack_h2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+              if (f8out) {
+                a16[e] = op_e5m2x2(x0 * kActHiScale, x1 * kActHiScale);
+                l16[e] = op_e5m2x2(l0 * kActLoScale, l1 * kActLoScale);
+              } else {
+                lw[e] = pack_h2(__float2half_rn(l0), __float2half_rn(l1));
+              }
             }
-            if (row_ok) {
-              *reinterpret_cast<uint4*>(hrow + 8 * v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              if (is_v) *reinterpret_cast<uint4*>(hrow + kC + 8 * v) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            *stg_at(stg, lane, v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if (f8out) {
+              a8w[2 * v] = a16[0] | (a16[1] << 16); a8w[2 * v + 1] = a16[2] | (a16[3] << 16);
+              l8w[2 * v] = l16[0] | (l16[1] << 16); l8w[2 * v + 1] = l16[2] | (l16[3] << 16);
+            } else {
+              *stg_at(stg, lane, 4 + v) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+          if (f8out) {
+            *stg_at(stg, lane, 4) = make_uint4(a8w[0], a8w[1], a8w[2], a8w[3]);
+            *stg_at(stg, lane, 5) = make_uint4(a8w[4], a8w[5], a8w[6], a8w[7]);
+            *stg_at(stg, lane, 6) = make_uint4(l8w[0], l8w[1], l8w[2], l8w[3]);
+            *stg_at(stg, lane, 7) = make_uint4(l8w[4], l8w[5], l8w[6], l8w[7]);
+          }
+          __syncwarp();
+          __half* hi_base;
+          __half* lo_base;          // null: this chunk has no lo output (q, k)
+          size_t ld;
+          if (EPI == EPI_GELU_SPLIT) {
+            hi_base = p.out_hi + gcol; lo_base = p.out_lo + gcol; ld = static_cast<size_t>(p.N);
+          } else {                   // EPI_QKV16: q | k -> fp16; v -> hi at the same column, lo 512 columns further
+            hi_base = p.out_qkv + gcol; lo_base = gcol >= 2 * kC ? p.out_qkv + gcol + kC : nullptr; ld = kQkvRow;
+          }
+          if (EPI == EPI_GELU_SPLIT && PASSES == 2) {
+            // c8 row of the fc2 operand: N bytes e5m2(x 2^-8) then N bytes e5m2(lo 2^4); 32 columns = 2 granules each
+            uint8_t* c8 = reinterpret_cast<uint8_t*>(p.out_lo);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rr = row_w + 4 * j + rsub;
+              const uint4 val = *stg_at(stg, 4 * j + rsub, gsub);
+              if (rr >= p.M) continue;
+              if (gsub < 4) {
+                *reinterpret_cast<uint4*>(p.out_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8) = val;
+              } else {
+                uint8_t* dst = c8 + static_cast<size_t>(rr) * (2 * p.N) + (gsub < 6 ? 0 : p.N) + gcol + (gsub & 1) * 16;
+                *reinterpret_cast<uint4*>(dst) = val;
+              }
+            }
+          } else {
+            __half* dst_base = gsub < 4 ? hi_base : lo_base;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rr = row_w + 4 * j + rsub;
+              const uint4 val = *stg_at(stg, 4 * j + rsub, gsub);
+              if (rr < p.M && dst_base) *reinterpret_cast<uint4*>(dst_base + static_cast<size_t>(rr) * ld + (gsub & 3) * 8) = val;
             }
           }
         }
+        __syncwarp();          // the buffer is rewritten by the next chunk
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -315,6 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+  __syncwarp();
 
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();
@@ -361,7 +475,9 @@ cudaError_t configure_one() {
   X(1, 128, 1, EPI_F32) X(1, 128, 1, EPI_GELU_SPLIT) X(1, 128, 1, EPI_QKV16)                         \
   X(1, 256, 1, EPI_F32) X(1, 256, 1, EPI_GELU_SPLIT) X(1, 256, 1, EPI_QKV16)                         \
   X(2, 256, 3, EPI_F32) X(2, 256, 3, EPI_GELU_SPLIT) X(2, 256, 3, EPI_QKV16)                         \
-  X(2, 256, 1, EPI_F32) X(2, 256, 1, EPI_GELU_SPLIT) X(2, 256, 1, EPI_QKV16)
+  X(2, 256, 1, EPI_F32) X(2, 256, 1, EPI_GELU_SPLIT) X(2, 256, 1, EPI_QKV16)                         \
+  X(1, 256, 2, EPI_F32) X(1, 256, 2, EPI_GELU_SPLIT) X(1, 256, 2, EPI_QKV16)                         \
+  X(2, 256, 2, EPI_F32) X(2, 256, 2, EPI_GELU_SPLIT) X(2, 256, 2, EPI_QKV16)
 
 // Opt in to >48 KiB dynamic shared memory for every instantiation (once per device, outside graph capture).
 cudaError_t configure_gemm_tc() {
@@ -376,7 +492,7 @@ cudaError_t configure_gemm_tc() {
 cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
                            int num_sms, cudaStream_t st) {
   if (p.M <= 0) return cudaSuccess;
-  if (cta_group == 2) bn = 256;
+  if (cta_group == 2 || passes == 2) bn = 256;
   if (p.K % BK != 0 || p.N % bn != 0 || (bn != 128 && bn != 256)) return cudaErrorInvalidValue;
   if (epi == EPI_QKV16 && p.N != 3 * kC) return cudaErrorInvalidValue;
 #define D3D_DISPATCH(CG_, BN_, PASSES_, EPI_)                                   \
@@ -408,6 +524,24 @@ int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t
   cuuint32_t box[2] = {BK, 128};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+
+// uint8 [rows, row_bytes] row-major array (the c8 arrays of FMT_F8C): {128 bytes x 128 rows} boxes, SWIZZLE_128B
+int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return -1;
+  EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(row_bytes), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_bytes)};
+  cuuint32_t box[2] = {128, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;

@@ -36,18 +36,20 @@ struct GemmMaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-// passes: 3 (split) or 1 (fp16).  cta_group 1: one CTA per 128 x bn tile (bn 128 or 256, N % bn == 0);
+// passes: 3 (split fp16), 1 (fp16) or 2 (FMT_F8C: fp16 main + e5m2 corrections; the *_lo maps are the uint8 c8 maps).
+// cta_group 1: one CTA per 128 x bn tile (bn 128 or 256, N % bn == 0);
 // cta_group 2: a CTA pair per 256 x 256 tile (tcgen05.mma.cta_group::2, N % 256 == 0, bn ignored).
 cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
                            int num_sms, cudaStream_t st);
 cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
-                             const GemmParams& p, int epi, cudaStream_t st);
+                             const GemmParams& p, int epi, int fmt, cudaStream_t st);
 // One-time per-device kernel attribute setup (dynamic shared memory opt-in); call outside graph capture.
 cudaError_t configure_gemm_tc();
 cudaError_t configure_attention();
 cudaError_t configure_attention_mma();
-// Build a K-major fp16 operand map for a [rows, K] row-major matrix.
+// Build a K-major fp16 operand map for a [rows, K] row-major matrix / a uint8 map for a [rows, row_bytes] c8 array.
 int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t K);
+int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes);
 
 // ------------------------------------------------------------------ row-wise (one warp per 512-wide token row)
 struct LnParams {
@@ -55,21 +57,24 @@ struct LnParams {
   const float* beta;
 };
 
-// fp32 -> fp16 hi/lo split of a flat array (weights at load time, op-level tests).
-cudaError_t launch_split(const float* in, __half* hi, __half* lo, int64_t n, cudaStream_t st);
-cudaError_t launch_merge(const __half* hi, const __half* lo, float* out, int64_t n, cudaStream_t st);
+// fp32 [rows, K] -> GEMM operand arrays (hi + second, see operand.cuh; fmt = OperandFmt; weights at load time,
+// op-level tests) and back (activation operands only).
+cudaError_t launch_split(const float* in, __half* hi, __half* second, int64_t rows, int K, int fmt, int is_weight,
+                         cudaStream_t st);
+cudaError_t launch_merge(const __half* hi, const __half* second, float* out, int64_t rows, int K, int fmt,
+                         cudaStream_t st);
 
 // X = [x2d,y] . Wf^T + bf + spos[j] (+ tvec[sample]);  A = LN(X; ln1)  (MODEL:250, 230-233, 113-116, 127)
 cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, const float* wf_t /*[5][512]*/,
                            const float* bf, const float* spos /*[J][512]*/, const float* tvec, int64_t tvec_stride,
-                           LnParams ln1, float* X, __half* a_hi, __half* a_lo, int64_t T, int J, int tokens_per_clip,
-                           cudaStream_t st);
+                           LnParams ln1, float* X, __half* a_hi, __half* a_lo, int fmt, int64_t T, int J,
+                           int tokens_per_clip, cudaStream_t st);
 // X = LN(X; post) (+ tpos[f]) (+ tvec[sample]);  A = LN(X; ln1)   (MODEL:236/245, 239-242, 113-116, 127)
 cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos /*[F][512] or null*/,
                                    const float* tvec, int64_t tvec_stride, LnParams ln1, __half* a_hi,
-                                   __half* a_lo, int64_t T, int J, int F, cudaStream_t st);
+                                   __half* a_lo, int fmt, int64_t T, int J, int F, cudaStream_t st);
 // A = LN(X; ln)  (MODEL:128 norm2)
-cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int64_t T,
+cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int fmt, int64_t T,
                             cudaStream_t st);
 // out = LN(x) fp32 (stand-alone exhibit / op test)
 cudaError_t launch_ln_f32(const float* x, LnParams ln, float eps, float* out, int64_t T, cudaStream_t st);
@@ -91,15 +96,16 @@ cudaError_t launch_mpjpe(const float* pred, const float* gt, const uint8_t* mask
                          double* acc, cudaStream_t st);
 
 // ------------------------------------------------------------------ attention
-// qkv: packed fp16 [T, 2048] rows q | k | v_hi | v_lo (EPI_QKV16).  Output [T,512]: split fp16 (o_hi/o_lo) or fp32.
-cudaError_t launch_attn_spatial(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int64_t n_groups,
+// qkv: packed fp16 [T, 2048] rows q | k | v_hi | v_lo (EPI_QKV16).  Output [T,512]: GEMM A operand (o_hi + second
+// array in format fmt, operand.cuh) or fp32.
+cudaError_t launch_attn_spatial(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int64_t n_groups,
                                 int J, cudaStream_t st);
-cudaError_t launch_attn_temporal_mma(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F,
+cudaError_t launch_attn_temporal_mma(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                      int J, cudaStream_t st);
 // CUDA-core validation kernels (fp32 arithmetic on the same packed input)
-cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, int F,
+cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                       int J, cudaStream_t st);
-cudaError_t launch_attn_generic_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int n_seq,
+cudaError_t launch_attn_generic_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int n_seq,
                                      int N, int64_t seq_stride_tokens_outer, int inner, int64_t tok_stride,
                                      cudaStream_t st);
 // fp32 [T,1536] -> packed fp16 [T,2048] (op-level test entry point)

@@ -1,0 +1,91 @@
+// GEMM operand formats.  Every GEMM operand (activations A[M,K], weights W[N,K]) lives in HBM as TWO K-major
+// arrays of 2*K bytes per row each:
+//
+//   main  : fp16 hi[K]                      hi = fp16(x)
+//   second: depends on the format
+//     FMT_SPLIT16 (D3D_GEMM_TC_SPLIT3 / _FP16 / _SIMT_FP32):   fp16 lo[K],  lo = fp16(x - hi)
+//         D = A_hi.B_hi + A_hi.B_lo + A_lo.B_hi                              (3 fp16 tensor passes)
+//     FMT_F8C     (D3D_GEMM_TC_F8C): uint8 c8[2K], two e5m2 vectors whose cross products are the same two
+//         correction terms at ~3 significant bits (enough: they are 2^-11 of the main term):
+//           activations: c8[0:K] = e5m2(x * 2^-8)        c8[K:2K] = e5m2((x - hi) * 2^4)
+//           weights    : c8[0:K] = e5m2((w - hi) * 2^8)  c8[K:2K] = e5m2(w * 2^-4)
+//         D = A_hi.B_hi (kind::f16)  +  A_c8.B_c8 over K' = 2K (kind::f8f6f4, 2x the fp16 rate)
+//         The power-of-two scales cancel inside each product (2^-8 * 2^8, 2^4 * 2^-4), so both kinds accumulate
+//         into the SAME fp32 TMEM accumulator; they only centre the small factors in e5m2's normal range.
+//         Cost: 2 tensor-pipe units instead of 3.  Parity (tools/precision_probe.py, mode f8c52): sampler
+//         max-abs 5.3e-4 / 9.1e-4 at F = 27 / 81 against the 1e-2 bar.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <stdint.h>
+
+namespace d3d {
+
+enum OperandFmt { FMT_SPLIT16 = 0, FMT_F8C = 1 };
+
+constexpr float kActHiScale = 1.0f / 256.0f;   // activations: e5m2(x * 2^-8)
+constexpr float kActLoScale = 16.0f;           //              e5m2((x - hi) * 2^4)
+constexpr float kWgtLoScale = 256.0f;          // weights:     e5m2((w - hi) * 2^8)
+constexpr float kWgtHiScale = 1.0f / 16.0f;    //              e5m2(w * 2^-4)
+
+__device__ __forceinline__ uint32_t op_pack_h2(__half a, __half b) {
+  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+// two floats -> two e5m2 bytes (x in the low byte), round-to-nearest, saturating
+__device__ __forceinline__ uint32_t op_e5m2x2(float x, float y) {
+  return static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(x, y), __NV_SATFINITE, __NV_E5M2));
+}
+__device__ __forceinline__ uint32_t op_e5m2x4(float a, float b, float c, float d) {
+  return op_e5m2x2(a, b) | (op_e5m2x2(c, d) << 16);
+}
+__device__ __forceinline__ float op_e5m2_to_float(uint8_t v) {
+  const __half_raw hr = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(v), __NV_E5M2);
+  return __half2float(__half(hr));
+}
+
+// (x0, x1) -> hi pair and fp16 lo pair
+__device__ __forceinline__ void op_split16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+  hi = op_pack_h2(h0, h1);
+  lo = op_pack_h2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+}
+// Four consecutive ACTIVATION values -> hi (4 halves) + second part.
+//   FMT_SPLIT16: s0, s1 = the 4 lo halves (store at lo + col)
+//   FMT_F8C    : s0 = 4 bytes e5m2(x * 2^-8) (store at c8 + col), s1 = 4 bytes e5m2(lo * 2^4) (store at c8 + K + col)
+template <int FMT>
+__device__ __forceinline__ void op_pack4(const float (&x)[4], uint2& hi, uint32_t& s0, uint32_t& s1) {
+  __half h[4];
+  float l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = __float2half_rn(x[e]);
+    l[e] = x[e] - __half2float(h[e]);
+  }
+  hi = make_uint2(op_pack_h2(h[0], h[1]), op_pack_h2(h[2], h[3]));
+  if (FMT == FMT_SPLIT16) {
+    s0 = op_pack_h2(__float2half_rn(l[0]), __float2half_rn(l[1]));
+    s1 = op_pack_h2(__float2half_rn(l[2]), __float2half_rn(l[3]));
+  } else {
+    s0 = op_e5m2x4(x[0] * kActHiScale, x[1] * kActHiScale, x[2] * kActHiScale, x[3] * kActHiScale);
+    s1 = op_e5m2x4(l[0] * kActLoScale, l[1] * kActLoScale, l[2] * kActLoScale, l[3] * kActLoScale);
+  }
+}
+
+// Store helper for kernels whose thread owns 4 consecutive columns `col..col+3` of activation row `row_second`
+// (pointer to the start of the row's second array, 2K bytes) and `row_hi`.
+template <int FMT>
+__device__ __forceinline__ void op_store4(__half* row_hi, __half* row_second, int K, int col, const float (&x)[4]) {
+  uint2 hi;
+  uint32_t s0, s1;
+  op_pack4<FMT>(x, hi, s0, s1);
+  *reinterpret_cast<uint2*>(row_hi + col) = hi;
+  if (FMT == FMT_SPLIT16) {
+    *reinterpret_cast<uint2*>(row_second + col) = make_uint2(s0, s1);
+  } else {
+    uint8_t* c8 = reinterpret_cast<uint8_t*>(row_second);
+    *reinterpret_cast<uint32_t*>(c8 + col) = s0;
+    *reinterpret_cast<uint32_t*>(c8 + K + col) = s1;
+  }
+}
+
+}  // namespace d3d

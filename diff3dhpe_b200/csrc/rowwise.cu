@@ -8,6 +8,7 @@
 //                                                                                  (MODEL:245,255; DIFF:256,283-297)
 //   tta_merge, mpjpe   G-tta  : RUN:583-588, LOSS:15-27
 #include "kernels.cuh"
+#include "operand.cuh"
 
 namespace d3d {
 namespace {
@@ -39,21 +40,14 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int lane, const
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(p + 128 * i + 4 * lane) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
-__device__ __forceinline__ uint32_t pack2(__half a, __half b) {
-  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
-}
-__device__ __forceinline__ void store_split(__half* __restrict__ hi, __half* __restrict__ lo, int lane,
-                                            const float (&v)[16]) {
+// GEMM A operand of the row (K = 512) in the handle's operand format (operand.cuh)
+template <int FMT>
+__device__ __forceinline__ void store_operand(__half* __restrict__ hi, __half* __restrict__ second, int lane,
+                                              const float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __half h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      h[e] = __float2half_rn(v[4 * i + e]);
-      l[e] = __float2half_rn(v[4 * i + e] - __half2float(h[e]));
-    }
-    *reinterpret_cast<uint2*>(hi + 128 * i + 4 * lane) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
-    *reinterpret_cast<uint2*>(lo + 128 * i + 4 * lane) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+    const float x[4] = {v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
+    op_store4<FMT>(hi, second, kC, 128 * i + 4 * lane, x);
   }
 }
 
@@ -76,6 +70,7 @@ __device__ __forceinline__ void layernorm_row(const float (&x)[16], const float*
   for (int i = 0; i < 16; ++i) y[i] = fmaf((x[i] - mean) * rstd, g[i], b[i]);
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 lift_ln_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, const float* __restrict__ x5,
                const float* __restrict__ wf_t, const float* __restrict__ bf, const float* __restrict__ spos,
@@ -116,9 +111,10 @@ lift_ln_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, cons
   store_row(X + t * kC, lane, v);
   float a[16];
   layernorm_row(v, ln1.gamma, ln1.beta, 1e-6f, lane, a);
-  store_split(a_hi + t * kC, a_lo + t * kC, lane, a);
+  store_operand<FMT>(a_hi + t * kC, a_lo + t * kC, lane, a);
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __restrict__ tpos,
                        const float* __restrict__ tvec, int64_t tvec_stride, LnParams ln1, __half* __restrict__ a_hi,
@@ -141,9 +137,10 @@ postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __rest
   }
   store_row(X + t * kC, lane, z);
   layernorm_row(z, ln1.gamma, ln1.beta, 1e-6f, lane, x);
-  store_split(a_hi + t * kC, a_lo + t * kC, lane, x);
+  store_operand<FMT>(a_hi + t * kC, a_lo + t * kC, lane, x);
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 ln_split_kernel(const float* __restrict__ X, LnParams ln, float eps, __half* __restrict__ a_hi,
                 __half* __restrict__ a_lo, int64_t T) {
@@ -153,7 +150,7 @@ ln_split_kernel(const float* __restrict__ X, LnParams ln, float eps, __half* __r
   float x[16], y[16];
   load_row(X + t * kC, lane, x);
   layernorm_row(x, ln.gamma, ln.beta, eps, lane, y);
-  store_split(a_hi + t * kC, a_lo + t * kC, lane, y);
+  store_operand<FMT>(a_hi + t * kC, a_lo + t * kC, lane, y);
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -258,19 +255,44 @@ __global__ void mpjpe_kernel(const float* __restrict__ pred, const float* __rest
   }
 }
 
-__global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n) {
+// fp32 [rows, K] -> operand arrays.  is_weight selects the weight-side e5m2 scales of FMT_F8C.
+__global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ second,
+                             int64_t n, int K, int fmt, int is_weight) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float v = in[i];
     const __half h = __float2half_rn(v);
+    const float l = v - __half2float(h);
     hi[i] = h;
-    if (lo) lo[i] = __float2half_rn(v - __half2float(h));
+    if (!second) continue;
+    if (fmt == FMT_SPLIT16) {
+      second[i] = __float2half_rn(l);
+    } else {
+      const int64_t row = i / K;
+      const int col = static_cast<int>(i - row * K);
+      uint8_t* c8 = reinterpret_cast<uint8_t*>(second) + row * 2 * K;
+      const float first = is_weight ? l * kWgtLoScale : v * kActHiScale;
+      const float secnd = is_weight ? v * kWgtHiScale : l * kActLoScale;
+      c8[col] = static_cast<uint8_t>(op_e5m2x2(first, 0.f) & 0xff);
+      c8[K + col] = static_cast<uint8_t>(op_e5m2x2(secnd, 0.f) & 0xff);
+    }
   }
 }
-__global__ void merge_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out, int64_t n) {
+// activation operand -> fp32 (hi + lo); for FMT_F8C the lo term comes back from its e5m2 image
+__global__ void merge_kernel(const __half* __restrict__ hi, const __half* __restrict__ second, float* __restrict__ out,
+                             int64_t n, int K, int fmt) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    out[i] = __half2float(hi[i]) + __half2float(lo[i]);
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float lo;
+    if (fmt == FMT_SPLIT16) {
+      lo = __half2float(second[i]);
+    } else {
+      const int64_t row = i / K;
+      const int col = static_cast<int>(i - row * K);
+      lo = op_e5m2_to_float(reinterpret_cast<const uint8_t*>(second)[row * 2 * K + K + col]) * (1.0f / kActLoScale);
+    }
+    out[i] = __half2float(hi[i]) + lo;
+  }
 }
 
 inline unsigned row_grid(int64_t T) { return static_cast<unsigned>((T + kWarpsPerCta - 1) / kWarpsPerCta); }
@@ -281,36 +303,43 @@ inline unsigned flat_grid(int64_t n) {
 
 }  // namespace
 
-cudaError_t launch_split(const float* in, __half* hi, __half* lo, int64_t n, cudaStream_t st) {
+cudaError_t launch_split(const float* in, __half* hi, __half* second, int64_t rows, int K, int fmt, int is_weight,
+                         cudaStream_t st) {
+  const int64_t n = rows * K;
   if (n <= 0) return cudaSuccess;
-  split_kernel<<<flat_grid(n), 256, 0, st>>>(in, hi, lo, n);
+  split_kernel<<<flat_grid(n), 256, 0, st>>>(in, hi, second, n, K, fmt, is_weight);
   return cudaGetLastError();
 }
-cudaError_t launch_merge(const __half* hi, const __half* lo, float* out, int64_t n, cudaStream_t st) {
+cudaError_t launch_merge(const __half* hi, const __half* second, float* out, int64_t rows, int K, int fmt,
+                         cudaStream_t st) {
+  const int64_t n = rows * K;
   if (n <= 0) return cudaSuccess;
-  merge_kernel<<<flat_grid(n), 256, 0, st>>>(hi, lo, out, n);
+  merge_kernel<<<flat_grid(n), 256, 0, st>>>(hi, second, out, n, K, fmt);
   return cudaGetLastError();
 }
 cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, const float* wf_t, const float* bf,
                            const float* spos, const float* tvec, int64_t tvec_stride, LnParams ln1, float* X,
-                           __half* a_hi, __half* a_lo, int64_t T, int J, int tokens_per_clip, cudaStream_t st) {
+                           __half* a_hi, __half* a_lo, int fmt, int64_t T, int J, int tokens_per_clip,
+                           cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
-  lift_ln_kernel<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(x2d, y, x5, wf_t, bf, spos, tvec, tvec_stride, ln1, X,
-                                                           a_hi, a_lo, T, J, tokens_per_clip);
+  auto kern = fmt == FMT_F8C ? lift_ln_kernel<FMT_F8C> : lift_ln_kernel<FMT_SPLIT16>;
+  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(x2d, y, x5, wf_t, bf, spos, tvec, tvec_stride, ln1, X, a_hi, a_lo, T,
+                                                 J, tokens_per_clip);
   return cudaGetLastError();
 }
 cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos, const float* tvec,
-                                   int64_t tvec_stride, LnParams ln1, __half* a_hi, __half* a_lo, int64_t T, int J,
-                                   int F, cudaStream_t st) {
+                                   int64_t tvec_stride, LnParams ln1, __half* a_hi, __half* a_lo, int fmt, int64_t T,
+                                   int J, int F, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
-  postnorm_add_ln_kernel<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, tpos, tvec, tvec_stride, ln1, a_hi,
-                                                                   a_lo, T, J, F);
+  auto kern = fmt == FMT_F8C ? postnorm_add_ln_kernel<FMT_F8C> : postnorm_add_ln_kernel<FMT_SPLIT16>;
+  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, tpos, tvec, tvec_stride, ln1, a_hi, a_lo, T, J, F);
   return cudaGetLastError();
 }
-cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int64_t T,
+cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int fmt, int64_t T,
                             cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
-  ln_split_kernel<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, ln, eps, a_hi, a_lo, T);
+  auto kern = fmt == FMT_F8C ? ln_split_kernel<FMT_F8C> : ln_split_kernel<FMT_SPLIT16>;
+  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, ln, eps, a_hi, a_lo, T);
   return cudaGetLastError();
 }
 cudaError_t launch_ln_f32(const float* x, LnParams ln, float eps, float* out, int64_t T, cudaStream_t st) {

@@ -30,7 +30,8 @@ def _default_cta_group(monkeypatch):
 
 @pytest.mark.parametrize("mode,tol,cg", [(_lib.GEMM_SIMT_FP32, 3e-6, 2), (_lib.GEMM_TC_SPLIT3, 3e-6, 2),
                                          (_lib.GEMM_TC_SPLIT3, 3e-6, 1), (_lib.GEMM_TC_FP16, 2e-3, 2),
-                                         (_lib.GEMM_TC_FP16, 2e-3, 1)])
+                                         (_lib.GEMM_TC_FP16, 2e-3, 1), (_lib.GEMM_TC_F8C, 2e-4, 2),
+                                         (_lib.GEMM_TC_F8C, 2e-4, 1), (_lib.GEMM_SIMT_F8C, 2e-4, 2)])
 @pytest.mark.parametrize("M,N,K", [(128, 1536, 512), (200, 512, 512), (1000, 1024, 512), (459, 512, 1024),
                                    (37 * 128 + 5, 256, 64), (1, 512, 512), (74 * 256 * 3 + 77, 512, 512)])
 def test_linear_parity(eng27, monkeypatch, mode, tol, cg, M, N, K):
@@ -45,13 +46,26 @@ def test_linear_parity(eng27, monkeypatch, mode, tol, cg, M, N, K):
     assert err < tol, f"relative error {err:.3e}"
 
 
-@pytest.mark.parametrize("mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3])
-def test_linear_gelu_split_epilogue(eng27, mode):
+@pytest.mark.parametrize("mode,tol", [(_lib.GEMM_SIMT_FP32, 2e-5), (_lib.GEMM_TC_SPLIT3, 2e-5), (_lib.GEMM_TC_F8C, 1.5e-3),
+                                      (_lib.GEMM_SIMT_F8C, 1.5e-3)])
+def test_linear_gelu_split_epilogue(eng27, mode, tol):
+    """fc1 epilogue: bias + exact-erf GELU, written as the A operand of fc2.  In the F8C format the operand keeps
+    hi exactly and the lo term as e5m2 (3 significant bits of a 2^-11 correction); the test reads back hi + lo."""
     M, N, K = 300, 1024, 512
     a, w, b = _rand((M, K), 5), _rand((N, K), 6, 0.05), _rand((N,), 7, 0.1)
     ref = torch.nn.functional.gelu(a.double() @ w.double().T + b.double())
     out = eng27.op_linear(a.cuda(), w.cuda(), b.cuda(), act=1, gemm_mode=mode).cpu()
-    assert (out.double() - ref).abs().max().item() < 2e-5
+    assert (out.double() - ref).abs().max().item() < tol
+
+
+def test_f8c_tc_matches_simt_elementwise(eng27):
+    """Same hi / e5m2 operands in: the tensor-core F8C kernel and the CUDA-core kernel form the same products, so
+    they differ only by fp32 accumulation order."""
+    M, N, K = 777, 1536, 512
+    a, w, b = _rand((M, K), 8).cuda(), _rand((N, K), 9, 0.05).cuda(), _rand((N,), 10).cuda()
+    x = eng27.op_linear(a, w, b, gemm_mode=_lib.GEMM_TC_F8C)
+    y = eng27.op_linear(a, w, b, gemm_mode=_lib.GEMM_SIMT_F8C)
+    assert (x - y).abs().max().item() < 2e-5
 
 
 def test_tc_matches_simt_elementwise(eng27):
@@ -102,7 +116,7 @@ def test_time_table_golden(golden):
     assert np.abs(tab - g["time_table"]).max() < 2e-5
 
 
-@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3])
+@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3, _lib.GEMM_TC_F8C, _lib.GEMM_SIMT_F8C])
 def test_residual_stream_after_blocks_golden(golden, gemm_mode):
     """Residual stream after STE block 0 and TTE block 0 (sub-sampled) against the imported reference."""
     g = golden("denoise_f27_b3")

@@ -30,7 +30,7 @@ def _mpjpe_delta(a, b, gt):
 
 
 @pytest.mark.parametrize("name", ["denoise_f27_b3", "denoise_f27_b2_notime"])
-@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3])
+@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3, _lib.GEMM_TC_F8C])
 def test_forward_denoise_golden(golden, name, gemm_mode):
     g = golden(name)
     F, B = int(g["F"]), int(g["B"])
@@ -43,11 +43,13 @@ def test_forward_denoise_golden(golden, name, gemm_mode):
 
 @pytest.mark.parametrize("name", ["sampler_f27_b2_s3_clip", "sampler_f27_b2_s3_eta", "sampler_f27_b2_s2_notime",
                                   "sampler_f81_b1_s2_noclip", "sampler_f243_b1_s1_clip", "sampler_f9_b2_s9_clip"])
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_sampler_golden(golden, name, use_graph):
+@pytest.mark.parametrize("use_graph,gemm_mode", [(False, _lib.GEMM_TC_SPLIT3), (True, _lib.GEMM_TC_SPLIT3),
+                                                 (True, _lib.GEMM_TC_F8C)])
+def test_sampler_golden(golden, name, use_graph, gemm_mode):
     g = golden(name)
     F, B, S, eta = int(g["F"]), int(g["B"]), int(g["S"]), float(g["eta"])
-    diff = _diffusion(F, S, eta, bool(g["clip"]), bool(g["with_time_emb"]), use_graph=use_graph, max_clips=B)
+    diff = _diffusion(F, S, eta, bool(g["clip"]), bool(g["with_time_emb"]), gemm_mode=gemm_mode, use_graph=use_graph,
+                      max_clips=B)
     x2d, gt = synthetic.make_inputs(B, F)
     y_T, steps = synthetic.make_noise(B, F, S)
     noise = (y_T.cuda(), steps.cuda() if eta != 0 else None)

@@ -84,6 +84,31 @@ def gemm_cg2_fp16():
 
 
 @stage
+def gemm_simt_f8c():
+    return _gemm(4, 300, 512, 512, 256)
+
+
+@stage
+def gemm_cg1_f8c():
+    return _gemm(3, 300, 512, 512, 256, cg=1)
+
+
+@stage
+def gemm_cg2_f8c_one_tile():
+    return _gemm(3, 256, 256, 64, 256, cg=2)
+
+
+@stage
+def gemm_cg2_f8c_residual():
+    return _gemm(3, 5000, 512, 1024, 256, cg=2, residual=True)
+
+
+@stage
+def gemm_cg2_f8c_gelu():
+    return _gemm(3, 5000, 1024, 512, 256, act=1, cg=2)
+
+
+@stage
 def gemm_cg2_many_tiles():
     return _gemm(0, 70001, 1536, 512, 256, cg=2, residual=True)
 
@@ -177,6 +202,26 @@ def sampler_f9_s9():
 
 
 @stage
+def sampler_f8c_simt():
+    return _sampler(4, 1, False)
+
+
+@stage
+def sampler_f8c():
+    return _sampler(3, 0, True)
+
+
+@stage
+def sampler_f8c_f243():
+    return _sampler(3, 0, True, "sampler_f243_b1_s1_clip")
+
+
+@stage
+def sampler_f8c_f9_s9():
+    return _sampler(3, 0, True, "sampler_f9_b2_s9_clip")
+
+
+@stage
 def bench_gemm():
     """ms / launch of the GEMM kernel alone at the cfg3 half-batch size (M = 1 057 536 tokens)."""
     torch, _lib, synthetic, Engine = _imports()
@@ -186,7 +231,7 @@ def bench_gemm():
     for cg in (1, 2):
         os.environ["D3D_GEMM_CG"] = str(cg)
         os.environ["D3D_GEMM_BN"] = "256"
-        for mode, name, passes in ((_lib.GEMM_TC_SPLIT3, "split3", 3), (_lib.GEMM_TC_FP16, "fp16", 1)):
+        for mode, name, passes in ((_lib.GEMM_TC_SPLIT3, "split3", 3), (_lib.GEMM_TC_F8C, "f8c", 2), (_lib.GEMM_TC_FP16, "fp16", 1)):
             for N, K, act in ((1536, 512, 0), (512, 512, 0), (1024, 512, 1), (512, 1024, 0)):
                 ms = eng.op_linear_bench(M, N, K, act, mode, iters=5)
                 tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12

@@ -9,7 +9,8 @@ the plain fp32 run on the same weights, inputs and noise.
 Linear modes:
   fp16      a_hi.b_hi                                             (1 fp16 pass)
   split3    a_hi.b_hi + a_hi.b_lo + a_lo.b_hi                     (3 fp16 passes)
-  f8corr    a_hi.b_hi + 2^-16 (e4m3(a).e4m3(2^16 b_lo) + e4m3(2^12 a_lo).e4m3(2^4 b))   (1 fp16 + 2 fp8 passes)
+  f8corr    a_hi.b_hi + 2^-16 (e4m3(a).e4m3(2^16 b_lo) + e4m3(2^12 a_lo).e4m3(2^4 b))   (1 fp16 + 2 fp8 passes, 2 accumulators)
+  f8c52     a_hi.b_hi + e5m2(2^-8 a).e5m2(2^8 b_lo) + e5m2(2^4 a_lo).e5m2(2^-4 b)       (same, ONE accumulator)
 Attention modes: fp32 | fp16 | split3 | qk3pv1 (QK^T split3, PV single fp16 pass)
 """
 import os
@@ -37,6 +38,10 @@ def e4m3(x):
     return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
 
 
+def e5m2(x):
+    return x.clamp(-57344.0, 57344.0).to(torch.float8_e5m2).float()
+
+
 def mm_mode(a, bt, mode):
     """a [.., M, K] @ bt [.., K, N] with operand rounding per mode, fp32 accumulate."""
     if mode == "fp32":
@@ -52,6 +57,12 @@ def mm_mode(a, bt, mode):
     if mode == "f8corr":
         corr = torch.matmul(e4m3(a), e4m3(bl * 65536.0)) + torch.matmul(e4m3(al * 4096.0), e4m3(bt * 16.0))
         return torch.matmul(ah, bh) + corr * (1.0 / 65536.0)
+    if mode == "f8c52":            # single accumulator: scale products are 1, all four fp8 operands e5m2
+        return (torch.matmul(ah, bh) + torch.matmul(e5m2(a * 2.0 ** -8), e5m2(bl * 2.0 ** 8)) +
+                torch.matmul(e5m2(al * 2.0 ** 4), e5m2(bt * 2.0 ** -4)))
+    if mode == "f8c43":            # a, a_lo in e4m3 (x 2^-4 / x 2^8), b_lo, b in e5m2 (x 2^4 / x 2^-8)
+        return (torch.matmul(ah, bh) + torch.matmul(e4m3(a * 2.0 ** -4), e5m2(bl * 2.0 ** 4)) +
+                torch.matmul(e4m3(al * 2.0 ** 8), e5m2(bt * 2.0 ** -8)))
     raise ValueError(mode)
 
 
