@@ -54,13 +54,34 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n (0..3) of the most recently committed groups are still in flight
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+// MUFU approximations (rel. error ~2^-22): the library exp2f / IEEE division carry slow-path branches
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // ------------------------------------------------------------------------------------------ temporal
 constexpr int kTStgRow = 272;                     // bytes per staged output row (256 + 16: conflict-free 4-byte writes)
 constexpr int kTStgWarp = 16 * kTStgRow;          // one 16-query tile per warp
 
 template <int FMT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_hi, __half* __restrict__ o_lo,
                          float* __restrict__ o_f32, int F, int J, int NK) {
   extern __shared__ __align__(16) __half smh[];
@@ -73,24 +94,27 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
   const int64_t tok0 = (seq / J) * (static_cast<int64_t>(F) * J) + (seq % J);
   const __half* base = qkv + head * kHd;                            // + tok * kQkvRow (+ 512 k, + 1024 v_hi, + 1536 v_lo)
 
-  // ---- stage K, V_hi rows of the sequence (128 B each) with cp.async; zero the rows beyond F
+  // ---- stage K, V_hi rows of the sequence (128 B each) with cp.async, one commit group per 64-key chunk so that
+  //      the first q-tile sweep can start on chunk 0 while chunks 1..3 are still in flight; zero the rows beyond F
   const uint32_t sK = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
   const uint32_t sV = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
-  for (int i = threadIdx.x; i < NK * 16; i += blockDim.x) {
-    const int r = i >> 4, c = i & 15;
-    const bool is_v = c >= 8;
-    const int c8 = c & 7;
-    const uint32_t dst = (is_v ? sV : sK) + static_cast<uint32_t>((r * KS + c8 * 8) * 2);
-    if (r < F) {
-      const __half* src = base + static_cast<size_t>(tok0 + static_cast<int64_t>(r) * J) * kQkvRow +
-                          (is_v ? 2 * kC : kC) + c8 * 8;
-      cp_async16(dst, src);
-    } else {
-      asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
+  const int n_chunks = NK >> 6;
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+      const int r = (kc << 6) + (i >> 4), c = i & 15;
+      const bool is_v = c >= 8;
+      const int c8 = c & 7;
+      const uint32_t dst = (is_v ? sV : sK) + static_cast<uint32_t>((r * KS + c8 * 8) * 2);
+      if (r < F) {
+        const __half* src = base + static_cast<size_t>(tok0 + static_cast<int64_t>(r) * J) * kQkvRow +
+                            (is_v ? 2 * kC : kC) + c8 * 8;
+        cp_async16(dst, src);
+      } else {
+        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
+      }
     }
+    cp_async_commit();
   }
-  cp_async_wait_all();
-  __syncthreads();
 
   const int g = lane >> 2, q4 = lane & 3;
   // ldmatrix lane -> row/col offsets
@@ -100,7 +124,7 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
   const int v_d = (lane >> 4) << 3;                          //            d offset (0 / 8)
 
   const int n_qt = (F + 15) >> 4;
-  const int n_chunks = NK >> 6;
+  bool first_sweep = true;        // every warp owns >= 1 q-tile (launch: warps = min(n_qt, 8)), so the syncs below are uniform
   for (int qt = warp; qt < n_qt; qt += nwarps) {
     const int q0 = qt << 4;
     const int r0 = q0 + g, r1 = r0 + 8;
@@ -124,6 +148,10 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
     for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 
     for (int kc = 0; kc < n_chunks; ++kc) {
+      if (first_sweep) {            // chunk kc of K / V has landed for every thread of the CTA
+        cp_async_wait_pending(n_chunks - 1 - kc);
+        __syncthreads();
+      }
       const int key0 = kc << 6;
       float s[8][4];
 #pragma unroll
@@ -156,13 +184,13 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);      // finite: every chunk holds >= 1 valid key
-      const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);      // exp2(-inf) = 0 on the first chunk
+      const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);      // exp2(-inf) = 0 on the first chunk
       m0 = mn0; m1 = mn1;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
-        s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+        s[nt][0] = ex2_approx(s[nt][0] - mn0); s[nt][1] = ex2_approx(s[nt][1] - mn0);
+        s[nt][2] = ex2_approx(s[nt][2] - mn1); s[nt][3] = ex2_approx(s[nt][3] - mn1);
         rs0 += s[nt][0] + s[nt][1];
         rs1 += s[nt][2] + s[nt][3];
       }
@@ -188,13 +216,14 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
         }
       }
     }
+    first_sweep = false;
     // ---- finalize: out = O / l - V[query],  V[query] = v_hi (smem) + v_lo (global).  The 16 x 64 tile is staged
     //      per warp (row = 128 B hi | 128 B second part, or 256 B fp32) and written with 16-byte stores.
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const float i0 = rcp_approx(l0), i1 = rcp_approx(l1);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int r = half ? r1 : r0;
@@ -258,7 +287,7 @@ constexpr int kSpRows = 3 * SJ + 1;                 // q, k, v tiles of one head
 constexpr int kSpWarpHalves = kSpRows * KS;         // 3744 halves = 7488 B per warp
 
 template <int FMT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 attn_spatial_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_hi, __half* __restrict__ o_lo,
                         float* __restrict__ o_f32, int64_t n_groups) {
   extern __shared__ __align__(16) __half smh[];
@@ -327,8 +356,8 @@ attn_spatial_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_h
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - mx0); s[nt][1] = exp2f(s[nt][1] - mx0);
-      s[nt][2] = exp2f(s[nt][2] - mx1); s[nt][3] = exp2f(s[nt][3] - mx1);
+      s[nt][0] = ex2_approx(s[nt][0] - mx0); s[nt][1] = ex2_approx(s[nt][1] - mx0);
+      s[nt][2] = ex2_approx(s[nt][2] - mx1); s[nt][3] = ex2_approx(s[nt][3] - mx1);
       l0 += s[nt][0] + s[nt][1];
       l1 += s[nt][2] + s[nt][3];
     }
@@ -336,7 +365,7 @@ attn_spatial_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_h
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const float i0 = rcp_approx(l0), i1 = rcp_approx(l1);
     // O = P V: k-step 0 = keys 0..15, k-step 1 = keys 16..31 (P is zero beyond key 16)
     uint32_t pa0[4], pa1[4];
     pa0[0] = pack2f(s[0][0], s[0][1]); pa0[1] = pack2f(s[0][2], s[0][3]);

@@ -29,6 +29,7 @@ struct Lin {
   float* bias = nullptr;
   bool have_w = false;
   CUtensorMap m_hi, m_lo;
+  CUtensorMap m_hi64, m_lo64;   // 64-row boxes (pair-cluster multicast slices)
 };
 
 struct Blk {
@@ -161,10 +162,10 @@ int mode_fmt(int gemm_mode) {
 
 // tensor maps of an operand: fp16 hi [rows,K]; second array = fp16 lo [rows,K] or uint8 c8 [rows,2K]
 int make_maps(CUtensorMap* m_hi, CUtensorMap* m_second, const __half* hi, const __half* second, int64_t rows, int K,
-              int fmt) {
-  if (make_operand_map(m_hi, hi, rows, K)) return -1;
-  if (fmt == FMT_F8C) return make_operand_map_u8(m_second, second, rows, 2 * static_cast<int64_t>(K));
-  return make_operand_map(m_second, second, rows, K);
+              int fmt, int box_rows = 128) {
+  if (make_operand_map(m_hi, hi, rows, K, box_rows)) return -1;
+  if (fmt == FMT_F8C) return make_operand_map_u8(m_second, second, rows, 2 * static_cast<int64_t>(K), box_rows);
+  return make_operand_map(m_second, second, rows, K, box_rows);
 }
 
 int alloc_operand(d3d_handle* h, OperandBuf* o, int64_t rows, int K) {
@@ -183,7 +184,8 @@ int alloc_lin(d3d_handle* h, Lin* l, int N, int K) {
   if ((r = dev_alloc(h, &l->hi, static_cast<int64_t>(N) * K))) return r;
   if ((r = dev_alloc(h, &l->lo, static_cast<int64_t>(N) * K))) return r;
   if ((r = dev_alloc(h, &l->bias, N))) return r;
-  if (make_maps(&l->m_hi, &l->m_lo, l->hi, l->lo, N, K, h->fmt))
+  if (make_maps(&l->m_hi, &l->m_lo, l->hi, l->lo, N, K, h->fmt) ||
+      make_maps(&l->m_hi64, &l->m_lo64, l->hi, l->lo, N, K, h->fmt, 64))
     return fail(h, -20, "cuTensorMapEncodeTiled failed for a weight operand");
   return 0;
 }
@@ -196,6 +198,12 @@ int env_int(const char* name, int dflt) {
 int pick_cg(int N) {
   const int cg = env_int("D3D_GEMM_CG", 2);
   return (cg == 2 && N % 256 == 0) ? 2 : 1;
+}
+
+// pairs per cluster of the F8C CTA-pair kernel: 2 = weight-tile multicast across two pairs (default), 1 = no multicast
+int pick_cs(int64_t M) {
+  const int cs = env_int("D3D_GEMM_CS", 2);
+  return (cs == 2 && M > 256) ? 2 : 1;
 }
 
 int pick_bn(const d3d_handle* h, int64_t M, int N) {
@@ -224,8 +232,9 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   } else {
     GemmMaps m;
     m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
+    m.b_hi64 = w.m_hi64; m.b_lo64 = w.m_lo64;
     const int passes = mode == D3D_GEMM_TC_FP16 ? 1 : (mode == D3D_GEMM_TC_F8C ? 2 : 3);
-    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), h->num_sms, st));
+    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), pick_cs(M), h->num_sms, st));
   }
   return 0;
 }
@@ -412,7 +421,7 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   h->blk.resize(h->nblk);
   const int64_t T = static_cast<int64_t>(cfg->max_clips) * h->F * h->J;
-  h->tok_cap = (T + 255) / 256 * 256;
+  h->tok_cap = (T + 511) / 512 * 512;
 
   auto body = [&]() -> int {
     int r;
@@ -858,7 +867,7 @@ cudaError_t tmp_alloc(OpLinearBufs& b, T** p, int64_t n) {
   return e;
 }
 int prep_op_linear(d3d_handle* h, OpLinearBufs& b, int64_t M, int N, int K, int act, int fmt) {
-  const int64_t Mp = (M + 255) / 256 * 256;
+  const int64_t Mp = (M + 511) / 512 * 512;
   CK(tmp_alloc(b, &b.a.hi, Mp * K));
   CK(tmp_alloc(b, &b.a.lo, Mp * K));
   CK(tmp_alloc(b, &b.w.hi, static_cast<int64_t>(N) * K));
@@ -869,7 +878,8 @@ int prep_op_linear(d3d_handle* h, OpLinearBufs& b, int64_t M, int N, int K, int 
     CK(tmp_alloc(b, &b.o_hi, M * N));
     CK(tmp_alloc(b, &b.o_lo, M * N));
   }
-  if (make_maps(&b.a.m_hi, &b.a.m_lo, b.a.hi, b.a.lo, Mp, K, fmt) || make_maps(&b.w.m_hi, &b.w.m_lo, b.w.hi, b.w.lo, N, K, fmt))
+  if (make_maps(&b.a.m_hi, &b.a.m_lo, b.a.hi, b.a.lo, Mp, K, fmt) || make_maps(&b.w.m_hi, &b.w.m_lo, b.w.hi, b.w.lo, N, K, fmt) ||
+      make_maps(&b.w.m_hi64, &b.w.m_lo64, b.w.hi, b.w.lo, N, K, fmt, 64))
     return fail(h, -20, "cuTensorMapEncodeTiled failed");
   return 0;
 }

@@ -63,18 +63,19 @@ struct Barriers {
 };
 
 // Exact-erf GELU (MODEL:52, nn.GELU()) without the branchy library erff: the epilogue is instruction-issue bound
-// (32 768 activations per 128 x 256 tile), so the form below is branch-free, 2 MUFU + ~14 FP32 ops:
+// (32 768 activations per 128 x 256 tile), so the form below is branch- and call-free, 2 MUFU + ~14 FP32 ops:
 //   gelu(v) = max(v, 0) - |v|/2 * erfc(|v| / sqrt 2),   erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),
 //   t = 1 / (1 + p z)   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 on erfc; using erfc for BOTH signs avoids the
 //   1 + erf cancellation in the negative tail).  Absolute error on gelu <= |v| * 1e-7.
 __device__ __forceinline__ float gelu_erf(float v) {
   const float z = fabsf(v) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));      // MUFU, rel. error 2^-23
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * z * z);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));   // MUFU, rel. error 2^-22
   return fmaxf(v, 0.0f) - (0.70710678118654752440f * z) * (poly * t * e);
 }
 
@@ -88,7 +89,11 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
 }
 
-template <int CG, int BN, int PASSES, int EPI>
+// CS = CTA pairs per cluster (CG == 2 only).  CS == 2: a cluster of 4 CTAs owns two vertically adjacent 256 x 256
+// tiles (same weight rows).  Each CTA loads only HALF of its 128-row weight tile and TMA-multicasts it to the CTA
+// with the same position in the other pair, so the L2 -> SM weight traffic per MAC halves (48 KB instead of 64 KB
+// per k-block and SM): the F8C GEMM runs at the ~6300 B/clk L2 output cap (profiles/r01e_full_gemm_tc.md).
+template <int CG, int BN, int PASSES, int EPI, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -101,12 +106,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;      // 0 = leader
-  const int unit = CG == 2 ? (blockIdx.x >> 1) : blockIdx.x;        // CTA (pair) index
-  const int n_units = CG == 2 ? (gridDim.x >> 1) : gridDim.x;
+  static_assert(CS == 1 || (CG == 2 && PASSES == 2), "pair clusters are implemented for the CTA-pair F8C kernel");
+  const uint32_t crank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // rank in the cluster (0 .. 2*CS-1)
+  const uint32_t rank = crank & 1u;                                 // position in the CTA pair, 0 = leader
+  const uint32_t pair = crank >> 1;                                 // pair index inside the cluster (0 .. CS-1)
+  const uint32_t leader = pair << 1;                                // cluster rank of this pair's leader
+  const int unit = blockIdx.x / (CG * CS);                          // cluster (or CTA) index
+  const int n_units = gridDim.x / (CG * CS);
   constexpr int TM = BM * CG;                                       // tile rows
   const int n_tiles_n = p.N / BN;
-  const int n_tiles_m = (p.M + TM - 1) / TM;
+  const int n_tiles_m = ((p.M + TM - 1) / TM + CS - 1) / CS;        // super-tiles of CS vertically adjacent tiles
   const int n_tiles = n_tiles_m * n_tiles_n;
   const int n_kb = p.K / BK;
   const int n_steps = PASSES == 2 ? 2 * n_kb : n_kb;       // ring stages consumed per tile
@@ -122,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&bars->full[s], 1);
-      ptx::mbar_init(&bars->empty[s], 1);
+      ptx::mbar_init(&bars->empty[s], CS);                      // every pair of the cluster releases the stage
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bars->tmem_full[a], 1);
@@ -145,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit; tile < n_tiles; tile += n_units) {
-        const int m0 = (tile / n_tiles_n) * TM + static_cast<int>(rank) * BM;
+        const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
         const int n0 = (tile % n_tiles_n) * BN + static_cast<int>(rank) * C::kBRows;
         for (int kb = 0; kb < n_steps; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -163,10 +172,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               for (int h = 0; h < C::kBRows / 128; ++h)
                 ptx::tma_load_2d(s + kTileBytesA + h * (128 * BK * 2), mb, &bars->full[stage], c0, n0 + h * 128);
             } else {
-              const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
+              const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), leader);
               if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * C::kStageBytes);
               ptx::tma_load_2d_cg2(s, ma, full_leader, c0, m0);
-              ptx::tma_load_2d_cg2(s + kTileBytesA, mb, full_leader, c0, n0);
+              if (CS == 1) {
+                ptx::tma_load_2d_cg2(s + kTileBytesA, mb, full_leader, c0, n0);
+              } else {
+                // my 64-row slice of the 128-row weight tile, multicast to the CTA at my position in every pair
+                // (the weight maps passed to this instantiation have {128 B x 64 row} boxes)
+                constexpr int kSlice = C::kTileBytesB / CS;
+                const uint16_t mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));
+                ptx::tma_load_2d_cg2_mc(s + kTileBytesA + pair * kSlice, mb, &bars->full[stage], c0,
+                                        n0 + static_cast<int>(pair) * (C::kBRows / CS), mask);
+              }
             }
           } else if (CG == 1) {
             ptx::mbar_arrive_expect_tx(&bars->full[stage], C::kStageBytes);
@@ -187,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
           } else {
             // both CTAs' bytes complete on the LEADER's full barrier; the leader arms it with the pair's total
-            const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
+            const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), leader);
             if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * C::kStageBytes);
             ptx::tma_load_2d_cg2(s, &tm_a_hi, full_leader, kb * BK, m0);
             s += kTileBytesA;
@@ -235,7 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 else ptx::mma_f16_ss(d_tmem, da, db, idesc, accum);
               }
             }
-            if (CG == 2) ptx::mma_commit_cg2(&bars->empty[stage], 3);
+            // frees the stage: in both CTAs of this pair and (CS == 2) in the pair that multicasts into them
+            if (CG == 2) ptx::mma_commit_cg2(&bars->empty[stage], static_cast<uint16_t>((1u << (2 * CS)) - 1));
             else ptx::mma_commit(&bars->empty[stage]);
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
             continue;
@@ -268,8 +287,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           else ptx::mma_commit(&bars->empty[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete -> epilogue warps (of both CTAs)
-        if (CG == 2) ptx::mma_commit_cg2(&bars->tmem_full[acc], 3);
+        // accumulator complete -> epilogue warps (of both CTAs of this pair)
+        if (CG == 2) ptx::mma_commit_cg2(&bars->tmem_full[acc], static_cast<uint16_t>(3u << leader));
         else ptx::mma_commit(&bars->tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -288,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = unit; tile < n_tiles; tile += n_units) {
-      const int m0 = (tile / n_tiles_n) * TM + static_cast<int>(rank) * BM;
+      const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
       const int n0 = (tile % n_tiles_n) * BN;
       const int row_w = m0 + q * 32;                    // first row of this warp
       const int colbase = n0 + half * (BN / 2);
@@ -422,7 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[acc]), 0));
+        if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[acc]), leader));
         else ptx::mbar_arrive(&bars->tmem_empty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -439,31 +458,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
-template <int CG, int BN, int PASSES, int EPI>
+// Clusters of 4 cannot straddle a GPC, so fewer than 148/4 of them may be co-resident: ask the runtime (once).
+template <int CG, int BN, int PASSES, int EPI, int CS>
+int max_clusters(int num_sms) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  int n = num_sms / (CG * CS);
+  if (CG * CS > 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(num_sms / (CG * CS) * (CG * CS)));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<CG, BN, PASSES>::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG * CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, gemm_tc_kernel<CG, BN, PASSES, EPI, CS>, &cfg) == cudaSuccess && q > 0 && q < n)
+      n = q;
+    (void)cudaGetLastError();
+  }
+  cached = n;
+  return n;
+}
+
+template <int CG, int BN, int PASSES, int EPI, int CS = 1>
 cudaError_t launch_one(const GemmMaps& m, const GemmParams& p, int num_sms, cudaStream_t st) {
   using C = Cfg<CG, BN, PASSES>;
-  auto kern = gemm_tc_kernel<CG, BN, PASSES, EPI>;
-  const int n_tiles = ((p.M + BM * CG - 1) / (BM * CG)) * (p.N / BN);
-  const int max_units = num_sms / CG;
+  auto kern = gemm_tc_kernel<CG, BN, PASSES, EPI, CS>;
+  const int tiles_m = (p.M + BM * CG - 1) / (BM * CG);
+  const int n_tiles = ((tiles_m + CS - 1) / CS) * (p.N / BN);
+  const int max_units = max_clusters<CG, BN, PASSES, EPI, CS>(num_sms);
   const int units = n_tiles < max_units ? n_tiles : max_units;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(units * CG));
+  cfg.gridDim = dim3(static_cast<unsigned>(units * CG * CS));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CG * CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, m.b_hi, m.b_lo, p);
+  return cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, CS == 2 ? m.b_hi64 : m.b_hi, CS == 2 ? m.b_lo64 : m.b_lo, p);
 }
 
-template <int CG, int BN, int PASSES, int EPI>
+template <int CG, int BN, int PASSES, int EPI, int CS = 1>
 cudaError_t configure_one() {
-  return cudaFuncSetAttribute(gemm_tc_kernel<CG, BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(gemm_tc_kernel<CG, BN, PASSES, EPI, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               Cfg<CG, BN, PASSES>::kSmemBytes);
 }
 
@@ -486,15 +533,23 @@ cudaError_t configure_gemm_tc() {
   if ((e = configure_one<CG_, BN_, PASSES_, EPI_>()) != cudaSuccess) return e;
   D3D_FOR_ALL_GEMMS(D3D_CFG)
 #undef D3D_CFG
+  if ((e = configure_one<2, 256, 2, EPI_F32, 2>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 2, EPI_GELU_SPLIT, 2>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 2, EPI_QKV16, 2>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
-                           int num_sms, cudaStream_t st) {
+                           int pair_cluster, int num_sms, cudaStream_t st) {
   if (p.M <= 0) return cudaSuccess;
   if (cta_group == 2 || passes == 2) bn = 256;
   if (p.K % BK != 0 || p.N % bn != 0 || (bn != 128 && bn != 256)) return cudaErrorInvalidValue;
   if (epi == EPI_QKV16 && p.N != 3 * kC) return cudaErrorInvalidValue;
+  if (pair_cluster == 2 && cta_group == 2 && passes == 2) {
+    if (epi == EPI_F32) return launch_one<2, 256, 2, EPI_F32, 2>(maps, p, num_sms, st);
+    if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 2, EPI_GELU_SPLIT, 2>(maps, p, num_sms, st);
+    return launch_one<2, 256, 2, EPI_QKV16, 2>(maps, p, num_sms, st);
+  }
 #define D3D_DISPATCH(CG_, BN_, PASSES_, EPI_)                                   \
   if (cta_group == CG_ && bn == BN_ && passes == PASSES_ && epi == EPI_)        \
     return launch_one<CG_, BN_, PASSES_, EPI_>(maps, p, num_sms, st);
@@ -510,7 +565,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t K) {
+int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t K, int box_rows) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -521,7 +576,7 @@ int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
-  cuuint32_t box[2] = {BK, 128};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -531,7 +586,7 @@ int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t
 
 
 // uint8 [rows, row_bytes] row-major array (the c8 arrays of FMT_F8C): {128 bytes x 128 rows} boxes, SWIZZLE_128B
-int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes) {
+int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes, int box_rows) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -539,7 +594,7 @@ int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_
   EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(row_bytes), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_bytes)};
-  cuuint32_t box[2] = {128, 128};
+  cuuint32_t box[2] = {128, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -34,13 +34,15 @@ struct GemmParams {
 // A: [M,K] fp16 (hi, lo), W: [N,K] fp16 (hi, lo); K-major.  Tensor maps use a {64, 128} box, SWIZZLE_128B.
 struct GemmMaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap b_hi64, b_lo64;     // weight maps with 64-row boxes (multicast slices of the pair-cluster kernel)
 };
 
 // passes: 3 (split fp16), 1 (fp16) or 2 (FMT_F8C: fp16 main + e5m2 corrections; the *_lo maps are the uint8 c8 maps).
 // cta_group 1: one CTA per 128 x bn tile (bn 128 or 256, N % bn == 0);
 // cta_group 2: a CTA pair per 256 x 256 tile (tcgen05.mma.cta_group::2, N % 256 == 0, bn ignored).
+// pair_cluster 2 (F8C + cta_group 2 only): clusters of two CTA pairs sharing the weight tile through TMA multicast.
 cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
-                           int num_sms, cudaStream_t st);
+                           int pair_cluster, int num_sms, cudaStream_t st);
 cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
                              const GemmParams& p, int epi, int fmt, cudaStream_t st);
 // One-time per-device kernel attribute setup (dynamic shared memory opt-in); call outside graph capture.
@@ -48,8 +50,8 @@ cudaError_t configure_gemm_tc();
 cudaError_t configure_attention();
 cudaError_t configure_attention_mma();
 // Build a K-major fp16 operand map for a [rows, K] row-major matrix / a uint8 map for a [rows, row_bytes] c8 array.
-int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t K);
-int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes);
+int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t K, int box_rows = 128);
+int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes, int box_rows = 128);
 
 // ------------------------------------------------------------------ row-wise (one warp per 512-wide token row)
 struct LnParams {

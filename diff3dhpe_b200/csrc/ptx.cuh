@@ -109,6 +109,20 @@ __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMa
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Multicast variant: the box is written at the same CTA-relative offset of every CTA in `cta_mask` (bit r = cluster
+// rank r); the completion bytes are signalled, per destination CTA, on the barrier at `bar_cta_addr`'s offset in the
+// EVEN CTA of that destination's pair (bit 24 of the executing CTA's own shared address cleared, as CUTLASS'
+// SM100_TMA_2SM_LOAD_MULTICAST does).
+__device__ __forceinline__ void tma_load_2d_cg2_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                   int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5}], [%2], %3;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(cta_mask),
+        "r"(c0), "r"(c1)
+      : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

@@ -26,6 +26,7 @@ def _rand(shape, seed, scale=1.0):
 def _default_cta_group(monkeypatch):
     monkeypatch.delenv("D3D_GEMM_CG", raising=False)
     monkeypatch.delenv("D3D_GEMM_BN", raising=False)
+    monkeypatch.delenv("D3D_GEMM_CS", raising=False)
 
 
 @pytest.mark.parametrize("mode,tol,cg", [(_lib.GEMM_SIMT_FP32, 3e-6, 2), (_lib.GEMM_TC_SPLIT3, 3e-6, 2),
@@ -58,9 +59,11 @@ def test_linear_gelu_split_epilogue(eng27, mode, tol):
     assert (out.double() - ref).abs().max().item() < tol
 
 
-def test_f8c_tc_matches_simt_elementwise(eng27):
+@pytest.mark.parametrize("cs", [1, 2])
+def test_f8c_tc_matches_simt_elementwise(eng27, monkeypatch, cs):
     """Same hi / e5m2 operands in: the tensor-core F8C kernel and the CUDA-core kernel form the same products, so
     they differ only by fp32 accumulation order."""
+    monkeypatch.setenv("D3D_GEMM_CS", str(cs))       # 2 = pair clusters with weight-tile TMA multicast (default)
     M, N, K = 777, 1536, 512
     a, w, b = _rand((M, K), 8).cuda(), _rand((N, K), 9, 0.05).cuda(), _rand((N,), 10).cuda()
     x = eng27.op_linear(a, w, b, gemm_mode=_lib.GEMM_TC_F8C)

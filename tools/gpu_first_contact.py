@@ -22,10 +22,11 @@ def _imports():
     return torch, _lib, synthetic, Engine
 
 
-def _gemm(mode, M, N, K, bn, act=0, cg=2, residual=False):
+def _gemm(mode, M, N, K, bn, act=0, cg=2, residual=False, cs=2):
     torch, _lib, synthetic, Engine = _imports()
     os.environ["D3D_GEMM_BN"] = str(bn)
     os.environ["D3D_GEMM_CG"] = str(cg)
+    os.environ["D3D_GEMM_CS"] = str(cs)
     eng = Engine(27, max_clips=1)
     g = torch.Generator().manual_seed(1)
     a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05, torch.randn(N, generator=g)
@@ -99,13 +100,33 @@ def gemm_cg2_f8c_one_tile():
 
 
 @stage
-def gemm_cg2_f8c_residual():
-    return _gemm(3, 5000, 512, 1024, 256, cg=2, residual=True)
+def gemm_cg2_f8c_residual_cs1():
+    return _gemm(3, 5000, 512, 1024, 256, cg=2, residual=True, cs=1)
 
 
 @stage
-def gemm_cg2_f8c_gelu():
-    return _gemm(3, 5000, 1024, 512, 256, act=1, cg=2)
+def gemm_cs2_f8c_two_tiles():
+    return _gemm(3, 512, 256, 64, 256, cg=2, cs=2)
+
+
+@stage
+def gemm_cs2_f8c_odd_tiles():
+    return _gemm(3, 700, 512, 512, 256, cg=2, cs=2)
+
+
+@stage
+def gemm_cs2_f8c_residual():
+    return _gemm(3, 5000, 512, 1024, 256, cg=2, residual=True, cs=2)
+
+
+@stage
+def gemm_cs2_f8c_gelu():
+    return _gemm(3, 5000, 1024, 512, 256, act=1, cg=2, cs=2)
+
+
+@stage
+def gemm_cs2_f8c_many_tiles():
+    return _gemm(3, 70001, 1536, 512, 256, cg=2, residual=True, cs=2)
 
 
 @stage
@@ -228,14 +249,17 @@ def bench_gemm():
     eng = Engine(27, max_clips=1)
     out = {}
     M = 1057536
-    for cg in (1, 2):
+    os.environ["D3D_GEMM_BN"] = "256"
+    for cg, cs in ((1, 1), (2, 1), (2, 2)):
         os.environ["D3D_GEMM_CG"] = str(cg)
-        os.environ["D3D_GEMM_BN"] = "256"
+        os.environ["D3D_GEMM_CS"] = str(cs)
         for mode, name, passes in ((_lib.GEMM_TC_SPLIT3, "split3", 3), (_lib.GEMM_TC_F8C, "f8c", 2), (_lib.GEMM_TC_FP16, "fp16", 1)):
+            if cs == 2 and name != "f8c":
+                continue
             for N, K, act in ((1536, 512, 0), (512, 512, 0), (1024, 512, 1), (512, 1024, 0)):
                 ms = eng.op_linear_bench(M, N, K, act, mode, iters=5)
                 tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
-                out[f"cg{cg}_{name}_N{N}_K{K}"] = [round(ms, 3), round(tf, 1), round(tf * passes, 1)]
+                out[f"cg{cg}cs{cs}_{name}_N{N}_K{K}"] = [round(ms, 3), round(tf, 1), round(tf * passes, 1)]
     return out
 
 
