@@ -70,6 +70,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -128,6 +129,13 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
   for (int qt = warp; qt < n_qt; qt += nwarps) {
     const int q0 = qt << 4;
     const int r0 = q0 + g, r1 = r0 + 8;
+    {
+      // The finalize step reads this tile's v_lo rows and the next sweep this warp's next Q tile straight from global
+      // (ncu: their exposed latency was ~17 % of the stall samples): pull those 128-byte rows into L2 now.
+      const int pr = (lane < 16 ? q0 : q0 + 16 * nwarps) + (lane & 15);
+      if (pr < F)
+        prefetch_l2(base + static_cast<size_t>(tok0 + static_cast<int64_t>(pr) * J) * kQkvRow + (lane < 16 ? 3 * kC : 0));
+    }
     // ---- Q fragments (A operand) straight from global: fp16 pairs
     uint32_t qa[4][4];
     {
@@ -257,13 +265,19 @@ attn_temporal_h16_kernel(const __half* __restrict__ qkv, __half* __restrict__ o_
       }
     }
     __syncwarp();
+    uint4 vals[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {                      // all shared loads first (distinct registers), then the stores
+      const int idx = it * 32 + lane;
+      vals[it] = *reinterpret_cast<const uint4*>(stg + (idx >> 4) * kTStgRow + (idx & 15) * 16);
+    }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int idx = it * 32 + lane;
       const int rr = idx >> 4, c = idx & 15;              // staged row, 16-byte chunk
       const int r = q0 + rr;
       if (r < F) {
-        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kTStgRow + c * 16);
+        const uint4 val = vals[it];
         const size_t tok = static_cast<size_t>(tok0 + static_cast<int64_t>(r) * J);
         if (o_f32) {
           *reinterpret_cast<uint4*>(o_f32 + tok * kC + head * kHd + c * 4) = val;

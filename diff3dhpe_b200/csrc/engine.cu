@@ -200,9 +200,11 @@ int pick_cg(int N) {
   return (cg == 2 && N % 256 == 0) ? 2 : 1;
 }
 
-// pairs per cluster of the F8C CTA-pair kernel: 2 = weight-tile multicast across two pairs (default), 1 = no multicast
+// pairs per cluster of the F8C CTA-pair kernel: 2 = weight-tile TMA multicast across two pairs, 1 = none (default:
+// measured on B200 the multicast variant is ~3 % SLOWER, profiles/r01f_micro.log -- L2 already serves the identical
+// unicast requests of neighbouring pairs, and 4-CTA clusters leave SMs of 18-SM GPCs idle)
 int pick_cs(int64_t M) {
-  const int cs = env_int("D3D_GEMM_CS", 2);
+  const int cs = env_int("D3D_GEMM_CS", 1);
   return (cs == 2 && M > 256) ? 2 : 1;
 }
 

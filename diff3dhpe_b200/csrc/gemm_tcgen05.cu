@@ -336,13 +336,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           __syncwarp();
           if (ci + 1 < kChunks) load_res(ci + 1);
         }
-        ptx::tmem_ld_wait();
         const int gcol = n0 + col0;
-        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + gcol);
+        float4 bias4[8];                                 // issued before the TMEM wait so their latency is hidden
+#pragma unroll
+        for (int v = 0; v < 8; ++v) bias4[v] = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + v);
+        ptx::tmem_ld_wait();
         if (EPI == EPI_F32) {
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
-            const float4 b = __ldg(bias4 + v);
+            const float4 b = bias4[v];
             float4 o;
             o.x = __uint_as_float(r[4 * v + 0]) + b.x;
             o.y = __uint_as_float(r[4 * v + 1]) + b.y;
@@ -356,11 +358,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             *reinterpret_cast<float4*>(cell) = o;
           }
           __syncwarp();
+          uint4 vals[8];                       // all shared loads first, then all global stores (distinct registers)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int rr = row_w + 4 * j + rsub;
-            const uint4 val = *stg_at(stg, 4 * j + rsub, gsub);
-            if (rr < p.M) *reinterpret_cast<uint4*>(p.out_f32 + static_cast<size_t>(rr) * p.N + gcol + gsub * 4) = val;
+            if (rr < p.M) *reinterpret_cast<uint4*>(p.out_f32 + static_cast<size_t>(rr) * p.N + gcol + gsub * 4) = vals[j];
           }
         } else {
           // fp16 outputs: row = hi (granules 0..3, 32 halves) | second part (granules 4..7):
@@ -374,7 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             uint32_t hw[4], lw[4], a16[4], l16[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float4 b = __ldg(bias4 + 2 * v + (e >> 1));
+              const float4 b = bias4[2 * v + (e >> 1)];
               float x0 = __uint_as_float(r[8 * v + 2 * e + 0]) + ((e & 1) ? b.z : b.x);
               float x1 = __uint_as_float(r[8 * v + 2 * e + 1]) + ((e & 1) ? b.w : b.y);
               if (gelu) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); }
@@ -414,25 +418,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           if (EPI == EPI_GELU_SPLIT && PASSES == 2) {
             // c8 row of the fc2 operand: N bytes e5m2(x 2^-8) then N bytes e5m2(lo 2^4); 32 columns = 2 granules each
             uint8_t* c8 = reinterpret_cast<uint8_t*>(p.out_lo);
+            uint4 vals[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int rr = row_w + 4 * j + rsub;
-              const uint4 val = *stg_at(stg, 4 * j + rsub, gsub);
               if (rr >= p.M) continue;
               if (gsub < 4) {
-                *reinterpret_cast<uint4*>(p.out_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8) = val;
+                *reinterpret_cast<uint4*>(p.out_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8) = vals[j];
               } else {
                 uint8_t* dst = c8 + static_cast<size_t>(rr) * (2 * p.N) + (gsub < 6 ? 0 : p.N) + gcol + (gsub & 1) * 16;
-                *reinterpret_cast<uint4*>(dst) = val;
+                *reinterpret_cast<uint4*>(dst) = vals[j];
               }
             }
           } else {
             __half* dst_base = gsub < 4 ? hi_base : lo_base;
+            uint4 vals[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int rr = row_w + 4 * j + rsub;
-              const uint4 val = *stg_at(stg, 4 * j + rsub, gsub);
-              if (rr < p.M && dst_base) *reinterpret_cast<uint4*>(dst_base + static_cast<size_t>(rr) * ld + (gsub & 3) * 8) = val;
+              if (rr < p.M && dst_base) *reinterpret_cast<uint4*>(dst_base + static_cast<size_t>(rr) * ld + (gsub & 3) * 8) = vals[j];
             }
           }
         }

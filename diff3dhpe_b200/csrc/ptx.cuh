@@ -96,8 +96,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier that may live in another CTA of the cluster.  Default .release.cta semantics (as CUTLASS'
+// ClusterBarrier::arrive): the .release.cluster form costs a cluster-scope membar that waits for every in-flight
+// global store of the warp -- ncu showed ERRBAR/membar as the top stall of the epilogue warps with it.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; the completion bytes are signalled on `bar_cluster_addr`, which may
 // live in the peer (leader) CTA's shared memory.
