@@ -254,16 +254,38 @@ def run_ours(args):
     achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12
     passes = {"split3": 3, "f8c": 2, "fp16": 1}[args.gemm]
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::f16, TMA, TMEM)",
+        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma cta_group::2 kind::f16 + kind::f8f6f4, TMA, TMEM)",
         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
         "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
         "executed_tflops": achieved * passes, "executed_frac": achieved * passes / peaks["tflops_sustained"],
-        "mma_passes": passes, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+        "mma_passes": passes, "executed_note": "fp16-equivalent tensor-pipe units per algorithmic FLOP (f8c: 1 fp16 pass + "
+                                                "2 e5m2 passes at twice the rate = 2)", "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
         "share_of_step": gemm_ms / total_prof_ms,
         "per_class_ms": {k: round(v[0], 3) for k, v in prof.items()},
         "algorithmic_flops_per_launch": gemm_flops / max(gemm_n, 1),
     }
     total_flops = tokens * flops_per_token_call(F_FRAMES) * S_STEPS
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), if it matches the mode
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        if t.get("gemm") == args.gemm and t.get("tokens_per_launch") == tokens:
+            roofline["traffic"] = t["dram_bytes_per_launch_avg"]
+            roofline["traffic_source"] = t.get("source")
+            roofline["algorithmic_hbm_bytes_per_launch"] = t.get("algorithmic_bytes_per_launch_avg")
+    # memory-bound kernel classes against the measured HBM copy bandwidth (SURVEY.md 8d byte counts + operand writes)
+    depth2 = 16
+    ln_bytes = tokens * S_STEPS * (depth2 * 4096 + (depth2 - 1) * 6144)          # norm2: r X, w A; post-norm+norm1: r X, w X, w A
+    attn_bytes = tokens * S_STEPS * depth2 * (4096 + 2048)                       # r q|k|v_hi|v_lo, w A operand
+    hbm = {}
+    for name, ms, nbytes in (("ln", prof["ln"][0], ln_bytes),
+                             ("attention", prof["attn_spatial"][0] + prof["attn_temporal"][0], attn_bytes),
+                             ("lift", prof["lift"][0], tokens * S_STEPS * (20 + 4096)),
+                             ("head_ddim", prof["head_ddim"][0], tokens * S_STEPS * (2048 + 24))):
+        gbs = nbytes / (ms / 1000.0) / 1e9
+        hbm[name] = {"achieved_gbs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peaks["hbm_gbs"], 3)}
+    roofline["hbm_bound_kernels"] = hbm
+    roofline["hbm_peak_gbs"] = peaks["hbm_gbs"]
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -305,7 +327,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU (BASELINE cfg3: 256)")
-    ap.add_argument("--gemm", default="split3", choices=["split3", "f8c", "fp16"])
+    ap.add_argument("--gemm", default="f8c", choices=["split3", "f8c", "fp16"],
+                    help="GEMM arithmetic: f8c (default; fp16 main + e5m2 correction products), split3 (3 fp16 passes), "
+                         "fp16 (1 pass, outside the parity bar)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -46,10 +46,10 @@ typedef struct d3d_handle d3d_handle;
 
 /* GEMM arithmetic of the qkv/proj/fc1/fc2 linears (tcgen05.mma, fp32 accumulation in TMEM). */
 enum {
-  D3D_GEMM_TC_SPLIT3 = 0, /* default: 3-pass split-fp16 (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi), ~fp32 accurate */
+  D3D_GEMM_TC_SPLIT3 = 0, /* 3-pass split-fp16 (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi), ~fp32 accurate */
   D3D_GEMM_TC_FP16 = 1,   /* single-pass fp16 operands: fast mode, outside the 0.1 mm MPJPE-delta bar   */
   D3D_GEMM_SIMT_FP32 = 2, /* CUDA-core fp32 validation kernel (same operands as SPLIT3, no tensor cores) */
-  D3D_GEMM_TC_F8C = 3,    /* fp16 main product + one e5m2 (kind::f8f6f4) product carrying both correction terms:
+  D3D_GEMM_TC_F8C = 3,    /* default of the Python drop-ins: fp16 main product + one e5m2 (kind::f8f6f4) product carrying both correction terms:
                              2 tensor-pipe units instead of 3, within the parity bar */
   D3D_GEMM_SIMT_F8C = 4   /* CUDA-core validation kernel on the F8C operand format */
 };

@@ -18,7 +18,7 @@ MAXABS_BAR, MPJPE_BAR = 1e-2, 1e-4
 MARGIN = 4.0
 
 
-def _diffusion(F, S, eta=0.0, clip=True, with_time_emb=True, gemm_mode=_lib.GEMM_TC_SPLIT3, attn_mode=_lib.ATTN_DEFAULT,
+def _diffusion(F, S, eta=0.0, clip=True, with_time_emb=True, gemm_mode=_lib.GEMM_TC_F8C, attn_mode=_lib.ATTN_DEFAULT,
                use_graph=True, max_clips=1):
     m = synthetic.make_model(F, with_time_emb=with_time_emb).cuda()
     m.gemm_mode, m.attn_mode, m.use_graph, m.max_clips_hint = gemm_mode, attn_mode, use_graph, max_clips
@@ -43,8 +43,8 @@ def test_forward_denoise_golden(golden, name, gemm_mode):
 
 @pytest.mark.parametrize("name", ["sampler_f27_b2_s3_clip", "sampler_f27_b2_s3_eta", "sampler_f27_b2_s2_notime",
                                   "sampler_f81_b1_s2_noclip", "sampler_f243_b1_s1_clip", "sampler_f9_b2_s9_clip"])
-@pytest.mark.parametrize("use_graph,gemm_mode", [(False, _lib.GEMM_TC_SPLIT3), (True, _lib.GEMM_TC_SPLIT3),
-                                                 (True, _lib.GEMM_TC_F8C)])
+@pytest.mark.parametrize("use_graph,gemm_mode", [(False, _lib.GEMM_TC_F8C), (True, _lib.GEMM_TC_F8C),
+                                                 (True, _lib.GEMM_TC_SPLIT3)])
 def test_sampler_golden(golden, name, use_graph, gemm_mode):
     g = golden(name)
     F, B, S, eta = int(g["F"]), int(g["B"]), int(g["S"]), float(g["eta"])

@@ -82,5 +82,34 @@ def full(path):
             print(f"| {k} | {units[idx[k]]} | " + " | ".join(r[idx[k]] for r in data) + " |")
 
 
+def traffic(path, gemm, tokens):
+    """profiles/gemm_traffic.json: average DRAM bytes per GEMM launch from a capture of the four GEMMs of one block."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def to_bytes(v, u):
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+
+    per = []
+    for r in data:
+        rd = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+        wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        name = re.sub(r"\(.*", "", r[idx["Kernel Name"]])[-40:]
+        per.append({"kernel": name, "dram_read": rd, "dram_write": wr,
+                    "ms": float(r[idx["gpu__time_duration.sum"]].replace(",", ""))})
+    avg = sum(p["dram_read"] + p["dram_write"] for p in per) / len(per)
+    # algorithmic HBM bytes per token (DESIGN.md section 4): qkv 6144, proj 6144, fc1 6144, fc2 8192
+    algo = int(tokens) * (6144 + 6144 + 6144 + 8192) / 4
+    print(json.dumps({"gemm": gemm, "tokens_per_launch": int(tokens), "dram_bytes_per_launch_avg": avg,
+                      "algorithmic_bytes_per_launch_avg": algo, "launches": per,
+                      "source": f"ncu --set full, {path.split('/')[-1]}"}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
