@@ -229,6 +229,11 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   p.out_hi = out_hi;
   p.out_lo = out_lo;
   p.out_qkv = out_qkv;
+  // measured (profiles/r01i_hint_sweep.log): evict_last operands + streaming outputs is ~2 % faster than no hints,
+  // evict_first activations ~3 % slower (the A tile is re-read by the other n-tiles' CTA pairs out of L2)
+  p.hint_a = env_int("D3D_GEMM_HINT_A", 1);
+  p.hint_b = env_int("D3D_GEMM_HINT_B", 1);
+  p.stream_out = env_int("D3D_GEMM_STREAM_OUT", 1);
   if (mode == D3D_GEMM_SIMT_FP32 || mode == D3D_GEMM_SIMT_F8C) {
     KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, mode_fmt(mode), st));
   } else {

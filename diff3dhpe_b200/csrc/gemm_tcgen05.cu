@@ -153,6 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_a = ptx::make_l2_policy(p.hint_a), pol_b = ptx::make_l2_policy(p.hint_b);
       for (int tile = unit; tile < n_tiles; tile += n_units) {
         const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
         const int n0 = (tile % n_tiles_n) * BN + static_cast<int>(rank) * C::kBRows;
@@ -174,9 +175,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             } else {
               const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), leader);
               if (rank == 0) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * C::kStageBytes);
-              ptx::tma_load_2d_cg2(s, ma, full_leader, c0, m0);
+              ptx::tma_load_2d_cg2_hint(s, ma, full_leader, c0, m0, pol_a);
               if (CS == 1) {
-                ptx::tma_load_2d_cg2(s + kTileBytesA, mb, full_leader, c0, n0);
+                ptx::tma_load_2d_cg2_hint(s + kTileBytesA, mb, full_leader, c0, n0, pol_b);
               } else {
                 // my 64-row slice of the 128-row weight tile, multicast to the CTA at my position in every pair
                 // (the weight maps passed to this instantiation have {128 B x 64 row} boxes)
@@ -317,9 +318,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = row_w + 4 * j + rsub;
-          resv[j] = rr < p.M ? *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(rr) * p.N + colbase +
-                                                                 ci * 32 + gsub * 4)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* src = p.residual + static_cast<size_t>(rr) * p.N + colbase + ci * 32 + gsub * 4;
+          resv[j] = rr >= p.M ? make_float4(0.f, 0.f, 0.f, 0.f)
+                              : (p.stream_out ? ptx::ld_global_cs(src) : *reinterpret_cast<const float4*>(src));
         }
       };
       if (has_res) load_res(0);              // in flight while the accumulator is still being computed
@@ -364,7 +365,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int rr = row_w + 4 * j + rsub;
-            if (rr < p.M) *reinterpret_cast<uint4*>(p.out_f32 + static_cast<size_t>(rr) * p.N + gcol + gsub * 4) = vals[j];
+            if (rr < p.M) {
+              float* dst = p.out_f32 + static_cast<size_t>(rr) * p.N + gcol + gsub * 4;
+              if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
+            }
           }
         } else {
           // fp16 outputs: row = hi (granules 0..3, 32 halves) | second part (granules 4..7):
@@ -425,12 +429,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             for (int j = 0; j < 8; ++j) {
               const int rr = row_w + 4 * j + rsub;
               if (rr >= p.M) continue;
-              if (gsub < 4) {
-                *reinterpret_cast<uint4*>(p.out_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8) = vals[j];
-              } else {
-                uint8_t* dst = c8 + static_cast<size_t>(rr) * (2 * p.N) + (gsub < 6 ? 0 : p.N) + gcol + (gsub & 1) * 16;
-                *reinterpret_cast<uint4*>(dst) = vals[j];
-              }
+              void* dst = gsub < 4 ? static_cast<void*>(p.out_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8)
+                                   : static_cast<void*>(c8 + static_cast<size_t>(rr) * (2 * p.N) + (gsub < 6 ? 0 : p.N) +
+                                                        gcol + (gsub & 1) * 16);
+              if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
             }
           } else {
             __half* dst_base = gsub < 4 ? hi_base : lo_base;
@@ -440,7 +442,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int rr = row_w + 4 * j + rsub;
-              if (rr < p.M && dst_base) *reinterpret_cast<uint4*>(dst_base + static_cast<size_t>(rr) * ld + (gsub & 3) * 8) = vals[j];
+              if (rr < p.M && dst_base) {
+                __half* dst = dst_base + static_cast<size_t>(rr) * ld + (gsub & 3) * 8;
+                if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
+              }
             }
           }
         }

@@ -29,6 +29,10 @@ struct GemmParams {
   __half* out_hi;         // EPI_GELU_SPLIT
   __half* out_lo;
   __half* out_qkv;        // EPI_QKV16
+  // L2 policy knobs (defaults chosen from ncu DRAM-traffic measurements): TMA eviction priority of the
+  // activation (A) and weight (B) operand loads (0 normal, 1 evict_last, 2 evict_first) and streaming (evict-first)
+  // output stores / residual loads
+  int hint_a, hint_b, stream_out;
 };
 
 // A: [M,K] fp16 (hi, lo), W: [N,K] fp16 (hi, lo); K-major.  Tensor maps use a {64, 128} box, SWIZZLE_128B.

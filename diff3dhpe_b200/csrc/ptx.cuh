@@ -126,6 +126,34 @@ __device__ __forceinline__ void tma_load_2d_cg2_mc(void* smem_dst, const CUtenso
         "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority policies for TMA loads: mode 0 normal, 1 evict_last (keep: operands re-read by other CTAs),
+// 2 evict_first (streamed once)
+__device__ __forceinline__ uint64_t make_l2_policy(int mode) {
+  uint64_t pol;
+  if (mode == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (mode == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_cg2_hint(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                     int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+        "l"(policy)
+      : "memory");
+}
+// streaming (evict-first) 16-byte global accesses for data touched once by this kernel
+__device__ __forceinline__ void st_global_cs(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_global_cs(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
