@@ -155,6 +155,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.clips
     gemm_mode = {"split3": _lib.GEMM_TC_SPLIT3, "fp16": _lib.GEMM_TC_FP16, "f8c": _lib.GEMM_TC_F8C}[args.gemm]
