@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("D3D_LIB", _PKG / "libdiff3d_b200.so"))
 
 GEMM_TC_SPLIT3, GEMM_TC_FP16, GEMM_SIMT_FP32, GEMM_TC_F8C, GEMM_SIMT_F8C = 0, 1, 2, 3, 4
-ATTN_DEFAULT, ATTN_SIMT = 0, 1
+ATTN_DEFAULT, ATTN_SIMT, ATTN_MMA_SYNC = 0, 1, 2
 PROF_CLASSES = ("gemm", "attn_spatial", "attn_temporal", "ln", "lift", "head_ddim")
 
 
@@ -56,6 +56,8 @@ PROTOTYPES = {
                                    C.c_void_p]),
     "d3d_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "d3d_op_time_table": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_void_p, C.c_void_p]),
+    "d3d_debug_attention_operand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_void_p]),
     "d3d_debug_forward_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                            C.c_void_p]),
 }

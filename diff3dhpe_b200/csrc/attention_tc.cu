@@ -1,0 +1,399 @@
+// G-tattn on the 5th-generation tensor cores: the temporal GRAND attention core (MODEL:76-83 with the rearranges of
+// MODEL:121,133 folded into the addressing) for F > 64 frames, as a persistent tcgen05 / TMEM / TMA kernel.
+//
+//     O = softmax(Q K^T * hd^-0.5) V  -  V[query]            ((P - I) V == P V - V)
+//
+// Why not the mma.sync kernel of attention_mma.cu: at F = 243 it is bound by shared-memory bandwidth (every warp
+// re-reads all of K and V through ldmatrix for each 16-query tile) and by issue slots (fragment shuffles, online-
+// softmax rescaling): 9.3 ms per call at cfg3 against an HBM floor of 2 ms (profiles/r01h_bench.json).  Here
+//   * one work unit = (clip b, joint j, head h); its Q, K, V_hi slabs ({F rows x 128 B}, row stride J tokens) are
+//     gathered by 4-D TMA boxes straight into the canonical K-major SWIZZLE_128B layout (rows >= F are zero-filled
+//     by the TMA unit), no transposed copy of the activations exists;
+//   * S = Q K^T is ONE tcgen05.mma chain per 128-query tile (M = 128, N = F rounded up to 16, K = 64) into TMEM;
+//   * each of 128 threads owns one query ROW of S (tcgen05.ld, lane = row): the softmax needs no shuffles, no
+//     online rescaling (two passes over TMEM: max, then exp2 / sum), and writes P as packed fp16 back into the
+//     same TMEM columns (tcgen05.st) -- P never touches shared memory;
+//   * O = P V is a second tcgen05.mma chain with A = P from TMEM and B = V from shared memory as an MN-major
+//     operand (V rows are keys, the contraction index), accumulating into the (dead) upper half of S;
+//   * the epilogue normalises, subtracts the exact V row (v_hi from shared memory + v_lo from global), packs the
+//     GEMM A-operand format and leaves through TMA stores (rows >= F are clipped by the hardware).
+// Two CTAs per SM (256 TMEM columns, <= 113 KB shared memory each) overlap one CTA's loads / MMAs with the other's
+// softmax.  The remaining bound is the MUFU unit (F^2 exp2 per unit) next to the HBM floor.
+//
+// Warp roles (192 threads): 0..3 softmax + epilogue (TMEM lane quadrant = warp), 4 = TMA producer, 5 = MMA issuer
+// and TMEM allocator.
+#include "kernels.cuh"
+#include "operand.cuh"
+#include "ptx.cuh"
+
+namespace d3d {
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kTile = 128 * 128;          // bytes of one {64 halves x 128 rows} box
+constexpr int kTmemCols = 256;            // S: up to 256 fp32 columns; P aliases [0,128), O aliases [128,192)
+constexpr int kOCol = 128;
+constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;   // head_dim ** -0.5 (MODEL:65) in the exp2 domain
+
+struct TcBars {
+  uint64_t full;        // TMA bytes of the unit landed                        (producer -> MMA)
+  uint64_t unit_done;   // smem of the unit may be overwritten                 (epilogue -> producer)
+  uint64_t s_full;      // S = Q K^T complete in TMEM                          (MMA -> softmax)
+  uint64_t p_full;      // P written to TMEM by all 128 rows                   (softmax -> MMA)
+  uint64_t o_full;      // O = P V complete in TMEM                            (MMA -> epilogue)
+  uint64_t tmem_free;   // O read out: the columns may receive the next S      (epilogue -> MMA)
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {      // one cvt.rn.f16x2.f32
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// MN-major SWIZZLE_128B operand (V as B of P.V: rows = keys = contraction index, 64 head channels contiguous):
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> 8 keys x 128 B per swizzle atom, next 8 keys
+// SBO = 1024 B further; one atom wide in N (64 halves), so LBO is unused.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
+                        const __grid_constant__ CUtensorMap tm_second, const __half* __restrict__ qkv, int F, int J,
+                        int n_units, int n_mt, int NKp) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* Qs = smem;                               // n_mt tiles, rows = queries
+  uint8_t* Ks = Qs + n_mt * kTile;                  // n_mt tiles, rows = keys (contiguous: one K-major operand)
+  uint8_t* Vs = Ks + n_mt * kTile;                  // n_mt tiles, rows = keys (one MN-major operand)
+  uint8_t* Stg = Vs + n_mt * kTile;                 // 16 KB: second-part staging of one 128-row output tile
+  TcBars* bars = reinterpret_cast<TcBars*>(Stg + kTile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();     // swizzle atoms need 1 KB alignment
+
+  if (warp == 4 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tm_qkv);
+    ptx::prefetch_tensormap(&tm_hi);
+    ptx::prefetch_tensormap(&tm_second);
+    ptx::mbar_init(&bars->full, 1);
+    ptx::mbar_init(&bars->unit_done, 1);
+    ptx::mbar_init(&bars->s_full, 1);
+    ptx::mbar_init(&bars->p_full, 128);
+    ptx::mbar_init(&bars->o_full, 1);
+    ptx::mbar_init(&bars->tmem_free, 128);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 5) ptx::tmem_alloc<kTmemCols>(&bars->tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int n = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++n) {
+        const int seq = unit >> 3, h = unit & 7;
+        const int b = seq / J, j = seq - b * J;
+        ptx::mbar_wait(&bars->unit_done, (n & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars->full, 3 * n_mt * kTile);
+        for (int t = 0; t < n_mt; ++t) {
+          ptx::tma_load_4d(Ks + t * kTile, &tm_qkv, &bars->full, kC + h * kHd, j, t * 128, b);
+          ptx::tma_load_4d(Qs + t * kTile, &tm_qkv, &bars->full, h * kHd, j, t * 128, b);
+          ptx::tma_load_4d(Vs + t * kTile, &tm_qkv, &bars->full, 2 * kC + h * kHd, j, t * 128, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      const uint32_t idesc_qk = ptx::make_idesc_f16(128, static_cast<uint32_t>(NKp), 0);
+      const uint32_t idesc_pv = ptx::make_idesc_f16(128, kHd, 0) | (1u << 16);      // B (= V) is MN-major
+      const uint32_t sQ = ptx::smem_u32(Qs), sK = ptx::smem_u32(Ks), sV = ptx::smem_u32(Vs);
+      const int n_ks = NKp >> 4;
+      int n = 0;
+      uint32_t it = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++n) {
+        ptx::mbar_wait(&bars->full, n & 1);
+        ptx::tc_fence_after();
+        for (int m = 0; m < n_mt; ++m, ++it) {
+          ptx::mbar_wait(&bars->tmem_free, (it & 1) ^ 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)            // S[128, NKp] = Q_m[128, 64] . K[NKp, 64]^T, 16 channels per MMA
+            ptx::mma_f16_ss(tmem_base, ptx::make_desc_k_sw128(sQ + m * kTile + k * 32),
+                            ptx::make_desc_k_sw128(sK + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+          ptx::mma_commit(&bars->s_full);
+          ptx::mbar_wait(&bars->p_full, it & 1);
+          ptx::tc_fence_after();
+          for (int ks = 0; ks < n_ks; ++ks)      // O[128, 64] += P[128, 16 keys] (TMEM) . V[16 keys, 64]
+            ptx::mma_f16_ts(tmem_base + kOCol, tmem_base + ks * 8, make_desc_mn_sw128(sV + ks * 2048), idesc_pv,
+                            ks != 0 ? 1u : 0u);
+          ptx::mma_commit(&bars->o_full);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue: thread = query row
+    const int row_l = warp * 32 + lane;                                   // row inside the 128-query tile
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int n_chunks = (NKp + 31) >> 5;
+    const int sw = (row_l & 7) << 4;                                      // swizzle XOR of this row (bytes)
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int seq = unit >> 3, h = unit & 7;
+      const int b = seq / J, j = seq - b * J;
+      for (int m = 0; m < n_mt; ++m, ++it) {
+        const int r = m * 128 + row_l;
+        const bool valid = r < F;
+        // v_lo row of this query (exact "- V" term): issued now, consumed in the epilogue
+        uint4 vl[8];
+        {
+          const __half* p = qkv + (static_cast<size_t>(b) * F + (valid ? r : 0)) * J * kQkvRow +
+                            static_cast<size_t>(j) * kQkvRow + 3 * kC + h * kHd;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) vl[g] = valid ? ld_nc_v4(p + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        ptx::mbar_wait(&bars->s_full, it & 1);
+        ptx::tc_fence_after();
+
+        // ---- pass 1: row maximum over the F real keys
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < n_chunks; c += 2) {
+          uint32_t ra[32], rb[32];
+          const bool two = c + 1 < n_chunks;
+          ptx::tmem_ld_32x32(taddr + c * 32, ra);
+          if (two) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          ptx::tmem_ld_wait();
+          if ((c + 1) * 32 <= F) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(ra[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < F) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(ra[i]));
+          }
+          if (two) {
+            if ((c + 2) * 32 <= F) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rb[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if ((c + 1) * 32 + i < F) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rb[i]));
+            }
+          }
+        }
+        const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
+
+        // ---- pass 2: P = exp2(S * c - max * c) as packed fp16 into the same TMEM columns, row sum in fp32
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
+          uint32_t pk[16];
+          if ((c + 1) * 32 <= F) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float e0 = ex2_approx(fmaf(__uint_as_float(rr[2 * i]), kScaleLog2e, nmxs));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(rr[2 * i + 1]), kScaleLog2e, nmxs));
+              ls[i & 3] += e0 + e1;
+              pk[i] = pack_f16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c * 32 + 2 * i;
+              const float e0 = col < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * i]), kScaleLog2e, nmxs)) : 0.f;
+              const float e1 = col + 1 < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * i + 1]), kScaleLog2e, nmxs)) : 0.f;
+              ls[i & 3] += e0 + e1;
+              pk[i] = pack_f16x2(e0, e1);
+            }
+          }
+          ptx::tmem_st_32x16(taddr + c * 16, pk);
+        };
+        for (int c = 0; c < n_chunks; c += 2) {
+          uint32_t ra[32], rb[32];
+          const bool two = c + 1 < n_chunks;
+          ptx::tmem_ld_32x32(taddr + c * 32, ra);
+          if (two) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          ptx::tmem_ld_wait();
+          exp_chunk(ra, c);
+          if (two) exp_chunk(rb, c + 1);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars->p_full);
+        const float inv = rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
+
+        // ---- O row out of TMEM, then the columns are free for the next S
+        ptx::mbar_wait(&bars->o_full, it & 1);
+        ptx::tc_fence_after();
+        uint32_t o0[32], o1[32];
+        ptx::tmem_ld_32x32(taddr + kOCol, o0);
+        ptx::tmem_ld_32x32(taddr + kOCol + 32, o1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars->tmem_free);
+
+        // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
+        if (threadIdx.x == 0) ptx::bulk_wait_read_all();      // the previous tile's stores are done reading smem
+        ptx::bar_sync(1, 128);
+        uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // Q_m is dead (S complete): hi staging, swizzled
+        const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint4 vh = *reinterpret_cast<const uint4*>(v_row + ((g << 4) ^ sw));
+          const uint32_t vhw[4] = {vh.x, vh.y, vh.z, vh.w};
+          const uint32_t vlw[4] = {vl[g].x, vl[g].y, vl[g].z, vl[g].w};
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __half2 a = *reinterpret_cast<const __half2*>(&vhw[e]);
+            const __half2 c = *reinterpret_cast<const __half2*>(&vlw[e]);
+            const float oa = __uint_as_float(g < 4 ? o0[8 * g + 2 * e] : o1[8 * (g & 3) + 2 * e]);
+            const float ob = __uint_as_float(g < 4 ? o0[8 * g + 2 * e + 1] : o1[8 * (g & 3) + 2 * e + 1]);
+            x[2 * e] = fmaf(oa, inv, -(__low2float(a) + __low2float(c)));
+            x[2 * e + 1] = fmaf(ob, inv, -(__high2float(a) + __high2float(c)));
+          }
+          uint32_t hw[4], lw[4];
+          float lo[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __half h0 = __float2half_rn(x[2 * e]), h1 = __float2half_rn(x[2 * e + 1]);
+            hw[e] = op_pack_h2(h0, h1);
+            lo[2 * e] = x[2 * e] - __half2float(h0);
+            lo[2 * e + 1] = x[2 * e + 1] - __half2float(h1);
+            if (FMT == FMT_SPLIT16) lw[e] = op_pack_h2(__float2half_rn(lo[2 * e]), __float2half_rn(lo[2 * e + 1]));
+          }
+          *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          if (FMT == FMT_SPLIT16) {            // lo rows: 128 B, swizzled like hi
+            *reinterpret_cast<uint4*>(Stg + row_l * 128 + ((g << 4) ^ sw)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          } else {                             // c8: [128 rows][64 B] e5m2(x 2^-8), then [128 rows][64 B] e5m2(lo 2^4)
+            *reinterpret_cast<uint2*>(Stg + row_l * 64 + g * 8) =
+                make_uint2(op_e5m2x4(x[0] * kActHiScale, x[1] * kActHiScale, x[2] * kActHiScale, x[3] * kActHiScale),
+                           op_e5m2x4(x[4] * kActHiScale, x[5] * kActHiScale, x[6] * kActHiScale, x[7] * kActHiScale));
+            *reinterpret_cast<uint2*>(Stg + 8192 + row_l * 64 + g * 8) =
+                make_uint2(op_e5m2x4(lo[0] * kActLoScale, lo[1] * kActLoScale, lo[2] * kActLoScale, lo[3] * kActLoScale),
+                           op_e5m2x4(lo[4] * kActLoScale, lo[5] * kActLoScale, lo[6] * kActLoScale, lo[7] * kActLoScale));
+          }
+        }
+        ptx::fence_proxy_async();
+        ptx::bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+          ptx::tma_store_4d(&tm_hi, Qs + m * kTile, h * kHd, j, m * 128, b);
+          if (FMT == FMT_SPLIT16) {
+            ptx::tma_store_4d(&tm_second, Stg, h * kHd, j, m * 128, b);
+          } else {
+            ptx::tma_store_4d(&tm_second, Stg, h * kHd, j, m * 128, b);
+            ptx::tma_store_4d(&tm_second, Stg + 8192, kC + h * kHd, j, m * 128, b);
+          }
+          ptx::bulk_commit();
+        }
+      }
+      if (threadIdx.x == 0) {          // V (v_hi rows) and the staging tiles of this unit are no longer read
+        ptx::bulk_wait_read_all();
+        ptx::mbar_arrive(&bars->unit_done);
+      }
+    }
+    if (threadIdx.x == 0) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// [B, F, J, row] token-major array viewed as a 4-D tensor (channel, j, f, b); box = {64 channels, 1, 128 frames, 1}
+int encode_tokens_4d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int elem_bytes, int64_t row_elems, int J,
+                     int F, int64_t B, CUtensorMapSwizzle swz) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return -1;
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t row_bytes = static_cast<cuuint64_t>(row_elems) * elem_bytes;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(J), static_cast<cuuint64_t>(F),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {row_bytes, row_bytes * J, row_bytes * J * F};
+  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(out, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+int tc_smem_bytes(int n_mt) { return (3 * n_mt + 1) * kTile + static_cast<int>(sizeof(TcBars)); }
+
+}  // namespace
+
+int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int F, int J,
+                      int64_t max_clips) {
+  if (encode_tokens_4d(&maps->qkv, const_cast<__half*>(qkv), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kQkvRow, J, F,
+                       max_clips, CU_TENSOR_MAP_SWIZZLE_128B))
+    return -1;
+  if (encode_tokens_4d(&maps->o_hi, o_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, J, F, max_clips,
+                       CU_TENSOR_MAP_SWIZZLE_128B))
+    return -1;
+  if (fmt == FMT_F8C)
+    return encode_tokens_4d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 2 * kC, J, F, max_clips,
+                            CU_TENSOR_MAP_SWIZZLE_NONE);
+  return encode_tokens_4d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, J, F, max_clips,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+cudaError_t configure_attention_tc() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_SPLIT16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                tc_smem_bytes(2))) != cudaSuccess)
+    return e;
+  return cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_F8C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              tc_smem_bytes(2));
+}
+
+cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
+                                    cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  if (F <= 64 || F > 256) return cudaErrorInvalidValue;
+  const int n_mt = (F + 127) / 128;
+  const int NKp = (F + 15) / 16 * 16;
+  const int n_units = B * J * kHeads;
+  const int grid = n_units < 2 * num_sms ? n_units : 2 * num_sms;
+  auto kern = fmt == FMT_F8C ? attn_temporal_tc_kernel<FMT_F8C> : attn_temporal_tc_kernel<FMT_SPLIT16>;
+  kern<<<grid, kTcThreads, tc_smem_bytes(n_mt), st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, n_units, n_mt, NKp);
+  return cudaGetLastError();
+}
+
+}  // namespace d3d

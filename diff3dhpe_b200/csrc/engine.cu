@@ -67,6 +67,8 @@ struct d3d_handle {
   float* X = nullptr;
   __half* QKV = nullptr;     // packed fp16 q | k | v_hi | v_lo, [tok_cap, 2048]
   OperandBuf A, ATT, H;
+  AttnTcMaps attn_tc;        // tcgen05 temporal attention: maps bound to QKV -> ATT
+  bool have_attn_tc = false;
   float *in_x2d = nullptr, *y = nullptr, *in_noise = nullptr;
   int64_t in_noise_cap = 0;
   float *t_f32 = nullptr, *e0 = nullptr, *h1 = nullptr, *h2 = nullptr;   // time-MLP scratch, max(max_clips, S) rows
@@ -254,10 +256,17 @@ int run_attention(d3d_handle* h, const __half* qkv, __half* o_hi, __half* o_lo, 
     else
       KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial(qkv, o_hi, o_lo, o_f32, h->fmt, static_cast<int64_t>(B) * h->F, h->J, st));
   } else {
-    if (mode == D3D_ATTN_SIMT)
+    if (mode == D3D_ATTN_SIMT) {
       KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_simt(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));
-    else
+    } else if (mode == D3D_ATTN_DEFAULT && h->have_attn_tc && qkv == h->QKV && env_int("D3D_ATTN_TC", 1)) {
+      // the tcgen05 kernel's tensor maps are bound to QKV -> ATT; an fp32 result (op-level entry point) is merged
+      // from the operand pair afterwards
+      if (!o_f32 && (o_hi != h->ATT.hi || o_lo != h->ATT.lo)) return fail(h, -2, "attention output must be the ATT operand");
+      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_tc(h->attn_tc, qkv, h->fmt, B, h->F, h->J, h->num_sms, st));
+      if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, o_f32, static_cast<int64_t>(B) * h->F * h->J, kC, h->fmt, st));
+    } else {
       KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));
+    }
   }
   return 0;
 }
@@ -436,6 +445,7 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
     CK(configure_gemm_tc());
     CK(configure_attention());
     CK(configure_attention_mma());
+    CK(configure_attention_tc());
     for (auto& b : h->blk) {
       if ((r = alloc_lin(h, &b.qkv, 3 * kC, kC))) return r;
       if ((r = alloc_lin(h, &b.proj, kC, kC))) return r;
@@ -463,6 +473,11 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
     if ((r = alloc_operand(h, &h->A, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->ATT, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->H, h->tok_cap, kHidden))) return r;
+    if (h->F > 64) {
+      if (make_attn_tc_maps(&h->attn_tc, h->QKV, h->ATT.hi, h->ATT.lo, h->fmt, h->F, h->J, cfg->max_clips))
+        return fail(h, -20, "cuTensorMapEncodeTiled failed for the temporal-attention maps");
+      h->have_attn_tc = true;
+    }
     if ((r = dev_alloc(h, &h->in_x2d, T * 2))) return r;
     if ((r = dev_alloc(h, &h->y, T * 3))) return r;
     h->t_rows_cap = cfg->max_clips > 1024 ? cfg->max_clips : 1024;
@@ -838,6 +853,21 @@ int d3d_op_attention(d3d_handle* h, const float* qkv, float* out, int32_t B, int
   // the hot path receives q | k | v_hi | v_lo fp16 rows from the qkv GEMM epilogue; here they are packed from fp32
   KL(launch_pack_qkv16(qkv, h->QKV, static_cast<int64_t>(B) * h->F * h->J, st));
   return run_attention(h, h->QKV, nullptr, nullptr, out, B, spatial != 0, attn_mode, st);
+}
+
+int d3d_debug_attention_operand(d3d_handle* h, const float* qkv, void* hi_out, void* second_out, int32_t B,
+                                int32_t spatial, int32_t attn_mode, void* stream) {
+  if (!h || !qkv || !hi_out || !second_out) return -1;
+  if (B < 1 || B > h->cfg.max_clips) return fail(h, -2, "B out of range [1, max_clips]");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  KL(launch_pack_qkv16(qkv, h->QKV, T, st));
+  int r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial != 0, attn_mode, st);
+  if (r) return r;
+  CK(cudaMemcpyAsync(hi_out, h->ATT.hi, static_cast<size_t>(T) * kC * 2, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(second_out, h->ATT.lo, static_cast<size_t>(T) * kC * 2, cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
 
 int d3d_op_time_table(d3d_handle* h, const float* t_host, int32_t R, float* out, void* stream) {

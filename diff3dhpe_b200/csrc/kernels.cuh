@@ -108,6 +108,16 @@ cudaError_t launch_attn_spatial(const __half* qkv, __half* o_hi, __half* o_lo, f
                                 int J, cudaStream_t st);
 cudaError_t launch_attn_temporal_mma(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                      int J, cudaStream_t st);
+// tcgen05 / TMEM / TMA temporal kernel (attention_tc.cu), 64 < F <= 256.  Its tensor maps are bound to one packed
+// qkv array and one output operand (hi + second array in format fmt) of up to max_clips clips.
+struct AttnTcMaps {
+  CUtensorMap qkv, o_hi, o_second;
+};
+int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int F, int J,
+                      int64_t max_clips);
+cudaError_t configure_attention_tc();
+cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
+                                    cudaStream_t st);
 // CUDA-core validation kernels (fp32 arithmetic on the same packed input)
 cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                       int J, cudaStream_t st);

@@ -207,6 +207,16 @@ class Engine:
                    self.h, "d3d_op_attention")
         return out
 
+    def debug_attention_operand(self, qkv, B, spatial, attn_mode=_lib.ATTN_DEFAULT):
+        """Attention output in the raw A-operand format of the proj GEMM: (hi fp16 [T,C], second uint8 [T,2C])."""
+        T = qkv.shape[0]
+        hi = torch.empty((T, self.C), device=self.device, dtype=torch.float16)
+        second = torch.empty((T, 2 * self.C), device=self.device, dtype=torch.uint8)
+        _lib.check(self.lib.d3d_debug_attention_operand(self.h, _ptr(qkv), _ptr(hi), _ptr(second), B, int(spatial),
+                                                        attn_mode, self._stream()), self.h,
+                   "d3d_debug_attention_operand")
+        return hi, second
+
     def op_time_table(self, t_host: Sequence[float]):
         R = len(t_host)
         arr = (C.c_float * R)(*[float(v) for v in t_host])

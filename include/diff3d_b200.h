@@ -55,8 +55,10 @@ enum {
 };
 /* Attention kernels. */
 enum {
-  D3D_ATTN_DEFAULT = 0,   /* spatial: smem/register kernel; temporal: tensor-core flash kernel */
-  D3D_ATTN_SIMT = 1       /* CUDA-core fp32 validation kernels */
+  D3D_ATTN_DEFAULT = 0,   /* spatial: mma.sync smem/register kernel; temporal: tcgen05/TMEM/TMA kernel for F > 64,
+                             mma.sync flash kernel for short sequences */
+  D3D_ATTN_SIMT = 1,      /* CUDA-core fp32 validation kernels */
+  D3D_ATTN_MMA_SYNC = 2   /* force the mma.sync (legacy tensor path) kernels for every F */
 };
 
 /* Mirrors the constructor of ConditionalDiffusionMixSTES2SGRANDLinLift (MODEL:140-142). */
@@ -178,6 +180,12 @@ D3D_API int d3d_op_time_table(d3d_handle* h, const float* t_host, int32_t R, flo
  * residual stream [B*F*J, C] as it stands BEFORE the next post-norm into x_out_dev. */
 D3D_API int d3d_debug_forward_blocks(d3d_handle* h, const float* x5_dev, const int64_t* t_dev, int32_t B,
                              int32_t n_blocks, float* x_out_dev, void* stream);
+
+/* Runs one attention core like d3d_op_attention but returns the result in the raw GEMM A-operand format the proj
+ * GEMM consumes: hi_out_dev [T, C] fp16 and second_out_dev [T, 2*C] bytes (operand format of the handle's gemm_mode:
+ * fp16 lo[C], or uint8 e5m2(x * 2^-8)[C] | e5m2((x - hi) * 2^4)[C]). */
+D3D_API int d3d_debug_attention_operand(d3d_handle* h, const float* qkv_dev, void* hi_out_dev, void* second_out_dev,
+                                int32_t B, int32_t spatial, int32_t attn_mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -90,7 +90,7 @@ def test_layernorm(eng27, eps):
 
 
 @pytest.mark.parametrize("F", [27, 81, 243, 9, 100, 1, 256])
-@pytest.mark.parametrize("mode,tol", [(_lib.ATTN_DEFAULT, 4e-3), (_lib.ATTN_SIMT, 3e-5)])
+@pytest.mark.parametrize("mode,tol", [(_lib.ATTN_DEFAULT, 4e-3), (_lib.ATTN_SIMT, 3e-5), (_lib.ATTN_MMA_SYNC, 4e-3)])
 @pytest.mark.parametrize("spatial", [True, False])
 def test_attention_core(F, mode, tol, spatial):
     """The kernels read q, k as fp16 and v as an fp16 hi/lo pair (what the qkv GEMM epilogue writes), so the
@@ -108,6 +108,36 @@ def test_attention_core(F, mode, tol, spatial):
     out = eng.op_attention(qkv.cuda(), B, spatial, mode).cpu().view(B, F, J, C)
     eng.close()
     assert (out - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_TC_F8C, _lib.GEMM_TC_SPLIT3])
+@pytest.mark.parametrize("F,B", [(243, 5), (81, 6), (129, 3), (128, 3), (65, 4), (256, 2)])
+def test_temporal_attention_tcgen05_operand(F, B, gemm_mode):
+    """The tcgen05/TMEM/TMA temporal kernel (default for F > 64) against the CUDA-core kernel, on EVERY byte of the
+    operand the proj GEMM consumes (hi fp16 | fp16 lo, or hi | e5m2(x 2^-8) | e5m2(lo 2^4)); B x 17 x 8 work units
+    exceed one wave of 2 x 148 CTAs, so the persistent loop, its barrier phases and the staging reuse are exercised."""
+    J, C = 17, 512
+    eng = Engine(F, max_clips=B, gemm_mode=gemm_mode)
+    qkv = _rand((B * F * J, 3 * C), 70 + F, 1.5)
+    qkv[:, :2 * C] = qkv[:, :2 * C].half().float()
+    ref = eng.op_attention(qkv.cuda(), B, False, _lib.ATTN_SIMT).cpu()
+    hi, second = eng.debug_attention_operand(qkv.cuda(), B, False, _lib.ATTN_DEFAULT)
+    hi_s, second_s = eng.debug_attention_operand(qkv.cuda(), B, False, _lib.ATTN_SIMT)
+    eng.close()
+    hi, hi_s = hi.float().cpu(), hi_s.float().cpu()
+    assert torch.isfinite(hi).all()
+    assert (hi - ref).abs().max().item() < 4e-3 + 2 ** -10 * ref.abs().max().item()
+    if gemm_mode == _lib.GEMM_TC_SPLIT3:
+        lo = second.view(torch.float16).float().cpu()
+        assert (hi + lo - ref).abs().max().item() < 4e-3
+    else:
+        a8 = second[:, :C].view(torch.float8_e5m2).float().cpu() * 256.0
+        lo8 = second[:, C:].view(torch.float8_e5m2).float().cpu() / 16.0
+        assert (a8 - ref).abs().max().item() < 4e-3 + 0.13 * ref.abs().max().item()
+        assert ((a8 - ref).abs() <= 0.126 * ref.abs() + 4e-3).all()
+        assert (hi + lo8 - ref).abs().max().item() < 4e-3
+        # lo is the residual of THIS kernel's hi: |lo8 - (x - hi)| <= 12.5 % of one fp16 half-ulp of x
+        assert (lo8.abs() <= 2 ** -11 * hi.abs() * 1.13 + 1e-7).all()
 
 
 def test_time_table_golden(golden):

@@ -242,6 +242,76 @@ def sampler_f8c_f9_s9():
     return _sampler(3, 0, True, "sampler_f9_b2_s9_clip")
 
 
+def _attn_tc(F, B, gemm_mode=3):
+    """tcgen05 temporal kernel vs the CUDA-core kernel: error statistics by query row / head / channel to localise
+    layout bugs (descriptor, swizzle, TMEM packing)."""
+    torch, _lib, synthetic, Engine = _imports()
+    J, C = 17, 512
+    eng = Engine(F, max_clips=B, gemm_mode=gemm_mode)
+    g = torch.Generator().manual_seed(7)
+    qkv = torch.randn(B * F * J, 3 * C, generator=g) * 1.5
+    qkv[:, :2 * C] = qkv[:, :2 * C].half().float()
+    ref = eng.op_attention(qkv.cuda(), B, False, 1).cpu().view(B, F, J, 8, 64)
+    out = eng.op_attention(qkv.cuda(), B, False, 0).cpu().view(B, F, J, 8, 64)
+    hi, second = eng.debug_attention_operand(qkv.cuda(), B, False, 0)
+    torch.cuda.synchronize()
+    err = (out - ref).abs()
+    res = {"max_err": err.max().item(), "mean_err": err.mean().item(), "finite": bool(torch.isfinite(out).all()),
+           "err_by_clip": [round(v, 5) for v in err.amax(dim=(1, 2, 3, 4)).tolist()],
+           "err_by_head": [round(v, 5) for v in err.amax(dim=(0, 1, 2, 4)).tolist()],
+           "err_by_frame_first8": [round(v, 5) for v in err.amax(dim=(0, 2, 3, 4)).tolist()[:8]],
+           "err_by_frame_128_136": [round(v, 5) for v in err.amax(dim=(0, 2, 3, 4)).tolist()[128:136]],
+           "err_by_frame_last4": [round(v, 5) for v in err.amax(dim=(0, 2, 3, 4)).tolist()[-4:]],
+           "err_by_chan_first8": [round(v, 5) for v in err.amax(dim=(0, 1, 2, 3)).tolist()[:8]],
+           "out0": out[0, 0, 0, 0, :4].tolist(), "ref0": ref[0, 0, 0, 0, :4].tolist()}
+    hi = hi.float().cpu().view(B, F, J, 8, 64)
+    res["hi_err"] = (hi - ref).abs().max().item()
+    if gemm_mode == 3:
+        a8 = second[:, :C].view(torch.float8_e5m2).float().cpu().view(B, F, J, 8, 64) * 256.0
+        res["a8_rel_err"] = ((a8 - ref).abs() / (ref.abs() + 1e-2)).max().item()
+    return res
+
+
+@stage
+def attn_tc_f243():
+    return _attn_tc(243, 5)
+
+
+@stage
+def attn_tc_f81():
+    return _attn_tc(81, 3)
+
+
+@stage
+def attn_tc_f243_split16():
+    return _attn_tc(243, 2, gemm_mode=0)
+
+
+@stage
+def bench_attention_tc():
+    """ms / call of the temporal attention alone at 256 clips x 243 frames: tcgen05 kernel vs mma.sync kernel, timed
+    on the operand path (pack kernel excluded by timing a pair of calls with and without attention is not possible
+    through the ABI, so the pack + copies are included in both and reported separately)."""
+    torch, _lib, synthetic, Engine = _imports()
+    B, F = 256, 243
+    eng = Engine(F, max_clips=B)
+    qkv = torch.randn(B * F * 17, 1536, device="cuda")
+    out = {}
+    for name, mode in (("tc", 0), ("mma_sync", 2), ("spatial", -1)):
+        args = (qkv, B, mode < 0, 0 if mode < 0 else mode)
+        for _ in range(2):
+            eng.debug_attention_operand(*args)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            eng.debug_attention_operand(*args)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name + "_plus_pack_ms"] = round(e0.elapsed_time(e1) / 5, 3)
+    return out
+
+
 @stage
 def bench_gemm():
     """ms / launch of the GEMM kernel alone at the cfg3 half-batch size (M = 1 057 536 tokens)."""
@@ -289,7 +359,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         print("RESULT " + json.dumps(STAGES[sys.argv[1]]()), flush=True)
         sys.exit(0)
+    only = os.environ.get("STAGES")
     for name in STAGES:
+        if only and name not in only.split(","):
+            continue
         try:
             p = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=400)
             res = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]

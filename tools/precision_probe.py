@@ -78,7 +78,12 @@ class Policy(TorchFunctionMode):
             x, w = args[0], args[1]
             b = args[2] if len(args) > 2 else kwargs.get("bias")
             with torch._C.DisableTorchFunction():
-                out = mm_mode(x, w.t(), self.lin)
+                if self.lin.endswith("_qk1") and w.shape[0] == 1536:
+                    # q | k columns: ONE fp16 pass (they are rounded to fp16 for the attention MMAs anyway); v: corrected
+                    base = self.lin[:-4]
+                    out = torch.cat([mm_mode(x, w[:1024].t(), "fp16"), mm_mode(x, w[1024:].t(), base)], dim=-1)
+                else:
+                    out = mm_mode(x, w.t(), self.lin[:-4] if self.lin.endswith("_qk1") else self.lin)
                 return out + b if b is not None else out
         if func in (torch.matmul, torch.Tensor.matmul, torch.Tensor.__matmul__) and self.attn != "fp32":
             a, b = args
@@ -88,6 +93,11 @@ class Policy(TorchFunctionMode):
                 self.n_qk += 1
                 if self.attn == "qk3pv1":
                     return mm_mode(a, b, "split3" if is_qk else "fp16")
+                if self.attn == "fp16xv":      # shipped kernel: fp16 QK^T and PV, the GRAND "- V" term exact
+                    if is_qk:
+                        return mm_mode(a, b, "fp16")
+                    eye = torch.eye(a.shape[-1], dtype=a.dtype)
+                    return mm_mode(a + eye, b, "fp16") - b
                 return mm_mode(a, b, self.attn)
         return func(*args, **kwargs)
 
@@ -105,8 +115,11 @@ def main():
         with torch.no_grad():
             ref = oracle.ddim_sample_loop(sd, x2d, y_T, steps, sampling_timesteps=S, clip_denoised=clip)
         print(f"F={Fr} B={B} S={S} clip_denoised={clip}  |ref|max={ref.abs().max():.3f}", flush=True)
-        for lin, attn in (("fp16", "fp16"), ("split3", "fp16"), ("split3", "split3"), ("f8corr", "fp16"),
-                          ("f8corr", "split3"), ("f8corr", "qk3pv1"), ("split2a", "split3")):
+        policies = (("fp16", "fp16"), ("split3", "fp16"), ("split3", "split3"), ("f8corr", "fp16"),
+                    ("f8corr", "split3"), ("f8corr", "qk3pv1"), ("split2a", "split3"))
+        if os.environ.get("PROBE_POLICIES"):     # e.g. PROBE_POLICIES=f8c52:fp16xv,f8c52_qk1:fp16xv
+            policies = tuple(tuple(p.split(":")) for p in os.environ["PROBE_POLICIES"].split(","))
+        for lin, attn in policies:
             with torch.no_grad(), Policy(lin, attn):
                 out = oracle.ddim_sample_loop(sd, x2d, y_T, steps, sampling_timesteps=S, clip_denoised=clip)
             err = (out - ref).abs()
