@@ -29,19 +29,24 @@
 namespace d3d {
 namespace {
 
-constexpr int kTcThreads = 192;
 constexpr int kTile = 128 * 128;          // bytes of one {64 halves x 128 rows} box
-constexpr int kTmemCols = 256;            // S: up to 256 fp32 columns; P aliases [0,128), O aliases [128,192)
+constexpr int kSlotCols = 256;            // TMEM columns of one slot: S up to 256 fp32; P aliases [0,128), O [128,192)
 constexpr int kOCol = 128;
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;   // head_dim ** -0.5 (MODEL:65) in the exp2 domain
 
+// NSLOT = 128-query tiles in flight per CTA (each with its own 4 softmax warps and 256 TMEM columns) = shared-memory
+// stages (units resident per CTA):
+//   NSLOT 2 (default): one CTA per SM, 320 threads.  While slot 0 runs its softmax on the CUDA cores, slot 1 is in
+//            its tensor-core phase (and vice versa), and the NEXT unit's Q/K/V are already landing in the other stage.
+//   NSLOT 1: two CTAs per SM, 192 threads, one stage: the first version (kept for A/B measurements).
+template <int NSLOT>
 struct TcBars {
-  uint64_t full;        // TMA bytes of the unit landed                        (producer -> MMA)
-  uint64_t unit_done;   // smem of the unit may be overwritten                 (epilogue -> producer)
-  uint64_t s_full;      // S = Q K^T complete in TMEM                          (MMA -> softmax)
-  uint64_t p_full;      // P written to TMEM by all 128 rows                   (softmax -> MMA)
-  uint64_t o_full;      // O = P V complete in TMEM                            (MMA -> epilogue)
-  uint64_t tmem_free;   // O read out: the columns may receive the next S      (epilogue -> MMA)
+  uint64_t full[NSLOT];         // TMA bytes of the unit in this stage landed              (producer -> MMA)
+  uint64_t stage_free[NSLOT];   // every tile of the unit has left this stage               (epilogues -> producer)
+  uint64_t s_full[NSLOT];       // S = Q K^T complete in this slot's TMEM columns           (MMA -> softmax)
+  uint64_t p_full[NSLOT];       // P written to TMEM by all 128 rows                        (softmax -> MMA)
+  uint64_t o_full[NSLOT];       // O = P V complete                                         (MMA -> epilogue)
+  uint64_t tmem_free[NSLOT];    // O read out: the columns may receive the next S           (epilogue -> MMA)
   uint32_t tmem_base;
 };
 
@@ -79,253 +84,275 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(kTcThreads, 2)
+
+// Work items of a CTA, in order: w = 0, 1, 2, ... ; unit n = w / n_mt (the CTA's n-th unit), 128-query tile
+// m = w % n_mt; slot = w % NSLOT (i-th item of that slot, i = w / NSLOT); stage = n % NSLOT (k-th use, k = n / NSLOT).
+template <int FMT, int NSLOT>
+__global__ void __launch_bounds__(128 * NSLOT + 64, NSLOT == 1 ? 2 : 1)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
                         const __grid_constant__ CUtensorMap tm_second, const __half* __restrict__ qkv, int F, int J,
                         int n_units, int n_mt, int NKp) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* Qs = smem;                               // n_mt tiles, rows = queries
-  uint8_t* Ks = Qs + n_mt * kTile;                  // n_mt tiles, rows = keys (contiguous: one K-major operand)
-  uint8_t* Vs = Ks + n_mt * kTile;                  // n_mt tiles, rows = keys (one MN-major operand)
-  uint8_t* Stg = Vs + n_mt * kTile;                 // 16 KB: second-part staging of one 128-row output tile
-  TcBars* bars = reinterpret_cast<TcBars*>(Stg + kTile);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // two CTAs per SM (NSLOT 1) leave no room for alignment slack: the base is checked instead
+  uint8_t* smem = NSLOT == 1 ? smem_raw
+                             : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = 3 * n_mt * kTile;          // Q tiles | K tiles | V tiles of one unit
+  uint8_t* StgAll = smem + NSLOT * stage_bytes;      // 16 KB per slot: second-part staging of one 128-row output tile
+  TcBars<NSLOT>* bars = reinterpret_cast<TcBars<NSLOT>*>(StgAll + NSLOT * kTile);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kTmaWarp = 4 * NSLOT, kMmaWarp = 4 * NSLOT + 1;
   if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();     // swizzle atoms need 1 KB alignment
+  const int n_local = blockIdx.x < n_units ? (n_units - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+  const int W = n_local * n_mt;
 
-  if (warp == 4 && ptx::elect_one()) {
+  if (warp == kTmaWarp && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tm_qkv);
     ptx::prefetch_tensormap(&tm_hi);
     ptx::prefetch_tensormap(&tm_second);
-    ptx::mbar_init(&bars->full, 1);
-    ptx::mbar_init(&bars->unit_done, 1);
-    ptx::mbar_init(&bars->s_full, 1);
-    ptx::mbar_init(&bars->p_full, 128);
-    ptx::mbar_init(&bars->o_full, 1);
-    ptx::mbar_init(&bars->tmem_free, 128);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->stage_free[s], n_mt);
+      ptx::mbar_init(&bars->s_full[s], 1);
+      ptx::mbar_init(&bars->p_full[s], 128);
+      ptx::mbar_init(&bars->o_full[s], 1);
+      ptx::mbar_init(&bars->tmem_free[s], 128);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 5) ptx::tmem_alloc<kTmemCols>(&bars->tmem_base);
+  if (warp == kMmaWarp) ptx::tmem_alloc<kSlotCols * NSLOT>(&bars->tmem_base);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      int n = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++n) {
+      for (int n = 0; n < n_local; ++n) {
+        const int unit = blockIdx.x + n * gridDim.x;
         const int seq = unit >> 3, h = unit & 7;
         const int b = seq / J, j = seq - b * J;
-        ptx::mbar_wait(&bars->unit_done, (n & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&bars->full, 3 * n_mt * kTile);
+        const int stage = n % NSLOT, k = n / NSLOT;
+        uint8_t* Qs = smem + stage * stage_bytes;
+        uint8_t* Ks = Qs + n_mt * kTile;
+        uint8_t* Vs = Ks + n_mt * kTile;
+        ptx::mbar_wait(&bars->stage_free[stage], (k & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars->full[stage], 3 * n_mt * kTile);
         for (int t = 0; t < n_mt; ++t) {
-          ptx::tma_load_4d(Ks + t * kTile, &tm_qkv, &bars->full, kC + h * kHd, j, t * 128, b);
-          ptx::tma_load_4d(Qs + t * kTile, &tm_qkv, &bars->full, h * kHd, j, t * 128, b);
-          ptx::tma_load_4d(Vs + t * kTile, &tm_qkv, &bars->full, 2 * kC + h * kHd, j, t * 128, b);
+          ptx::tma_load_4d(Ks + t * kTile, &tm_qkv, &bars->full[stage], kC + h * kHd, j, t * 128, b);
+          ptx::tma_load_4d(Qs + t * kTile, &tm_qkv, &bars->full[stage], h * kHd, j, t * 128, b);
+          ptx::tma_load_4d(Vs + t * kTile, &tm_qkv, &bars->full[stage], 2 * kC + h * kHd, j, t * 128, b);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (ptx::elect_one()) {
       const uint32_t idesc_qk = ptx::make_idesc_f16(128, static_cast<uint32_t>(NKp), 0);
       const uint32_t idesc_pv = ptx::make_idesc_f16(128, kHd, 0) | (1u << 16);      // B (= V) is MN-major
-      const uint32_t sQ = ptx::smem_u32(Qs), sK = ptx::smem_u32(Ks), sV = ptx::smem_u32(Vs);
+      const uint32_t s0 = ptx::smem_u32(smem);
       const int n_ks = NKp >> 4;
-      int n = 0;
-      uint32_t it = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++n) {
-        ptx::mbar_wait(&bars->full, n & 1);
+      auto issue_pv = [&](int w) {           // O[128, 64] = P[128, NKp] (TMEM) . V[NKp, 64], 16 keys per MMA
+        const int slot = w % NSLOT, i = w / NSLOT, stage = (w / n_mt) % NSLOT;
+        const uint32_t sV = s0 + stage * stage_bytes + 2 * n_mt * kTile;
+        const uint32_t tcol = tmem_base + slot * kSlotCols;
+        ptx::mbar_wait(&bars->p_full[slot], i & 1);
         ptx::tc_fence_after();
-        for (int m = 0; m < n_mt; ++m, ++it) {
-          ptx::mbar_wait(&bars->tmem_free, (it & 1) ^ 1);
+        for (int ks = 0; ks < n_ks; ++ks)
+          ptx::mma_f16_ts(tcol + kOCol, tcol + ks * 8, make_desc_mn_sw128(sV + ks * 2048), idesc_pv, ks != 0 ? 1u : 0u);
+        ptx::mma_commit(&bars->o_full[slot]);
+      };
+      for (int w = 0; w < W; ++w) {
+        const int n = w / n_mt, m = w - n * n_mt;
+        const int slot = w % NSLOT, i = w / NSLOT, stage = n % NSLOT;
+        const uint32_t sQ = s0 + stage * stage_bytes, sK = sQ + n_mt * kTile;
+        if (m == 0) {
+          ptx::mbar_wait(&bars->full[stage], (n / NSLOT) & 1);
           ptx::tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)            // S[128, NKp] = Q_m[128, 64] . K[NKp, 64]^T, 16 channels per MMA
-            ptx::mma_f16_ss(tmem_base, ptx::make_desc_k_sw128(sQ + m * kTile + k * 32),
-                            ptx::make_desc_k_sw128(sK + k * 32), idesc_qk, k != 0 ? 1u : 0u);
-          ptx::mma_commit(&bars->s_full);
-          ptx::mbar_wait(&bars->p_full, it & 1);
-          ptx::tc_fence_after();
-          for (int ks = 0; ks < n_ks; ++ks)      // O[128, 64] += P[128, 16 keys] (TMEM) . V[16 keys, 64]
-            ptx::mma_f16_ts(tmem_base + kOCol, tmem_base + ks * 8, make_desc_mn_sw128(sV + ks * 2048), idesc_pv,
-                            ks != 0 ? 1u : 0u);
-          ptx::mma_commit(&bars->o_full);
         }
+        ptx::mbar_wait(&bars->tmem_free[slot], (i & 1) ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)            // S[128, NKp] = Q_m[128, 64] . K[NKp, 64]^T, 16 channels per MMA
+          ptx::mma_f16_ss(tmem_base + slot * kSlotCols, ptx::make_desc_k_sw128(sQ + m * kTile + k * 32),
+                          ptx::make_desc_k_sw128(sK + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+        ptx::mma_commit(&bars->s_full[slot]);
+        // the P.V of the item NSLOT-1 back: with two slots, S of this item is already being computed while the other
+        // slot's softmax finishes
+        if (w >= NSLOT - 1) issue_pv(w - (NSLOT - 1));
       }
+      for (int w = W - (NSLOT - 1); w < W; ++w)
+        if (w >= 0) issue_pv(w);
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue: thread = query row
-    const int row_l = warp * 32 + lane;                                   // row inside the 128-query tile
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int slot = warp >> 2;
+    const int row_l = (warp & 3) * 32 + lane;                             // row inside the 128-query tile
+    const uint32_t taddr = tmem_base + slot * kSlotCols + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int n_chunks = (NKp + 31) >> 5;
     const int sw = (row_l & 7) << 4;                                      // swizzle XOR of this row (bytes)
-    uint32_t it = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const bool issuer = row_l == 0;                                       // issues the slot's TMA stores
+    uint8_t* Stg = StgAll + slot * kTile;
+    for (int w = slot; w < W; w += NSLOT) {
+      const int n = w / n_mt, m = w - n * n_mt;
+      const int i = w / NSLOT, stage = n % NSLOT;
+      const int unit = blockIdx.x + n * gridDim.x;
       const int seq = unit >> 3, h = unit & 7;
       const int b = seq / J, j = seq - b * J;
-      for (int m = 0; m < n_mt; ++m, ++it) {
-        const int r = m * 128 + row_l;
-        const bool valid = r < F;
-        // v_lo row of this query (exact "- V" term): issued now, consumed in the epilogue
-        uint4 vl[8];
-        {
-          const __half* p = qkv + (static_cast<size_t>(b) * F + (valid ? r : 0)) * J * kQkvRow +
-                            static_cast<size_t>(j) * kQkvRow + 3 * kC + h * kHd;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) vl[g] = valid ? ld_nc_v4(p + g * 8) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        ptx::mbar_wait(&bars->s_full, it & 1);
-        ptx::tc_fence_after();
+      uint8_t* Qs = smem + stage * stage_bytes;
+      const uint8_t* Vs = Qs + 2 * n_mt * kTile;
+      const int r = m * 128 + row_l;
+      const bool valid = r < F;
+      ptx::mbar_wait(&bars->s_full[slot], i & 1);
+      ptx::tc_fence_after();
 
-        // ---- pass 1: row maximum over the F real keys
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int c = 0; c < n_chunks; c += 2) {
-          uint32_t ra[32], rb[32];
-          const bool two = c + 1 < n_chunks;
-          ptx::tmem_ld_32x32(taddr + c * 32, ra);
-          if (two) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
-          ptx::tmem_ld_wait();
-          if ((c + 1) * 32 <= F) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(ra[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < F) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(ra[i]));
-          }
-          if (two) {
-            if ((c + 2) * 32 <= F) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rb[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if ((c + 1) * 32 + i < F) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rb[i]));
-            }
-          }
-        }
-        const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
-
-        // ---- pass 2: P = exp2(S * c - max * c) as packed fp16 into the same TMEM columns, row sum in fp32
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
-          uint32_t pk[16];
-          if ((c + 1) * 32 <= F) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float e0 = ex2_approx(fmaf(__uint_as_float(rr[2 * i]), kScaleLog2e, nmxs));
-              const float e1 = ex2_approx(fmaf(__uint_as_float(rr[2 * i + 1]), kScaleLog2e, nmxs));
-              ls[i & 3] += e0 + e1;
-              pk[i] = pack_f16x2(e0, e1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int col = c * 32 + 2 * i;
-              const float e0 = col < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * i]), kScaleLog2e, nmxs)) : 0.f;
-              const float e1 = col + 1 < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * i + 1]), kScaleLog2e, nmxs)) : 0.f;
-              ls[i & 3] += e0 + e1;
-              pk[i] = pack_f16x2(e0, e1);
-            }
-          }
-          ptx::tmem_st_32x16(taddr + c * 16, pk);
-        };
-        for (int c = 0; c < n_chunks; c += 2) {
-          uint32_t ra[32], rb[32];
-          const bool two = c + 1 < n_chunks;
-          ptx::tmem_ld_32x32(taddr + c * 32, ra);
-          if (two) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
-          ptx::tmem_ld_wait();
-          exp_chunk(ra, c);
-          if (two) exp_chunk(rb, c + 1);
-        }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars->p_full);
-        const float inv = rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
-
-        // ---- O row out of TMEM, then the columns are free for the next S
-        ptx::mbar_wait(&bars->o_full, it & 1);
-        ptx::tc_fence_after();
-        uint32_t o0[32], o1[32];
-        ptx::tmem_ld_32x32(taddr + kOCol, o0);
-        ptx::tmem_ld_32x32(taddr + kOCol + 32, o1);
+      // ---- pass 1: row maximum over the F real keys
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      for (int c = 0; c < n_chunks; c += 2) {
+        uint32_t ra[32], rb[32];
+        const bool two = c + 1 < n_chunks;
+        ptx::tmem_ld_32x32(taddr + c * 32, ra);
+        if (two) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars->tmem_free);
-
-        // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
-        if (threadIdx.x == 0) ptx::bulk_wait_read_all();      // the previous tile's stores are done reading smem
-        ptx::bar_sync(1, 128);
-        uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // Q_m is dead (S complete): hi staging, swizzled
-        const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
+        if ((c + 1) * 32 <= F) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint4 vh = *reinterpret_cast<const uint4*>(v_row + ((g << 4) ^ sw));
-          const uint32_t vhw[4] = {vh.x, vh.y, vh.z, vh.w};
-          const uint32_t vlw[4] = {vl[g].x, vl[g].y, vl[g].z, vl[g].w};
-          float x[8];
+          for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(ra[e]));
+        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __half2 a = *reinterpret_cast<const __half2*>(&vhw[e]);
-            const __half2 c = *reinterpret_cast<const __half2*>(&vlw[e]);
-            const float oa = __uint_as_float(g < 4 ? o0[8 * g + 2 * e] : o1[8 * (g & 3) + 2 * e]);
-            const float ob = __uint_as_float(g < 4 ? o0[8 * g + 2 * e + 1] : o1[8 * (g & 3) + 2 * e + 1]);
-            x[2 * e] = fmaf(oa, inv, -(__low2float(a) + __low2float(c)));
-            x[2 * e + 1] = fmaf(ob, inv, -(__high2float(a) + __high2float(c)));
-          }
-          uint32_t hw[4], lw[4];
-          float lo[8];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __half h0 = __float2half_rn(x[2 * e]), h1 = __float2half_rn(x[2 * e + 1]);
-            hw[e] = op_pack_h2(h0, h1);
-            lo[2 * e] = x[2 * e] - __half2float(h0);
-            lo[2 * e + 1] = x[2 * e + 1] - __half2float(h1);
-            if (FMT == FMT_SPLIT16) lw[e] = op_pack_h2(__float2half_rn(lo[2 * e]), __float2half_rn(lo[2 * e + 1]));
-          }
-          *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          if (FMT == FMT_SPLIT16) {            // lo rows: 128 B, swizzled like hi
-            *reinterpret_cast<uint4*>(Stg + row_l * 128 + ((g << 4) ^ sw)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          } else {                             // c8: [128 rows][64 B] e5m2(x 2^-8), then [128 rows][64 B] e5m2(lo 2^4)
-            *reinterpret_cast<uint2*>(Stg + row_l * 64 + g * 8) =
-                make_uint2(op_e5m2x4(x[0] * kActHiScale, x[1] * kActHiScale, x[2] * kActHiScale, x[3] * kActHiScale),
-                           op_e5m2x4(x[4] * kActHiScale, x[5] * kActHiScale, x[6] * kActHiScale, x[7] * kActHiScale));
-            *reinterpret_cast<uint2*>(Stg + 8192 + row_l * 64 + g * 8) =
-                make_uint2(op_e5m2x4(lo[0] * kActLoScale, lo[1] * kActLoScale, lo[2] * kActLoScale, lo[3] * kActLoScale),
-                           op_e5m2x4(lo[4] * kActLoScale, lo[5] * kActLoScale, lo[6] * kActLoScale, lo[7] * kActLoScale));
-          }
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e < F) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(ra[e]));
         }
-        ptx::fence_proxy_async();
-        ptx::bar_sync(1, 128);
-        if (threadIdx.x == 0) {
-          ptx::tma_store_4d(&tm_hi, Qs + m * kTile, h * kHd, j, m * 128, b);
-          if (FMT == FMT_SPLIT16) {
-            ptx::tma_store_4d(&tm_second, Stg, h * kHd, j, m * 128, b);
+        if (two) {
+          if ((c + 2) * 32 <= F) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rb[e]));
           } else {
-            ptx::tma_store_4d(&tm_second, Stg, h * kHd, j, m * 128, b);
-            ptx::tma_store_4d(&tm_second, Stg + 8192, kC + h * kHd, j, m * 128, b);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if ((c + 1) * 32 + e < F) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rb[e]));
           }
-          ptx::bulk_commit();
         }
       }
-      if (threadIdx.x == 0) {          // V (v_hi rows) and the staging tiles of this unit are no longer read
-        ptx::bulk_wait_read_all();
-        ptx::mbar_arrive(&bars->unit_done);
+      const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
+
+      // ---- pass 2: P = exp2(S * c - max * c) as packed fp16 into the same TMEM columns, row sum in fp32
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
+        uint32_t pk[16];
+        if ((c + 1) * 32 <= F) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs));
+            ls[e & 3] += e0 + e1;
+            pk[e] = pack_f16x2(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int col = c * 32 + 2 * e;
+            const float e0 = col < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs)) : 0.f;
+            const float e1 = col + 1 < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs)) : 0.f;
+            ls[e & 3] += e0 + e1;
+            pk[e] = pack_f16x2(e0, e1);
+          }
+        }
+        ptx::tmem_st_32x16(taddr + c * 16, pk);
+      };
+      for (int c = 0; c < n_chunks; c += 2) {
+        uint32_t ra[32], rb[32];
+        const bool two = c + 1 < n_chunks;
+        ptx::tmem_ld_32x32(taddr + c * 32, ra);
+        if (two) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+        ptx::tmem_ld_wait();
+        exp_chunk(ra, c);
+        if (two) exp_chunk(rb, c + 1);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars->p_full[slot]);
+      const float inv = rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
+      // v_lo row of this query (exact "- V" term): in flight while the tensor core computes P V
+      uint4 vl[8];
+      {
+        const __half* p = qkv + (static_cast<size_t>(b) * F + (valid ? r : 0)) * J * kQkvRow +
+                          static_cast<size_t>(j) * kQkvRow + 3 * kC + h * kHd;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) vl[g] = valid ? ld_nc_v4(p + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+
+      // ---- O row out of TMEM, then the columns are free for the next S
+      ptx::mbar_wait(&bars->o_full[slot], i & 1);
+      ptx::tc_fence_after();
+      uint32_t o0[32], o1[32];
+      ptx::tmem_ld_32x32(taddr + kOCol, o0);
+      ptx::tmem_ld_32x32(taddr + kOCol + 32, o1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars->tmem_free[slot]);
+
+      // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
+      ptx::bar_sync(1 + slot, 128);          // the issuer is past the read-wait of the previous tile's stores: Stg is free
+      uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // Q_m is dead (S complete): hi staging, swizzled
+      const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 vh = *reinterpret_cast<const uint4*>(v_row + ((g << 4) ^ sw));
+        const uint32_t vhw[4] = {vh.x, vh.y, vh.z, vh.w};
+        const uint32_t vlw[4] = {vl[g].x, vl[g].y, vl[g].z, vl[g].w};
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 a = *reinterpret_cast<const __half2*>(&vhw[e]);
+          const __half2 c = *reinterpret_cast<const __half2*>(&vlw[e]);
+          const float oa = __uint_as_float(g < 4 ? o0[8 * g + 2 * e] : o1[8 * (g & 3) + 2 * e]);
+          const float ob = __uint_as_float(g < 4 ? o0[8 * g + 2 * e + 1] : o1[8 * (g & 3) + 2 * e + 1]);
+          x[2 * e] = fmaf(oa, inv, -(__low2float(a) + __low2float(c)));
+          x[2 * e + 1] = fmaf(ob, inv, -(__high2float(a) + __high2float(c)));
+        }
+        uint32_t hw[4], lw[4];
+        float lo[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half h0 = __float2half_rn(x[2 * e]), h1 = __float2half_rn(x[2 * e + 1]);
+          hw[e] = op_pack_h2(h0, h1);
+          lo[2 * e] = x[2 * e] - __half2float(h0);
+          lo[2 * e + 1] = x[2 * e + 1] - __half2float(h1);
+          if (FMT == FMT_SPLIT16) lw[e] = op_pack_h2(__float2half_rn(lo[2 * e]), __float2half_rn(lo[2 * e + 1]));
+        }
+        *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (FMT == FMT_SPLIT16) {            // lo rows: 128 B, swizzled like hi
+          *reinterpret_cast<uint4*>(Stg + row_l * 128 + ((g << 4) ^ sw)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        } else {                             // c8: [128 rows][64 B] e5m2(x 2^-8), then [128 rows][64 B] e5m2(lo 2^4)
+          *reinterpret_cast<uint2*>(Stg + row_l * 64 + g * 8) =
+              make_uint2(op_e5m2x4(x[0] * kActHiScale, x[1] * kActHiScale, x[2] * kActHiScale, x[3] * kActHiScale),
+                         op_e5m2x4(x[4] * kActHiScale, x[5] * kActHiScale, x[6] * kActHiScale, x[7] * kActHiScale));
+          *reinterpret_cast<uint2*>(Stg + 8192 + row_l * 64 + g * 8) =
+              make_uint2(op_e5m2x4(lo[0] * kActLoScale, lo[1] * kActLoScale, lo[2] * kActLoScale, lo[3] * kActLoScale),
+                         op_e5m2x4(lo[4] * kActLoScale, lo[5] * kActLoScale, lo[6] * kActLoScale, lo[7] * kActLoScale));
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::bar_sync(1 + slot, 128);          // every row is staged, and nobody still reads v_hi rows of this tile
+      if (issuer) {
+        ptx::tma_store_4d(&tm_hi, Qs + m * kTile, h * kHd, j, m * 128, b);
+        ptx::tma_store_4d(&tm_second, Stg, h * kHd, j, m * 128, b);
+        if (FMT != FMT_SPLIT16) ptx::tma_store_4d(&tm_second, Stg + 8192, kC + h * kHd, j, m * 128, b);
+        ptx::bulk_commit();
+        ptx::bulk_wait_read_all();           // Stg / Q_m have been read: the tile has left shared memory
+        ptx::mbar_arrive(&bars->stage_free[stage]);
       }
     }
-    if (threadIdx.x == 0) ptx::bulk_wait_all();
+    if (issuer) ptx::bulk_wait_all();
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+    ptx::tmem_dealloc<kSlotCols * NSLOT>(tmem_base);
   }
 }
 
@@ -355,7 +382,10 @@ int encode_tokens_4d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int e
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
-int tc_smem_bytes(int n_mt) { return (3 * n_mt + 1) * kTile + static_cast<int>(sizeof(TcBars)); }
+template <int NSLOT>
+int tc_smem_bytes(int n_mt) {
+  return NSLOT * (3 * n_mt + 1) * kTile + static_cast<int>(sizeof(TcBars<NSLOT>)) + (NSLOT == 1 ? 0 : 1024);
+}
 
 }  // namespace
 
@@ -376,23 +406,31 @@ int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half*
 
 cudaError_t configure_attention_tc() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_SPLIT16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                tc_smem_bytes(2))) != cudaSuccess)
+#define D3D_CFG_TC(FMT_, NSLOT_)                                                                                       \
+  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_, NSLOT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                tc_smem_bytes<NSLOT_>(2))) != cudaSuccess)                                           \
     return e;
-  return cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_F8C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              tc_smem_bytes(2));
+  D3D_CFG_TC(FMT_SPLIT16, 1) D3D_CFG_TC(FMT_F8C, 1) D3D_CFG_TC(FMT_SPLIT16, 2) D3D_CFG_TC(FMT_F8C, 2)
+#undef D3D_CFG_TC
+  return cudaSuccess;
 }
 
-cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
-                                    cudaStream_t st) {
+cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int slots,
+                                    int num_sms, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   if (F <= 64 || F > 256) return cudaErrorInvalidValue;
   const int n_mt = (F + 127) / 128;
   const int NKp = (F + 15) / 16 * 16;
   const int n_units = B * J * kHeads;
-  const int grid = n_units < 2 * num_sms ? n_units : 2 * num_sms;
-  auto kern = fmt == FMT_F8C ? attn_temporal_tc_kernel<FMT_F8C> : attn_temporal_tc_kernel<FMT_SPLIT16>;
-  kern<<<grid, kTcThreads, tc_smem_bytes(n_mt), st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, n_units, n_mt, NKp);
+  if (slots == 1) {
+    const int grid = n_units < 2 * num_sms ? n_units : 2 * num_sms;
+    auto kern = fmt == FMT_F8C ? attn_temporal_tc_kernel<FMT_F8C, 1> : attn_temporal_tc_kernel<FMT_SPLIT16, 1>;
+    kern<<<grid, 192, tc_smem_bytes<1>(n_mt), st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, n_units, n_mt, NKp);
+  } else {
+    const int grid = n_units < num_sms ? n_units : num_sms;
+    auto kern = fmt == FMT_F8C ? attn_temporal_tc_kernel<FMT_F8C, 2> : attn_temporal_tc_kernel<FMT_SPLIT16, 2>;
+    kern<<<grid, 320, tc_smem_bytes<2>(n_mt), st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, n_units, n_mt, NKp);
+  }
   return cudaGetLastError();
 }
 

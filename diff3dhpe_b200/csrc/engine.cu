@@ -243,7 +243,8 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
     m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
     m.b_hi64 = w.m_hi64; m.b_lo64 = w.m_lo64;
     const int passes = mode == D3D_GEMM_TC_FP16 ? 1 : (mode == D3D_GEMM_TC_F8C ? 2 : 3);
-    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), pick_cs(M), h->num_sms, st));
+    const int ew = env_int(epi == EPI_GELU_SPLIT ? "D3D_GEMM_EW_GELU" : "D3D_GEMM_EW_QKV", epi == EPI_GELU_SPLIT ? 16 : 8);
+    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), pick_cs(M), ew, h->num_sms, st));
   }
   return 0;
 }
@@ -262,7 +263,8 @@ int run_attention(d3d_handle* h, const __half* qkv, __half* o_hi, __half* o_lo, 
       // the tcgen05 kernel's tensor maps are bound to QKV -> ATT; an fp32 result (op-level entry point) is merged
       // from the operand pair afterwards
       if (!o_f32 && (o_hi != h->ATT.hi || o_lo != h->ATT.lo)) return fail(h, -2, "attention output must be the ATT operand");
-      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_tc(h->attn_tc, qkv, h->fmt, B, h->F, h->J, h->num_sms, st));
+      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_tc(h->attn_tc, qkv, h->fmt, B, h->F, h->J, env_int("D3D_ATTN_TC_SLOTS", 2) == 1 ? 1 : 2,
+                                                             h->num_sms, st));
       if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, o_f32, static_cast<int64_t>(B) * h->F * h->J, kC, h->fmt, st));
     } else {
       KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));

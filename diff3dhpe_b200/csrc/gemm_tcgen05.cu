@@ -36,22 +36,32 @@ namespace {
 
 constexpr int BM = 128;                      // rows per CTA
 constexpr int BK = 64;                       // 64 fp16 = 128 B = one swizzle row
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
+constexpr int kProducerRegs = 40;          // setmaxnreg targets of the EW = 16 kernels (640 threads launch with 96 each)
+constexpr int kEpilogueRegs = 104;
+// setmaxnreg.inc draws from the registers the SAME CTA released with setmaxnreg.dec (not from the SM's unallocated
+// remainder): the four epilogue warpgroups may not ask for more than the producer warpgroup gave back, or they block
+// forever (first attempt: 40 / 112 -> deadlock on the GPU)
+static_assert(4 * 128 * (kEpilogueRegs - 96) <= 128 * (96 - kProducerRegs), "setmaxnreg pool overdrawn");
 constexpr int kTileBytesA = BM * BK * 2;     // 16 KiB
 constexpr int kSmemBudget = 200 * 1024;
 
-template <int CG, int BN, int PASSES>
+// EW = epilogue warps per CTA: 8 (two warps per TMEM lane quadrant, 128 columns each) or 16 (four per quadrant, 64
+// columns each).  The bias+GELU+split epilogue of fc1 costs ~25 instructions per output element; with 8 warps it, not
+// the MMA or L2, bounded that GEMM (11.9 us per 256 x 256 tile against 8.6 us for the qkv GEMM at the same K).
+template <int CG, int BN, int PASSES, int EW = 8>
 struct Cfg {
   static constexpr int kBRows = BN / CG;                  // weight rows staged by one CTA
   static constexpr int kTileBytesB = kBRows * BK * 2;
+  static constexpr int kThreads = 128 + 32 * EW;
   static constexpr int kStageBytes = (PASSES == 3 ? 2 : 1) * (kTileBytesA + kTileBytesB);
-  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kStagingBytes = EW * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
+  static constexpr int kRing = kSmemBudget + 8 * 4096 - kStagingBytes;
+  static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;   // 256 or 512 (power of two)
-  static constexpr int kStagingBytes = kEpiWarps * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256 x 256 tiles");
+  static_assert(EW == 8 || (EW == 16 && BN == 256), "16 epilogue warps split a 256-column tile four ways");
 };
 
 struct Barriers {
@@ -93,12 +103,12 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 // tiles (same weight rows).  Each CTA loads only HALF of its 128-row weight tile and TMA-multicasts it to the CTA
 // with the same position in the other pair, so the L2 -> SM weight traffic per MAC halves (48 KB instead of 64 KB
 // per k-block and SM): the F8C GEMM runs at the ~6300 B/clk L2 output cap (profiles/r01e_full_gemm_tc.md).
-template <int CG, int BN, int PASSES, int EPI, int CS>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CG, int BN, int PASSES, int EPI, int CS, int EW = 8>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const GemmParams p) {
-  using C = Cfg<CG, BN, PASSES>;
+  using C = Cfg<CG, BN, PASSES, EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + C::kStages * C::kStageBytes;
@@ -135,7 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bars->tmem_full[a], 1);
-      ptx::mbar_init(&bars->tmem_empty[a], kEpiWarps * CG);     // leader's copy collects both CTAs' warps
+      ptx::mbar_init(&bars->tmem_empty[a], EW * CG);            // leader's copy collects both CTAs' warps
     }
     ptx::fence_barrier_init();
   }
@@ -147,9 +157,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // EW == 16: 640 threads launch with 96 registers each; the producer warpgroup (warps 0..3) hands its surplus to the
+  // epilogue warpgroups.  The setmaxnreg sits INSIDE each role branch: ptxas allocates per branch only then.
+#define D3D_PRODUCER_REGS() \
+  do { if (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs)); } while (0)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs of a pair)
+    D3D_PRODUCER_REGS();
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -224,6 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    D3D_PRODUCER_REGS();
     if (rank == 0 && ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(TM, BN, 0 /*fp16*/);
       int stage = 0;
@@ -294,15 +310,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (8 warps per CTA)
+  } else if (warp < 4) {
+    D3D_PRODUCER_REGS();
+  } else {
+    // ------------------------------------------------------------ epilogue (EW warps per CTA)
+    if (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpilogueRegs));
     // TMEM hands every lane one ROW (32 consecutive columns); storing that layout directly costs 32 cache lines
     // per store instruction and made the epilogue, not the MMA, the bottleneck (1-pass and 3-pass GEMMs took
     // the same time).  Each warp therefore transposes its 32 x 32 chunk through a swizzled 4 KB buffer and
     // moves global data with "8 lanes = 128 contiguous bytes of one row" accesses (4 rows per instruction).
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = (warp - 4) >> 2;       // which half of the BN columns
-    constexpr int kChunks = BN / 64;        // 32-column chunks per warp
+    const int half = (warp - 4) >> 2;       // which slice of the BN columns (BN / kColsW columns each)
+    constexpr int kColsW = BN / (EW / 4);   // columns per warp
+    constexpr int kChunks = kColsW / 32;    // 32-column chunks per warp
     uint8_t* stg = staging + (warp - 4) * 4096;
     const int rsub = lane >> 3, gsub = lane & 7;      // coalesced mapping: instruction j covers rows 4j + rsub
     int acc = 0;
@@ -311,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
       const int n0 = (tile % n_tiles_n) * BN;
       const int row_w = m0 + q * 32;                    // first row of this warp
-      const int colbase = n0 + half * (BN / 2);
+      const int colbase = n0 + half * kColsW;
       const bool has_res = EPI == EPI_F32 && p.residual != nullptr;
       float4 resv[8];
       auto load_res = [&](int ci) {                     // residual chunk ci, coalesced (row 4j + rsub, granule gsub)
@@ -328,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::tc_fence_after();
 #pragma unroll
       for (int ci = 0; ci < kChunks; ++ci) {
-        const int col0 = half * (BN / 2) + ci * 32;     // column inside the tile
+        const int col0 = half * kColsW + ci * 32;       // column inside the tile
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + acc * BN + col0 + (static_cast<uint32_t>(q * 32) << 16), r);
         if (has_res) {
@@ -460,6 +480,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+#undef D3D_PRODUCER_REGS
   __syncwarp();
 
   ptx::tc_fence_before();
@@ -472,7 +493,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 }
 
 // Clusters of 4 cannot straddle a GPC, so fewer than 148/4 of them may be co-resident: ask the runtime (once).
-template <int CG, int BN, int PASSES, int EPI, int CS>
+template <int CG, int BN, int PASSES, int EPI, int CS, int EW = 8>
 int max_clusters(int num_sms) {
   static int cached = -1;
   if (cached >= 0) return cached;
@@ -480,8 +501,8 @@ int max_clusters(int num_sms) {
   if (CG * CS > 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(num_sms / (CG * CS) * (CG * CS)));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<CG, BN, PASSES>::kSmemBytes;
+    cfg.blockDim = dim3(Cfg<CG, BN, PASSES, EW>::kThreads);
+    cfg.dynamicSmemBytes = Cfg<CG, BN, PASSES, EW>::kSmemBytes;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG * CS;
@@ -490,7 +511,7 @@ int max_clusters(int num_sms) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int q = 0;
-    if (cudaOccupancyMaxActiveClusters(&q, gemm_tc_kernel<CG, BN, PASSES, EPI, CS>, &cfg) == cudaSuccess && q > 0 && q < n)
+    if (cudaOccupancyMaxActiveClusters(&q, gemm_tc_kernel<CG, BN, PASSES, EPI, CS, EW>, &cfg) == cudaSuccess && q > 0 && q < n)
       n = q;
     (void)cudaGetLastError();
   }
@@ -498,17 +519,17 @@ int max_clusters(int num_sms) {
   return n;
 }
 
-template <int CG, int BN, int PASSES, int EPI, int CS = 1>
+template <int CG, int BN, int PASSES, int EPI, int CS = 1, int EW = 8>
 cudaError_t launch_one(const GemmMaps& m, const GemmParams& p, int num_sms, cudaStream_t st) {
-  using C = Cfg<CG, BN, PASSES>;
-  auto kern = gemm_tc_kernel<CG, BN, PASSES, EPI, CS>;
+  using C = Cfg<CG, BN, PASSES, EW>;
+  auto kern = gemm_tc_kernel<CG, BN, PASSES, EPI, CS, EW>;
   const int tiles_m = (p.M + BM * CG - 1) / (BM * CG);
   const int n_tiles = ((tiles_m + CS - 1) / CS) * (p.N / BN);
-  const int max_units = max_clusters<CG, BN, PASSES, EPI, CS>(num_sms);
+  const int max_units = max_clusters<CG, BN, PASSES, EPI, CS, EW>(num_sms);
   const int units = n_tiles < max_units ? n_tiles : max_units;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(units * CG * CS));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -521,10 +542,10 @@ cudaError_t launch_one(const GemmMaps& m, const GemmParams& p, int num_sms, cuda
   return cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, CS == 2 ? m.b_hi64 : m.b_hi, CS == 2 ? m.b_lo64 : m.b_lo, p);
 }
 
-template <int CG, int BN, int PASSES, int EPI, int CS = 1>
+template <int CG, int BN, int PASSES, int EPI, int CS = 1, int EW = 8>
 cudaError_t configure_one() {
-  return cudaFuncSetAttribute(gemm_tc_kernel<CG, BN, PASSES, EPI, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              Cfg<CG, BN, PASSES>::kSmemBytes);
+  return cudaFuncSetAttribute(gemm_tc_kernel<CG, BN, PASSES, EPI, CS, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Cfg<CG, BN, PASSES, EW>::kSmemBytes);
 }
 
 }  // namespace
@@ -549,13 +570,19 @@ cudaError_t configure_gemm_tc() {
   if ((e = configure_one<2, 256, 2, EPI_F32, 2>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 2, EPI_GELU_SPLIT, 2>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 2, EPI_QKV16, 2>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 2, EPI_GELU_SPLIT, 1, 16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 2, EPI_QKV16, 1, 16>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
-                           int pair_cluster, int num_sms, cudaStream_t st) {
+                           int pair_cluster, int epi_warps, int num_sms, cudaStream_t st) {
   if (p.M <= 0) return cudaSuccess;
   if (cta_group == 2 || passes == 2) bn = 256;
+  if (epi_warps == 16 && cta_group == 2 && passes == 2 && pair_cluster != 2) {
+    if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 2, EPI_GELU_SPLIT, 1, 16>(maps, p, num_sms, st);
+    if (epi == EPI_QKV16) return launch_one<2, 256, 2, EPI_QKV16, 1, 16>(maps, p, num_sms, st);
+  }
   if (p.K % BK != 0 || p.N % bn != 0 || (bn != 128 && bn != 256)) return cudaErrorInvalidValue;
   if (epi == EPI_QKV16 && p.N != 3 * kC) return cudaErrorInvalidValue;
   if (pair_cluster == 2 && cta_group == 2 && passes == 2) {

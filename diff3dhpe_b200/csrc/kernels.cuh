@@ -45,8 +45,9 @@ struct GemmMaps {
 // cta_group 1: one CTA per 128 x bn tile (bn 128 or 256, N % bn == 0);
 // cta_group 2: a CTA pair per 256 x 256 tile (tcgen05.mma.cta_group::2, N % 256 == 0, bn ignored).
 // pair_cluster 2 (F8C + cta_group 2 only): clusters of two CTA pairs sharing the weight tile through TMA multicast.
+// epi_warps 16 (F8C CTA-pair kernel, GELU / QKV epilogues): 16 epilogue warps per CTA instead of 8.
 cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
-                           int pair_cluster, int num_sms, cudaStream_t st);
+                           int pair_cluster, int epi_warps, int num_sms, cudaStream_t st);
 cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
                              const GemmParams& p, int epi, int fmt, cudaStream_t st);
 // One-time per-device kernel attribute setup (dynamic shared memory opt-in); call outside graph capture.
@@ -116,8 +117,10 @@ struct AttnTcMaps {
 int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int F, int J,
                       int64_t max_clips);
 cudaError_t configure_attention_tc();
-cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
-                                    cudaStream_t st);
+// slots: 2 = one CTA per SM with two 128-query tiles in flight and double-buffered units (default), 1 = two
+// single-slot CTAs per SM.
+cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int slots,
+                                    int num_sms, cudaStream_t st);
 // CUDA-core validation kernels (fp32 arithmetic on the same packed input)
 cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                       int J, cudaStream_t st);
