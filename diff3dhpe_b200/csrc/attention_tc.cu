@@ -17,11 +17,12 @@
 //     operand (V rows are keys, the contraction index), accumulating into the (dead) upper half of S;
 //   * the epilogue normalises, subtracts the exact V row (v_hi from shared memory + v_lo from global), packs the
 //     GEMM A-operand format and leaves through TMA stores (rows >= F are clipped by the hardware).
-// Two CTAs per SM (256 TMEM columns, <= 113 KB shared memory each) overlap one CTA's loads / MMAs with the other's
-// softmax.  The remaining bound is the MUFU unit (F^2 exp2 per unit) next to the HBM floor.
+// One CTA per SM keeps two 128-query tiles ("slots", 256 TMEM columns each) and two units (shared-memory stages) in
+// flight: while one slot runs its softmax on the CUDA cores the other is in its tensor-core phase, and the next
+// unit's Q/K/V are already landing.  Measured history and ncu evidence: DESIGN.md section 4.2.
 //
-// Warp roles (192 threads): 0..3 softmax + epilogue (TMEM lane quadrant = warp), 4 = TMA producer, 5 = MMA issuer
-// and TMEM allocator.
+// Warp roles (320 threads): 0..3 softmax + epilogue of slot 0 (TMEM lane quadrant = warp & 3), 4..7 of slot 1,
+// 8 = TMA producer, 9 = MMA issuer and TMEM allocator.
 #include "kernels.cuh"
 #include "operand.cuh"
 #include "ptx.cuh"
@@ -35,10 +36,8 @@ constexpr int kOCol = 128;
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;   // head_dim ** -0.5 (MODEL:65) in the exp2 domain
 
 // NSLOT = 128-query tiles in flight per CTA (each with its own 4 softmax warps and 256 TMEM columns) = shared-memory
-// stages (units resident per CTA):
-//   NSLOT 2 (default): one CTA per SM, 320 threads.  While slot 0 runs its softmax on the CUDA cores, slot 1 is in
-//            its tensor-core phase (and vice versa), and the NEXT unit's Q/K/V are already landing in the other stage.
-//   NSLOT 1: two CTAs per SM, 192 threads, one stage: the first version (kept for A/B measurements).
+// stages (units resident per CTA).  Shipped: 2.  (A first version with one slot and two CTAs per SM measured 430 ms
+// per cfg3 step against 398 ms, profiles/r01m_bench_slots*.json.)
 template <int NSLOT>
 struct TcBars {
   uint64_t full[NSLOT];         // TMA bytes of the unit in this stage landed              (producer -> MMA)
@@ -47,6 +46,7 @@ struct TcBars {
   uint64_t p_full[NSLOT];       // P written to TMEM by all 128 rows                        (softmax -> MMA)
   uint64_t o_full[NSLOT];       // O = P V complete                                         (MMA -> epilogue)
   uint64_t tmem_free[NSLOT];    // O read out: the columns may receive the next S           (epilogue -> MMA)
+  uint64_t vlo_full[NSLOT];     // v_lo rows of the tile landed in the (dead) Q tile        (TMA -> epilogue)
   uint32_t tmem_base;
 };
 
@@ -65,12 +65,6 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {      // one
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-
 // MN-major SWIZZLE_128B operand (V as B of P.V: rows = keys = contraction index, 64 head channels contiguous):
 // canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> 8 keys x 128 B per swizzle atom, next 8 keys
 // SBO = 1024 B further; one atom wide in N (64 halves), so LBO is unused.
@@ -85,24 +79,111 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 
+// One query row (= this thread's TMEM lane) of S -> P, two passes over tensor memory:
+//   pass 1: m = max over the F real keys;   pass 2: P = exp2(S c - m c) as packed fp16 into columns [0, n/2) of the
+//   same slot (column k/2 is written after S columns <= k+1 were read), row sum in fp32.  Returns 1 / sum.
+// TMEM reads are issued one batch (two 32-column chunks) ahead of the batch being processed.  NCH > 0: the number of
+// chunks is a compile-time constant and F > 32 (NCH - 1), so every offset is an immediate and only the last chunk is
+// masked; NCH == 0: runtime chunk count (<= 8).
+template <int NCH>
+__device__ __forceinline__ float softmax_row(uint32_t taddr, int F, int n_chunks_rt) {
+  constexpr int kMax = NCH > 0 ? NCH : 8;
+  const int n = NCH > 0 ? NCH : n_chunks_rt;
+  uint32_t a0[32], a1[32], b0[32], b1[32];
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  auto full = [&](int c) { return (NCH > 0 && c < NCH - 1) || (c + 1) * 32 <= F; };
+  auto max_chunk = [&](const uint32_t (&rr)[32], int c) {
+    if (full(c)) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rr[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (c * 32 + e < F) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rr[e]));
+    }
+  };
+  ptx::tmem_ld_32x32(taddr, a0);
+  if (1 < n) ptx::tmem_ld_32x32(taddr + 32, a1);
+#pragma unroll
+  for (int c = 0; c < kMax; c += 4) {
+    if (c < n) {
+      ptx::tmem_ld_wait();
+      if (c + 2 < n) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, b0);
+      if (c + 3 < n) ptx::tmem_ld_32x32(taddr + (c + 3) * 32, b1);
+      max_chunk(a0, c);
+      if (c + 1 < n) max_chunk(a1, c + 1);
+    }
+    if (c + 2 < n) {
+      ptx::tmem_ld_wait();
+      if (c + 4 < n) ptx::tmem_ld_32x32(taddr + (c + 4) * 32, a0);
+      if (c + 5 < n) ptx::tmem_ld_32x32(taddr + (c + 5) * 32, a1);
+      max_chunk(b0, c + 2);
+      if (c + 3 < n) max_chunk(b1, c + 3);
+    }
+  }
+  // pass 2 starts streaming before the max is reduced
+  ptx::tmem_ld_32x32(taddr, a0);
+  if (1 < n) ptx::tmem_ld_32x32(taddr + 32, a1);
+  const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
+  float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
+    uint32_t pk[16];
+    if (full(c)) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs));
+        ls[e & 3] += e0 + e1;
+        pk[e] = pack_f16x2(e0, e1);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int col = c * 32 + 2 * e;
+        const float e0 = col < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs)) : 0.f;
+        const float e1 = col + 1 < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs)) : 0.f;
+        ls[e & 3] += e0 + e1;
+        pk[e] = pack_f16x2(e0, e1);
+      }
+    }
+    ptx::tmem_st_32x16(taddr + c * 16, pk);
+  };
+#pragma unroll
+  for (int c = 0; c < kMax; c += 4) {
+    if (c < n) {
+      ptx::tmem_ld_wait();
+      if (c + 2 < n) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, b0);
+      if (c + 3 < n) ptx::tmem_ld_32x32(taddr + (c + 3) * 32, b1);
+      exp_chunk(a0, c);
+      if (c + 1 < n) exp_chunk(a1, c + 1);
+    }
+    if (c + 2 < n) {
+      ptx::tmem_ld_wait();
+      if (c + 4 < n) ptx::tmem_ld_32x32(taddr + (c + 4) * 32, a0);
+      if (c + 5 < n) ptx::tmem_ld_32x32(taddr + (c + 5) * 32, a1);
+      exp_chunk(b0, c + 2);
+      if (c + 3 < n) exp_chunk(b1, c + 3);
+    }
+  }
+  ptx::tmem_st_wait();
+  return rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
+}
+
 // Work items of a CTA, in order: w = 0, 1, 2, ... ; unit n = w / n_mt (the CTA's n-th unit), 128-query tile
 // m = w % n_mt; slot = w % NSLOT (i-th item of that slot, i = w / NSLOT); stage = n % NSLOT (k-th use, k = n / NSLOT).
-template <int FMT, int NSLOT>
-__global__ void __launch_bounds__(128 * NSLOT + 64, NSLOT == 1 ? 2 : 1)
+template <int FMT, int NSLOT, int NCH>
+__global__ void __maxnreg__(200)      // 320 threads x 200 registers = 64 000 (launch bounds would round down to 168 and spill)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
                         const __grid_constant__ CUtensorMap tm_second, const __half* __restrict__ qkv, int F, int J,
                         int n_units, int n_mt, int NKp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // two CTAs per SM (NSLOT 1) leave no room for alignment slack: the base is checked instead
-  uint8_t* smem = NSLOT == 1 ? smem_raw
-                             : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = 3 * n_mt * kTile;          // Q tiles | K tiles | V tiles of one unit
   uint8_t* StgAll = smem + NSLOT * stage_bytes;      // 16 KB per slot: second-part staging of one 128-row output tile
   TcBars<NSLOT>* bars = reinterpret_cast<TcBars<NSLOT>*>(StgAll + NSLOT * kTile);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kTmaWarp = 4 * NSLOT, kMmaWarp = 4 * NSLOT + 1;
-  if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();     // swizzle atoms need 1 KB alignment
   const int n_local = blockIdx.x < n_units ? (n_units - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
   const int W = n_local * n_mt;
 
@@ -118,6 +199,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       ptx::mbar_init(&bars->p_full[s], 128);
       ptx::mbar_init(&bars->o_full[s], 1);
       ptx::mbar_init(&bars->tmem_free[s], 128);
+      ptx::mbar_init(&bars->vlo_full[s], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -192,6 +274,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const int row_l = (warp & 3) * 32 + lane;                             // row inside the 128-query tile
     const uint32_t taddr = tmem_base + slot * kSlotCols + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int n_chunks = (NKp + 31) >> 5;
+    if (NCH > 0 && (n_chunks != NCH || F <= 32 * (NCH - 1))) __trap();    // launcher / instantiation mismatch
     const int sw = (row_l & 7) << 4;                                      // swizzle XOR of this row (bytes)
     const bool issuer = row_l == 0;                                       // issues the slot's TMA stores
     uint8_t* Stg = StgAll + slot * kTile;
@@ -204,84 +287,15 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       uint8_t* Qs = smem + stage * stage_bytes;
       const uint8_t* Vs = Qs + 2 * n_mt * kTile;
       const int r = m * 128 + row_l;
-      const bool valid = r < F;
       ptx::mbar_wait(&bars->s_full[slot], i & 1);
       ptx::tc_fence_after();
-
-      // ---- pass 1: row maximum over the F real keys
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      for (int c = 0; c < n_chunks; c += 2) {
-        uint32_t ra[32], rb[32];
-        const bool two = c + 1 < n_chunks;
-        ptx::tmem_ld_32x32(taddr + c * 32, ra);
-        if (two) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
-        ptx::tmem_ld_wait();
-        if ((c + 1) * 32 <= F) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(ra[e]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (c * 32 + e < F) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(ra[e]));
-        }
-        if (two) {
-          if ((c + 2) * 32 <= F) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rb[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if ((c + 1) * 32 + e < F) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rb[e]));
-          }
-        }
+      if (issuer) {      // Q_m is dead once S is complete: it receives the v_lo rows of the tile (exact "- V" term)
+        ptx::mbar_arrive_expect_tx(&bars->vlo_full[slot], kTile);
+        ptx::tma_load_4d(Qs + m * kTile, &tm_qkv, &bars->vlo_full[slot], 3 * kC + h * kHd, j, m * 128, b);
       }
-      const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
-
-      // ---- pass 2: P = exp2(S * c - max * c) as packed fp16 into the same TMEM columns, row sum in fp32
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
-        uint32_t pk[16];
-        if ((c + 1) * 32 <= F) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs));
-            ls[e & 3] += e0 + e1;
-            pk[e] = pack_f16x2(e0, e1);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int col = c * 32 + 2 * e;
-            const float e0 = col < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs)) : 0.f;
-            const float e1 = col + 1 < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs)) : 0.f;
-            ls[e & 3] += e0 + e1;
-            pk[e] = pack_f16x2(e0, e1);
-          }
-        }
-        ptx::tmem_st_32x16(taddr + c * 16, pk);
-      };
-      for (int c = 0; c < n_chunks; c += 2) {
-        uint32_t ra[32], rb[32];
-        const bool two = c + 1 < n_chunks;
-        ptx::tmem_ld_32x32(taddr + c * 32, ra);
-        if (two) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
-        ptx::tmem_ld_wait();
-        exp_chunk(ra, c);
-        if (two) exp_chunk(rb, c + 1);
-      }
-      ptx::tmem_st_wait();
+      const float inv = softmax_row<NCH>(taddr, F, n_chunks);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->p_full[slot]);
-      const float inv = rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
-      // v_lo row of this query (exact "- V" term): in flight while the tensor core computes P V
-      uint4 vl[8];
-      {
-        const __half* p = qkv + (static_cast<size_t>(b) * F + (valid ? r : 0)) * J * kQkvRow +
-                          static_cast<size_t>(j) * kQkvRow + 3 * kC + h * kHd;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) vl[g] = valid ? ld_nc_v4(p + g * 8) : make_uint4(0u, 0u, 0u, 0u);
-      }
 
       // ---- O row out of TMEM, then the columns are free for the next S
       ptx::mbar_wait(&bars->o_full[slot], i & 1);
@@ -295,13 +309,15 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
       // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
       ptx::bar_sync(1 + slot, 128);          // the issuer is past the read-wait of the previous tile's stores: Stg is free
-      uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // Q_m is dead (S complete): hi staging, swizzled
+      ptx::mbar_wait(&bars->vlo_full[slot], i & 1);
+      uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // v_lo row in, hi row out (same thread, same 16 bytes)
       const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const uint4 vh = *reinterpret_cast<const uint4*>(v_row + ((g << 4) ^ sw));
+        const uint4 vl = *reinterpret_cast<const uint4*>(hi_row + ((g << 4) ^ sw));
         const uint32_t vhw[4] = {vh.x, vh.y, vh.z, vh.w};
-        const uint32_t vlw[4] = {vl[g].x, vl[g].y, vl[g].z, vl[g].w};
+        const uint32_t vlw[4] = {vl.x, vl.y, vl.z, vl.w};
         float x[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -384,7 +400,7 @@ int encode_tokens_4d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int e
 
 template <int NSLOT>
 int tc_smem_bytes(int n_mt) {
-  return NSLOT * (3 * n_mt + 1) * kTile + static_cast<int>(sizeof(TcBars<NSLOT>)) + (NSLOT == 1 ? 0 : 1024);
+  return NSLOT * (3 * n_mt + 1) * kTile + static_cast<int>(sizeof(TcBars<NSLOT>)) + 1024 /*alignment slack*/;
 }
 
 }  // namespace
@@ -406,31 +422,36 @@ int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half*
 
 cudaError_t configure_attention_tc() {
   cudaError_t e;
-#define D3D_CFG_TC(FMT_, NSLOT_)                                                                                       \
-  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_, NSLOT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                tc_smem_bytes<NSLOT_>(2))) != cudaSuccess)                                           \
+#define D3D_CFG_TC(FMT_, NCH_)                                                                                       \
+  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_, 2, NCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                tc_smem_bytes<2>(2))) != cudaSuccess)                                               \
     return e;
-  D3D_CFG_TC(FMT_SPLIT16, 1) D3D_CFG_TC(FMT_F8C, 1) D3D_CFG_TC(FMT_SPLIT16, 2) D3D_CFG_TC(FMT_F8C, 2)
+  D3D_CFG_TC(FMT_SPLIT16, 0) D3D_CFG_TC(FMT_F8C, 0) D3D_CFG_TC(FMT_SPLIT16, 3) D3D_CFG_TC(FMT_F8C, 3)
+  D3D_CFG_TC(FMT_SPLIT16, 8) D3D_CFG_TC(FMT_F8C, 8)
 #undef D3D_CFG_TC
   return cudaSuccess;
 }
 
-cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int slots,
-                                    int num_sms, cudaStream_t st) {
+cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
+                                    cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   if (F <= 64 || F > 256) return cudaErrorInvalidValue;
   const int n_mt = (F + 127) / 128;
   const int NKp = (F + 15) / 16 * 16;
   const int n_units = B * J * kHeads;
-  if (slots == 1) {
-    const int grid = n_units < 2 * num_sms ? n_units : 2 * num_sms;
-    auto kern = fmt == FMT_F8C ? attn_temporal_tc_kernel<FMT_F8C, 1> : attn_temporal_tc_kernel<FMT_SPLIT16, 1>;
-    kern<<<grid, 192, tc_smem_bytes<1>(n_mt), st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, n_units, n_mt, NKp);
+  const int n_chunks = (NKp + 31) / 32;
+  const int nch = (n_chunks == 8 && F > 224) ? 8 : ((n_chunks == 3 && F > 64) ? 3 : 0);   // F = 243 / 81 specialisations
+  const int grid = n_units < num_sms ? n_units : num_sms;
+  const int smem = tc_smem_bytes<2>(n_mt);
+#define D3D_LAUNCH_TC(FMT_, NCH_)                                                                               \
+  attn_temporal_tc_kernel<FMT_, 2, NCH_><<<grid, 320, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, \
+                                                                  n_units, n_mt, NKp)
+  if (fmt == FMT_F8C) {
+    if (nch == 8) D3D_LAUNCH_TC(FMT_F8C, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_F8C, 3); else D3D_LAUNCH_TC(FMT_F8C, 0);
   } else {
-    const int grid = n_units < num_sms ? n_units : num_sms;
-    auto kern = fmt == FMT_F8C ? attn_temporal_tc_kernel<FMT_F8C, 2> : attn_temporal_tc_kernel<FMT_SPLIT16, 2>;
-    kern<<<grid, 320, tc_smem_bytes<2>(n_mt), st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, n_units, n_mt, NKp);
+    if (nch == 8) D3D_LAUNCH_TC(FMT_SPLIT16, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_SPLIT16, 3); else D3D_LAUNCH_TC(FMT_SPLIT16, 0);
   }
+#undef D3D_LAUNCH_TC
   return cudaGetLastError();
 }
 

@@ -117,10 +117,8 @@ struct AttnTcMaps {
 int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int F, int J,
                       int64_t max_clips);
 cudaError_t configure_attention_tc();
-// slots: 2 = one CTA per SM with two 128-query tiles in flight and double-buffered units (default), 1 = two
-// single-slot CTAs per SM.
-cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int slots,
-                                    int num_sms, cudaStream_t st);
+cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
+                                    cudaStream_t st);
 // CUDA-core validation kernels (fp32 arithmetic on the same packed input)
 cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                       int J, cudaStream_t st);
