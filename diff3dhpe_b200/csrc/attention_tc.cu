@@ -21,8 +21,8 @@
 // flight: while one slot runs its softmax on the CUDA cores the other is in its tensor-core phase, and the next
 // unit's Q/K/V are already landing.  Measured history and ncu evidence: DESIGN.md section 4.2.
 //
-// Warp roles (320 threads): 0..3 softmax + epilogue of slot 0 (TMEM lane quadrant = warp & 3), 4..7 of slot 1,
-// 8 = TMA producer, 9 = MMA issuer and TMEM allocator.
+// Warp roles (384 threads): 0..3 softmax + epilogue of slot 0 (TMEM lane quadrant = warp & 3), 4..7 of slot 1,
+// 8 = TMA producer, 9 = MMA issuer and TMEM allocator, 10..11 idle (they complete the control warpgroup).
 #include "kernels.cuh"
 #include "operand.cuh"
 #include "ptx.cuh"
@@ -30,6 +30,13 @@
 namespace d3d {
 namespace {
 
+constexpr int kTcThreads = 384;           // 3 warpgroups: softmax slot 0, softmax slot 1, control (TMA, MMA, 2 idle warps)
+// 384 threads launch with 168 registers each (3 warps per SM sub-partition x 168 x 32 <= 16 384).  The softmax rows
+// keep four 32-column TMEM batches in flight (128 registers): the control warpgroup hands its surplus over with
+// setmaxnreg (2 x 128 x (216 - 168) <= 128 x (168 - 40)); each setmaxnreg sits inside its role branch so that ptxas
+// allocates per branch.
+constexpr int kCtrlRegs = 40, kSoftmaxRegs = 216;
+static_assert(2 * 128 * (kSoftmaxRegs - 168) <= 128 * (168 - kCtrlRegs), "setmaxnreg pool overdrawn");
 constexpr int kTile = 128 * 128;          // bytes of one {64 halves x 128 rows} box
 constexpr int kSlotCols = 256;            // TMEM columns of one slot: S up to 256 fp32; P aliases [0,128), O [128,192)
 constexpr int kOCol = 128;
@@ -172,7 +179,7 @@ __device__ __forceinline__ float softmax_row(uint32_t taddr, int F, int n_chunks
 // Work items of a CTA, in order: w = 0, 1, 2, ... ; unit n = w / n_mt (the CTA's n-th unit), 128-query tile
 // m = w % n_mt; slot = w % NSLOT (i-th item of that slot, i = w / NSLOT); stage = n % NSLOT (k-th use, k = n / NSLOT).
 template <int FMT, int NSLOT, int NCH>
-__global__ void __maxnreg__(200)      // 320 threads x 200 registers = 64 000 (launch bounds would round down to 168 and spill)
+__global__ void __launch_bounds__(kTcThreads, 1)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
                         const __grid_constant__ CUtensorMap tm_second, const __half* __restrict__ qkv, int F, int J,
                         int n_units, int n_mt, int NKp) {
@@ -211,6 +218,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
     if (ptx::elect_one()) {
       for (int n = 0; n < n_local; ++n) {
         const int unit = blockIdx.x + n * gridDim.x;
@@ -231,6 +239,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
     if (ptx::elect_one()) {
       const uint32_t idesc_qk = ptx::make_idesc_f16(128, static_cast<uint32_t>(NKp), 0);
       const uint32_t idesc_pv = ptx::make_idesc_f16(128, kHd, 0) | (1u << 16);      // B (= V) is MN-major
@@ -268,8 +277,11 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       for (int w = W - (NSLOT - 1); w < W; ++w)
         if (w >= 0) issue_pv(w);
     }
+  } else if (warp > kMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   } else {
     // ------------------------------------------------------------------ softmax + epilogue: thread = query row
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSoftmaxRegs));
     const int slot = warp >> 2;
     const int row_l = (warp & 3) * 32 + lane;                             // row inside the 128-query tile
     const uint32_t taddr = tmem_base + slot * kSlotCols + (static_cast<uint32_t>((warp & 3) * 32) << 16);
@@ -444,7 +456,7 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, i
   const int grid = n_units < num_sms ? n_units : num_sms;
   const int smem = tc_smem_bytes<2>(n_mt);
 #define D3D_LAUNCH_TC(FMT_, NCH_)                                                                               \
-  attn_temporal_tc_kernel<FMT_, 2, NCH_><<<grid, 320, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, \
+  attn_temporal_tc_kernel<FMT_, 2, NCH_><<<grid, kTcThreads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, \
                                                                   n_units, n_mt, NKp)
   if (fmt == FMT_F8C) {
     if (nch == 8) D3D_LAUNCH_TC(FMT_F8C, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_F8C, 3); else D3D_LAUNCH_TC(FMT_F8C, 0);
