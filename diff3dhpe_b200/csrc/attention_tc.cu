@@ -37,6 +37,7 @@ constexpr int kTcThreads = 384;           // 3 warpgroups: softmax slot 0, softm
 // allocates per branch.
 constexpr int kCtrlRegs = 40, kSoftmaxRegs = 216;
 static_assert(2 * 128 * (kSoftmaxRegs - 168) <= 128 * (168 - kCtrlRegs), "setmaxnreg pool overdrawn");
+constexpr int kSpatialRows = 7 * 17;      // spatial mode: tokens (7 frames) per unit
 constexpr int kTile = 128 * 128;          // bytes of one {64 halves x 128 rows} box
 constexpr int kSlotCols = 256;            // TMEM columns of one slot: S up to 256 fp32; P aliases [0,128), O [128,192)
 constexpr int kOCol = 128;
@@ -176,9 +177,59 @@ __device__ __forceinline__ float softmax_row(uint32_t taddr, int F, int n_chunks
   return rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
 }
 
+// Spatial mode: the 128-row tile holds 7 frames x 17 joints (rows 119..127 belong to the next unit and are never
+// stored); query row r attends only the 17 keys of its own frame, columns [17 (r / 17), +17) of S.  A warp's 32 rows
+// touch at most 3 frames, i.e. a 51-column window inside the three aligned 32-column chunks starting at chunk
+// wq >> 1 (wq = TMEM lane quadrant); each thread masks its own 17 columns out of those 96.  P is written for all
+// 128 keys (zero outside the window), so the P.V chain is the same as in the temporal mode.
+__device__ __forceinline__ float softmax_row_spatial(uint32_t taddr, int row_l, int wq) {
+  const int cs = wq >> 1;
+  uint32_t a[32], b[32], c[32];
+  ptx::tmem_ld_32x32(taddr + cs * 32, a);
+  ptx::tmem_ld_32x32(taddr + cs * 32 + 32, b);
+  ptx::tmem_ld_32x32(taddr + cs * 32 + 64, c);
+  ptx::tmem_ld_wait();
+  const int fr = row_l < 119 ? row_l / 17 : 6;
+  const unsigned lo = static_cast<unsigned>(17 * fr - 32 * cs);      // first column of the window, in loaded columns
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    if (static_cast<unsigned>(e) - lo < 17u) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(a[e]));
+    if (static_cast<unsigned>(e + 32) - lo < 17u) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(b[e]));
+    if (static_cast<unsigned>(e + 64) - lo < 17u) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(c[e]));
+  }
+  const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
+  float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  auto exp_chunk = [&](const uint32_t (&rr)[32], int base) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const bool in0 = static_cast<unsigned>(base + 2 * e) - lo < 17u, in1 = static_cast<unsigned>(base + 2 * e + 1) - lo < 17u;
+      const float e0 = in0 ? ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs)) : 0.f;
+      const float e1 = in1 ? ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs)) : 0.f;
+      ls[e & 3] += e0 + e1;
+      pk[e] = pack_f16x2(e0, e1);
+    }
+    ptx::tmem_st_32x16(taddr + cs * 16 + (base >> 1), pk);
+  };
+  exp_chunk(a, 0);
+  exp_chunk(b, 32);
+  exp_chunk(c, 64);
+  {
+    uint32_t z[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) z[e] = 0u;
+    ptx::tmem_st_32x16(taddr + (cs == 0 ? 48 : 0), z);      // the 32 keys this warp did not load
+  }
+  ptx::tmem_st_wait();
+  return rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
+}
+
 // Work items of a CTA, in order: w = 0, 1, 2, ... ; unit n = w / n_mt (the CTA's n-th unit), 128-query tile
 // m = w % n_mt; slot = w % NSLOT (i-th item of that slot, i = w / NSLOT); stage = n % NSLOT (k-th use, k = n / NSLOT).
-template <int FMT, int NSLOT, int NCH>
+// SPATIAL: unit = (group of 7 frames = 119 consecutive tokens, head); the maps are 2-D token-major views encoded with
+// rank 4 (coordinates (channel, token, 0, 0)), n_mt == 1, NKp == 128 and the store maps have 119-row boxes.
+template <int FMT, int NSLOT, int NCH, bool SPATIAL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
                         const __grid_constant__ CUtensorMap tm_second, const __half* __restrict__ qkv, int F, int J,
@@ -223,7 +274,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       for (int n = 0; n < n_local; ++n) {
         const int unit = blockIdx.x + n * gridDim.x;
         const int seq = unit >> 3, h = unit & 7;
-        const int b = seq / J, j = seq - b * J;
+        const int b = SPATIAL ? 0 : seq / J, j = SPATIAL ? seq * 119 : seq - b * J;     // j: token coordinate when SPATIAL
         const int stage = n % NSLOT, k = n / NSLOT;
         uint8_t* Qs = smem + stage * stage_bytes;
         uint8_t* Ks = Qs + n_mt * kTile;
@@ -286,7 +337,8 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const int row_l = (warp & 3) * 32 + lane;                             // row inside the 128-query tile
     const uint32_t taddr = tmem_base + slot * kSlotCols + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int n_chunks = (NKp + 31) >> 5;
-    if (NCH > 0 && (n_chunks != NCH || F <= 32 * (NCH - 1))) __trap();    // launcher / instantiation mismatch
+    if (!SPATIAL && NCH > 0 && (n_chunks != NCH || F <= 32 * (NCH - 1))) __trap();    // launcher / instantiation mismatch
+    if (SPATIAL && (n_mt != 1 || NKp != 128)) __trap();
     const int sw = (row_l & 7) << 4;                                      // swizzle XOR of this row (bytes)
     const bool issuer = row_l == 0;                                       // issues the slot's TMA stores
     uint8_t* Stg = StgAll + slot * kTile;
@@ -295,7 +347,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       const int i = w / NSLOT, stage = n % NSLOT;
       const int unit = blockIdx.x + n * gridDim.x;
       const int seq = unit >> 3, h = unit & 7;
-      const int b = seq / J, j = seq - b * J;
+      const int b = SPATIAL ? 0 : seq / J, j = SPATIAL ? seq * 119 : seq - b * J;
       uint8_t* Qs = smem + stage * stage_bytes;
       const uint8_t* Vs = Qs + 2 * n_mt * kTile;
       const int r = m * 128 + row_l;
@@ -305,7 +357,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         ptx::mbar_arrive_expect_tx(&bars->vlo_full[slot], kTile);
         ptx::tma_load_4d(Qs + m * kTile, &tm_qkv, &bars->vlo_full[slot], 3 * kC + h * kHd, j, m * 128, b);
       }
-      const float inv = softmax_row<NCH>(taddr, F, n_chunks);
+      const float inv = SPATIAL ? softmax_row_spatial(taddr, row_l, warp & 3) : softmax_row<NCH>(taddr, F, n_chunks);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->p_full[slot]);
 
@@ -388,9 +440,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// [B, F, J, row] token-major array viewed as a 4-D tensor (channel, j, f, b); box = {64 channels, 1, 128 frames, 1}
-int encode_tokens_4d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int elem_bytes, int64_t row_elems, int J,
-                     int F, int64_t B, CUtensorMapSwizzle swz) {
+int encode_rank4(CUtensorMap* out, void* base, CUtensorMapDataType dt, const cuuint64_t (&dims)[4],
+                 const cuuint64_t (&strides)[3], const cuuint32_t (&box)[4], CUtensorMapSwizzle swz) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -399,15 +450,32 @@ int encode_tokens_4d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int e
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return -1;
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  const cuuint64_t row_bytes = static_cast<cuuint64_t>(row_elems) * elem_bytes;
-  cuuint64_t dims[4] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(J), static_cast<cuuint64_t>(F),
-                        static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[3] = {row_bytes, row_bytes * J, row_bytes * J * F};
-  cuuint32_t box[4] = {64, 1, 128, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+// [B, F, J, row] token-major array viewed as a 4-D tensor (channel, j, f, b); box = {64 channels, 1, 128 frames, 1}
+int encode_tokens_4d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int elem_bytes, int64_t row_elems, int J,
+                     int F, int64_t B, CUtensorMapSwizzle swz) {
+  const cuuint64_t row_bytes = static_cast<cuuint64_t>(row_elems) * elem_bytes;
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(J), static_cast<cuuint64_t>(F),
+                              static_cast<cuuint64_t>(B)};
+  const cuuint64_t strides[3] = {row_bytes, row_bytes * J, row_bytes * J * F};
+  const cuuint32_t box[4] = {64, 1, 128, 1};
+  return encode_rank4(out, base, dt, dims, strides, box, swz);
+}
+
+// The same array as a plain [tokens, row] matrix (rank 4 with two unit dimensions, so that the kernel's 4-D TMA
+// instructions serve both modes); box = {64 channels, box_rows tokens, 1, 1}
+int encode_tokens_2d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int elem_bytes, int64_t row_elems,
+                     int64_t tokens, int box_rows, CUtensorMapSwizzle swz) {
+  const cuuint64_t row_bytes = static_cast<cuuint64_t>(row_elems) * elem_bytes;
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(tokens), 1, 1};
+  const cuuint64_t strides[3] = {row_bytes, row_bytes * tokens, row_bytes * tokens};
+  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
+  return encode_rank4(out, base, dt, dims, strides, box, swz);
 }
 
 template <int NSLOT>
@@ -432,14 +500,31 @@ int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half*
                           CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt,
+                              int64_t tokens) {
+  // loads: 128-row boxes (rows beyond the 119 of a unit are read but masked); stores: 119-row boxes
+  if (encode_tokens_2d(&maps->qkv, const_cast<__half*>(qkv), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kQkvRow, tokens, 128,
+                       CU_TENSOR_MAP_SWIZZLE_128B))
+    return -1;
+  if (encode_tokens_2d(&maps->o_hi, o_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, tokens, kSpatialRows,
+                       CU_TENSOR_MAP_SWIZZLE_128B))
+    return -1;
+  if (fmt == FMT_F8C)
+    return encode_tokens_2d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 2 * kC, tokens, kSpatialRows,
+                            CU_TENSOR_MAP_SWIZZLE_NONE);
+  return encode_tokens_2d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, tokens, kSpatialRows,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 cudaError_t configure_attention_tc() {
   cudaError_t e;
-#define D3D_CFG_TC(FMT_, NCH_)                                                                                       \
-  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_, 2, NCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                tc_smem_bytes<2>(2))) != cudaSuccess)                                               \
+#define D3D_CFG_TC(FMT_, NCH_, SP_)                                                                                       \
+  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_, 2, NCH_, SP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                tc_smem_bytes<2>(2))) != cudaSuccess)                                                    \
     return e;
-  D3D_CFG_TC(FMT_SPLIT16, 0) D3D_CFG_TC(FMT_F8C, 0) D3D_CFG_TC(FMT_SPLIT16, 3) D3D_CFG_TC(FMT_F8C, 3)
-  D3D_CFG_TC(FMT_SPLIT16, 8) D3D_CFG_TC(FMT_F8C, 8)
+  D3D_CFG_TC(FMT_SPLIT16, 0, false) D3D_CFG_TC(FMT_F8C, 0, false) D3D_CFG_TC(FMT_SPLIT16, 3, false)
+  D3D_CFG_TC(FMT_F8C, 3, false) D3D_CFG_TC(FMT_SPLIT16, 8, false) D3D_CFG_TC(FMT_F8C, 8, false)
+  D3D_CFG_TC(FMT_SPLIT16, 0, true) D3D_CFG_TC(FMT_F8C, 0, true)
 #undef D3D_CFG_TC
   return cudaSuccess;
 }
@@ -456,7 +541,7 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, i
   const int grid = n_units < num_sms ? n_units : num_sms;
   const int smem = tc_smem_bytes<2>(n_mt);
 #define D3D_LAUNCH_TC(FMT_, NCH_)                                                                               \
-  attn_temporal_tc_kernel<FMT_, 2, NCH_><<<grid, kTcThreads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, \
+  attn_temporal_tc_kernel<FMT_, 2, NCH_, false><<<grid, kTcThreads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, \
                                                                   n_units, n_mt, NKp)
   if (fmt == FMT_F8C) {
     if (nch == 8) D3D_LAUNCH_TC(FMT_F8C, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_F8C, 3); else D3D_LAUNCH_TC(FMT_F8C, 0);
@@ -464,6 +549,23 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, i
     if (nch == 8) D3D_LAUNCH_TC(FMT_SPLIT16, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_SPLIT16, 3); else D3D_LAUNCH_TC(FMT_SPLIT16, 0);
   }
 #undef D3D_LAUNCH_TC
+  return cudaGetLastError();
+}
+
+// Spatial mode (J == 17): units of 7 frames x one head
+cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int64_t tokens, int num_sms, cudaStream_t st) {
+  if (tokens <= 0) return cudaSuccess;
+  const int64_t groups = (tokens + kSpatialRows - 1) / kSpatialRows;
+  if (groups * kHeads > 0x7fffffff) return cudaErrorInvalidValue;
+  const int n_units = static_cast<int>(groups) * kHeads;
+  const int grid = n_units < num_sms ? n_units : num_sms;
+  const int smem = tc_smem_bytes<2>(1);
+  if (fmt == FMT_F8C)
+    attn_temporal_tc_kernel<FMT_F8C, 2, 0, true><<<grid, kTcThreads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, nullptr,
+                                                                               kSpatialRows, 17, n_units, 1, 128);
+  else
+    attn_temporal_tc_kernel<FMT_SPLIT16, 2, 0, true><<<grid, kTcThreads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second,
+                                                                                   nullptr, kSpatialRows, 17, n_units, 1, 128);
   return cudaGetLastError();
 }
 

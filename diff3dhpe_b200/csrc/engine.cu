@@ -69,6 +69,8 @@ struct d3d_handle {
   OperandBuf A, ATT, H;
   AttnTcMaps attn_tc;        // tcgen05 temporal attention: maps bound to QKV -> ATT
   bool have_attn_tc = false;
+  AttnTcMaps attn_sp;        // spatial mode of the same kernel (J == 17)
+  bool have_attn_sp = false;
   float *in_x2d = nullptr, *y = nullptr, *in_noise = nullptr;
   int64_t in_noise_cap = 0;
   float *t_f32 = nullptr, *e0 = nullptr, *h1 = nullptr, *h2 = nullptr;   // time-MLP scratch, max(max_clips, S) rows
@@ -252,10 +254,16 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
 int run_attention(d3d_handle* h, const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, bool spatial,
                   int mode, cudaStream_t st) {
   if (spatial) {
-    if (mode == D3D_ATTN_SIMT || h->J != 17)
+    if (mode == D3D_ATTN_SIMT || h->J != 17) {
       KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, h->fmt, B * h->F, h->J, h->J, 1, 1, st));
-    else
+    } else if (mode == D3D_ATTN_DEFAULT && h->have_attn_sp && qkv == h->QKV && env_int("D3D_ATTN_TC_SPATIAL", 1)) {
+      if (!o_f32 && (o_hi != h->ATT.hi || o_lo != h->ATT.lo)) return fail(h, -2, "attention output must be the ATT operand");
+      const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial_tc(h->attn_sp, h->fmt, T, h->num_sms, st));
+      if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, o_f32, T, kC, h->fmt, st));
+    } else {
       KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial(qkv, o_hi, o_lo, o_f32, h->fmt, static_cast<int64_t>(B) * h->F, h->J, st));
+    }
   } else {
     if (mode == D3D_ATTN_SIMT) {
       KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_simt(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));
@@ -474,6 +482,11 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
     if ((r = alloc_operand(h, &h->A, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->ATT, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->H, h->tok_cap, kHidden))) return r;
+    if (h->J == 17) {
+      if (make_attn_tc_maps_spatial(&h->attn_sp, h->QKV, h->ATT.hi, h->ATT.lo, h->fmt, h->tok_cap))
+        return fail(h, -20, "cuTensorMapEncodeTiled failed for the spatial-attention maps");
+      h->have_attn_sp = true;
+    }
     if (h->F > 64) {
       if (make_attn_tc_maps(&h->attn_tc, h->QKV, h->ATT.hi, h->ATT.lo, h->fmt, h->F, h->J, cfg->max_clips))
         return fail(h, -20, "cuTensorMapEncodeTiled failed for the temporal-attention maps");

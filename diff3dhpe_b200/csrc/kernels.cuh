@@ -116,6 +116,9 @@ struct AttnTcMaps {
 };
 int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int F, int J,
                       int64_t max_clips);
+// spatial mode of the same kernel (J == 17): units of 7 frames (119 consecutive tokens) x one head, block-diagonal mask
+int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int64_t tokens);
+cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int64_t tokens, int num_sms, cudaStream_t st);
 cudaError_t configure_attention_tc();
 cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
                                     cudaStream_t st);

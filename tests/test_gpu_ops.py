@@ -111,20 +111,21 @@ def test_attention_core(F, mode, tol, spatial):
 
 
 @pytest.mark.parametrize("gemm_mode", [_lib.GEMM_TC_F8C, _lib.GEMM_TC_SPLIT3])
-@pytest.mark.parametrize("F,B", [(243, 5), (81, 6), (129, 3), (128, 3), (65, 4), (256, 2)])
-def test_temporal_attention_tcgen05_operand(F, B, gemm_mode):
-    """The tcgen05/TMEM/TMA temporal kernel (default for F > 64) against the CUDA-core kernel, on EVERY byte of the
-    operand the proj GEMM consumes (hi fp16 | fp16 lo, or hi | e5m2(x 2^-8) | e5m2(lo 2^4)); B x 17 x 8 work units
-    exceed one wave of 2 x 148 CTAs, so the persistent loop, its barrier phases and the staging reuse are exercised."""
+@pytest.mark.parametrize("F,B,spatial", [(243, 5, False), (81, 6, False), (129, 3, False), (128, 3, False), (65, 4, False),
+                                         (256, 2, False), (243, 5, True), (27, 40, True), (7, 17, True), (1, 1, True)])
+def test_attention_tcgen05_operand(F, B, spatial, gemm_mode):
+    """The tcgen05/TMEM/TMA attention kernel (temporal: default for F > 64; spatial: units of 7 frames with a
+    block-diagonal mask) against the CUDA-core kernel, on EVERY byte of the operand the proj GEMM consumes (hi fp16 |
+    fp16 lo, or hi | e5m2(x 2^-8) | e5m2(lo 2^4)).  The larger cases exceed one wave of 148 CTAs x 2 slots, so the
+    persistent loop, its barrier phases, the stage / staging reuse and the ragged last spatial group are exercised."""
     J, C = 17, 512
     eng = Engine(F, max_clips=B, gemm_mode=gemm_mode)
     qkv = _rand((B * F * J, 3 * C), 70 + F, 1.5)
     qkv[:, :2 * C] = qkv[:, :2 * C].half().float()
-    ref = eng.op_attention(qkv.cuda(), B, False, _lib.ATTN_SIMT).cpu()
-    hi, second = eng.debug_attention_operand(qkv.cuda(), B, False, _lib.ATTN_DEFAULT)
-    hi_s, second_s = eng.debug_attention_operand(qkv.cuda(), B, False, _lib.ATTN_SIMT)
+    ref = eng.op_attention(qkv.cuda(), B, spatial, _lib.ATTN_SIMT).cpu()
+    hi, second = eng.debug_attention_operand(qkv.cuda(), B, spatial, _lib.ATTN_DEFAULT)
     eng.close()
-    hi, hi_s = hi.float().cpu(), hi_s.float().cpu()
+    hi = hi.float().cpu()
     assert torch.isfinite(hi).all()
     assert (hi - ref).abs().max().item() < 4e-3 + 2 ** -10 * ref.abs().max().item()
     if gemm_mode == _lib.GEMM_TC_SPLIT3:

@@ -1,17 +1,22 @@
 mkdir -p gpurun_out
-T=r01n
+T=r01o
+STAGES=attn_sp_tc_f243,attn_sp_tc_f27_split16 timeout 300 python tools/gpu_first_contact.py > gpurun_out/${T}_contact.log 2>&1; cut -c1-1200 gpurun_out/${T}_contact.log
 timeout 300 python -m pytest tests/test_gpu_ops.py -k "attention" -x -q > gpurun_out/${T}_pytest_attn.log 2>&1; tail -3 gpurun_out/${T}_pytest_attn.log
 timeout 300 python -m pytest tests/test_gpu_sampler.py -x -q > gpurun_out/${T}_pytest_sampler.log 2>&1; tail -3 gpurun_out/${T}_pytest_sampler.log
-timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
-python - <<PY
+run_bench() {  # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err
+  python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/${T}_bench.json"))
-    print(round(d["value"]), d["ms_per_step"], d["clocks"]["sm_mhz"], d["roofline"]["per_class_ms"])
+    d=json.load(open("gpurun_out/${T}_bench_$name.json"))
+    print("$name", round(d["value"]), d["ms_per_step"], d["clocks"]["sm_mhz"], d["roofline"]["per_class_ms"])
 except Exception as e:
-    print("bench failed", e)
+    print("bench $name failed", e)
 PY
-for k in attn_temporal_tc; do
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 20 -c 1 -o gpurun_out/${T}_full_$k -f python bench.py --steps 1 --warmup 3 --clips 128 --no-cpu-baseline > gpurun_out/${T}_full_$k.log 2>&1
-  echo "ncu $k rc=$?"
-done
+}
+run_bench default D3D_X=0
+run_bench cs2 D3D_GEMM_CS=2 D3D_GEMM_EW_GELU=8
+run_bench sp_old D3D_ATTN_TC_SPATIAL=0
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_temporal_tc -s 20 -c 2 -o gpurun_out/${T}_full_attn_tc -f python bench.py --steps 1 --warmup 3 --clips 128 --no-cpu-baseline > gpurun_out/${T}_full_attn_tc.log 2>&1
+echo "ncu rc=$?"

@@ -242,7 +242,7 @@ def sampler_f8c_f9_s9():
     return _sampler(3, 0, True, "sampler_f9_b2_s9_clip")
 
 
-def _attn_tc(F, B, gemm_mode=3):
+def _attn_tc(F, B, gemm_mode=3, spatial=False):
     """tcgen05 temporal kernel vs the CUDA-core kernel: error statistics by query row / head / channel to localise
     layout bugs (descriptor, swizzle, TMEM packing)."""
     torch, _lib, synthetic, Engine = _imports()
@@ -251,9 +251,9 @@ def _attn_tc(F, B, gemm_mode=3):
     g = torch.Generator().manual_seed(7)
     qkv = torch.randn(B * F * J, 3 * C, generator=g) * 1.5
     qkv[:, :2 * C] = qkv[:, :2 * C].half().float()
-    ref = eng.op_attention(qkv.cuda(), B, False, 1).cpu().view(B, F, J, 8, 64)
-    out = eng.op_attention(qkv.cuda(), B, False, 0).cpu().view(B, F, J, 8, 64)
-    hi, second = eng.debug_attention_operand(qkv.cuda(), B, False, 0)
+    ref = eng.op_attention(qkv.cuda(), B, spatial, 1).cpu().view(B, F, J, 8, 64)
+    out = eng.op_attention(qkv.cuda(), B, spatial, 0).cpu().view(B, F, J, 8, 64)
+    hi, second = eng.debug_attention_operand(qkv.cuda(), B, spatial, 0)
     torch.cuda.synchronize()
     err = (out - ref).abs()
     res = {"max_err": err.max().item(), "mean_err": err.mean().item(), "finite": bool(torch.isfinite(out).all()),
@@ -263,6 +263,7 @@ def _attn_tc(F, B, gemm_mode=3):
            "err_by_frame_128_136": [round(v, 5) for v in err.amax(dim=(0, 2, 3, 4)).tolist()[128:136]],
            "err_by_frame_last4": [round(v, 5) for v in err.amax(dim=(0, 2, 3, 4)).tolist()[-4:]],
            "err_by_chan_first8": [round(v, 5) for v in err.amax(dim=(0, 1, 2, 3)).tolist()[:8]],
+           "err_by_joint": [round(v, 5) for v in err.amax(dim=(0, 1, 3, 4)).tolist()],
            "out0": out[0, 0, 0, 0, :4].tolist(), "ref0": ref[0, 0, 0, 0, :4].tolist()}
     hi = hi.float().cpu().view(B, F, J, 8, 64)
     res["hi_err"] = (hi - ref).abs().max().item()
@@ -275,6 +276,16 @@ def _attn_tc(F, B, gemm_mode=3):
 @stage
 def attn_tc_f243():
     return _attn_tc(243, 5)
+
+
+@stage
+def attn_sp_tc_f243():
+    return _attn_tc(243, 5, spatial=True)
+
+
+@stage
+def attn_sp_tc_f27_split16():
+    return _attn_tc(27, 3, gemm_mode=0, spatial=True)
 
 
 @stage

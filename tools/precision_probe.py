@@ -67,13 +67,20 @@ def mm_mode(a, bt, mode):
 
 
 class Policy(TorchFunctionMode):
-    def __init__(self, lin, attn):
+    def __init__(self, lin, attn, n_calls=0):
+        """lin = "early>last" runs the first n_calls-1 denoiser calls of the sampler with the `early` linear mode and
+        only the last one with `last` (DDIM damps the errors of the early steps)."""
         super().__init__()
-        self.lin, self.attn = lin, attn
+        self.lin_early, self.lin_last = (lin.split(">") + [lin])[:2] if ">" in lin else (lin, lin)
+        self.lin, self.attn = self.lin_early, attn
         self.n_qk = 0
+        self.n_calls, self.call_idx = n_calls, 0
 
     def __torch_function__(self, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
+        if func is F.linear and args[1].shape[1] == 5:        # fusion_layer: a new denoiser call starts
+            self.call_idx += 1
+            self.lin = self.lin_last if self.call_idx >= self.n_calls else self.lin_early
         if func is F.linear and args[1].shape[1] >= 64 and self.lin != "fp32":
             x, w = args[0], args[1]
             b = args[2] if len(args) > 2 else kwargs.get("bias")
@@ -120,7 +127,7 @@ def main():
         if os.environ.get("PROBE_POLICIES"):     # e.g. PROBE_POLICIES=f8c52:fp16xv,f8c52_qk1:fp16xv
             policies = tuple(tuple(p.split(":")) for p in os.environ["PROBE_POLICIES"].split(","))
         for lin, attn in policies:
-            with torch.no_grad(), Policy(lin, attn):
+            with torch.no_grad(), Policy(lin, attn, S):
                 out = oracle.ddim_sample_loop(sd, x2d, y_T, steps, sampling_timesteps=S, clip_denoised=clip)
             err = (out - ref).abs()
             dm = abs(oracle.mpjpe(out, gt).item() - oracle.mpjpe(ref, gt).item())
