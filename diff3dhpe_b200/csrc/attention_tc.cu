@@ -46,10 +46,11 @@ constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;   // head_dim ** -0.
 // NSLOT = 128-query tiles in flight per CTA (each with its own 4 softmax warps and 256 TMEM columns) = shared-memory
 // stages (units resident per CTA).  Shipped: 2.  (A first version with one slot and two CTAs per SM measured 430 ms
 // per cfg3 step against 398 ms, profiles/r01m_bench_slots*.json.)
+constexpr int kMaxStages = 4;
 template <int NSLOT>
 struct TcBars {
-  uint64_t full[NSLOT];         // TMA bytes of the unit in this stage landed              (producer -> MMA)
-  uint64_t stage_free[NSLOT];   // every tile of the unit has left this stage               (epilogues -> producer)
+  uint64_t full[kMaxStages];        // TMA bytes of the unit in this stage landed          (producer -> MMA)
+  uint64_t stage_free[kMaxStages];  // every tile of the unit has left this stage           (epilogues -> producer)
   uint64_t s_full[NSLOT];       // S = Q K^T complete in this slot's TMEM columns           (MMA -> softmax)
   uint64_t p_full[NSLOT];       // P written to TMEM by all 128 rows                        (softmax -> MMA)
   uint64_t o_full[NSLOT];       // O = P V complete                                         (MMA -> epilogue)
@@ -226,18 +227,26 @@ __device__ __forceinline__ float softmax_row_spatial(uint32_t taddr, int row_l, 
 }
 
 // Work items of a CTA, in order: w = 0, 1, 2, ... ; unit n = w / n_mt (the CTA's n-th unit), 128-query tile
-// m = w % n_mt; slot = w % NSLOT (i-th item of that slot, i = w / NSLOT); stage = n % NSLOT (k-th use, k = n / NSLOT).
-// SPATIAL: unit = (group of 7 frames = 119 consecutive tokens, head); the maps are 2-D token-major views encoded with
-// rank 4 (coordinates (channel, token, 0, 0)), n_mt == 1, NKp == 128 and the store maps have 119-row boxes.
+// m = w % n_mt; slot = w % NSLOT (i-th item of that slot, i = w / NSLOT); shared-memory stage = n % n_stage (k-th use,
+// k = n / n_stage).  n_stage = 2 when a unit has two tiles (96 KB per unit), 4 when it has one (48 KB): units are
+// then loaded two to three items ahead of the tile being processed -- with only two stages the single-tile modes
+// (spatial, F <= 128) were bound by the load -> MMA -> softmax -> MMA -> store latency chain of two units in flight
+// (ncu: 62 % of the stall samples were softmax warps waiting on s_full / o_full, profiles/r01o_full_attn_tc.md).
+// SPATIAL: unit = (clip, group g of 7 frames = 119 consecutive tokens, head); groups never straddle clips (the last
+// group of a clip holds F % 7 frames), so a frame's position inside the tile -- and with it every rounding -- depends
+// only on its index inside the clip: results are bit-identical under any batch split.  The maps are 2-D token-major
+// views encoded with rank 4 (coordinates (channel, token, 0, 0)); n_mt == 1, NKp == 128; the store maps have 119-row
+// boxes, the *_tail maps (F % 7) * 17-row boxes.  J carries the groups per clip.
 template <int FMT, int NSLOT, int NCH, bool SPATIAL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
-                        const __grid_constant__ CUtensorMap tm_second, const __half* __restrict__ qkv, int F, int J,
-                        int n_units, int n_mt, int NKp) {
+                        const __grid_constant__ CUtensorMap tm_second, const __grid_constant__ CUtensorMap tm_hi_tail,
+                        const __grid_constant__ CUtensorMap tm_second_tail, int F, int J, int n_units, int n_mt, int NKp,
+                        int n_stage) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = 3 * n_mt * kTile;          // Q tiles | K tiles | V tiles of one unit
-  uint8_t* StgAll = smem + NSLOT * stage_bytes;      // 16 KB per slot: second-part staging of one 128-row output tile
+  uint8_t* StgAll = smem + n_stage * stage_bytes;    // 16 KB per slot: second-part staging of one 128-row output tile
   TcBars<NSLOT>* bars = reinterpret_cast<TcBars<NSLOT>*>(StgAll + NSLOT * kTile);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,10 +258,12 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     ptx::prefetch_tensormap(&tm_qkv);
     ptx::prefetch_tensormap(&tm_hi);
     ptx::prefetch_tensormap(&tm_second);
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
+    for (int s = 0; s < n_stage; ++s) {
       ptx::mbar_init(&bars->full[s], 1);
       ptx::mbar_init(&bars->stage_free[s], n_mt);
+    }
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
       ptx::mbar_init(&bars->s_full[s], 1);
       ptx::mbar_init(&bars->p_full[s], 128);
       ptx::mbar_init(&bars->o_full[s], 1);
@@ -274,8 +285,9 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       for (int n = 0; n < n_local; ++n) {
         const int unit = blockIdx.x + n * gridDim.x;
         const int seq = unit >> 3, h = unit & 7;
-        const int b = SPATIAL ? 0 : seq / J, j = SPATIAL ? seq * 119 : seq - b * J;     // j: token coordinate when SPATIAL
-        const int stage = n % NSLOT, k = n / NSLOT;
+        int b = seq / J, j = seq - b * J;
+        if (SPATIAL) { j = (b * F + 7 * j) * 17; b = 0; }        // token coordinate of the group's first row
+        const int stage = n % n_stage, k = n / n_stage;
         uint8_t* Qs = smem + stage * stage_bytes;
         uint8_t* Ks = Qs + n_mt * kTile;
         uint8_t* Vs = Ks + n_mt * kTile;
@@ -297,7 +309,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       const uint32_t s0 = ptx::smem_u32(smem);
       const int n_ks = NKp >> 4;
       auto issue_pv = [&](int w) {           // O[128, 64] = P[128, NKp] (TMEM) . V[NKp, 64], 16 keys per MMA
-        const int slot = w % NSLOT, i = w / NSLOT, stage = (w / n_mt) % NSLOT;
+        const int slot = w % NSLOT, i = w / NSLOT, stage = (w / n_mt) % n_stage;
         const uint32_t sV = s0 + stage * stage_bytes + 2 * n_mt * kTile;
         const uint32_t tcol = tmem_base + slot * kSlotCols;
         ptx::mbar_wait(&bars->p_full[slot], i & 1);
@@ -308,10 +320,10 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       };
       for (int w = 0; w < W; ++w) {
         const int n = w / n_mt, m = w - n * n_mt;
-        const int slot = w % NSLOT, i = w / NSLOT, stage = n % NSLOT;
+        const int slot = w % NSLOT, i = w / NSLOT, stage = n % n_stage;
         const uint32_t sQ = s0 + stage * stage_bytes, sK = sQ + n_mt * kTile;
         if (m == 0) {
-          ptx::mbar_wait(&bars->full[stage], (n / NSLOT) & 1);
+          ptx::mbar_wait(&bars->full[stage], (n / n_stage) & 1);
           ptx::tc_fence_after();
         }
         ptx::mbar_wait(&bars->tmem_free[slot], (i & 1) ^ 1);
@@ -344,10 +356,12 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     uint8_t* Stg = StgAll + slot * kTile;
     for (int w = slot; w < W; w += NSLOT) {
       const int n = w / n_mt, m = w - n * n_mt;
-      const int i = w / NSLOT, stage = n % NSLOT;
+      const int i = w / NSLOT, stage = n % n_stage;
       const int unit = blockIdx.x + n * gridDim.x;
       const int seq = unit >> 3, h = unit & 7;
-      const int b = SPATIAL ? 0 : seq / J, j = SPATIAL ? seq * 119 : seq - b * J;
+      int b = seq / J, j = seq - b * J;
+      const bool tail = SPATIAL && j == J - 1 && F % 7 != 0;      // last group of a clip: fewer than 7 frames to store
+      if (SPATIAL) { j = (b * F + 7 * j) * 17; b = 0; }
       uint8_t* Qs = smem + stage * stage_bytes;
       const uint8_t* Vs = Qs + 2 * n_mt * kTile;
       const int r = m * 128 + row_l;
@@ -417,9 +431,11 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       ptx::fence_proxy_async();
       ptx::bar_sync(1 + slot, 128);          // every row is staged, and nobody still reads v_hi rows of this tile
       if (issuer) {
-        ptx::tma_store_4d(&tm_hi, Qs + m * kTile, h * kHd, j, m * 128, b);
-        ptx::tma_store_4d(&tm_second, Stg, h * kHd, j, m * 128, b);
-        if (FMT != FMT_SPLIT16) ptx::tma_store_4d(&tm_second, Stg + 8192, kC + h * kHd, j, m * 128, b);
+        const CUtensorMap* mh = tail ? &tm_hi_tail : &tm_hi;
+        const CUtensorMap* ms = tail ? &tm_second_tail : &tm_second;
+        ptx::tma_store_4d(mh, Qs + m * kTile, h * kHd, j, m * 128, b);
+        ptx::tma_store_4d(ms, Stg, h * kHd, j, m * 128, b);
+        if (FMT != FMT_SPLIT16) ptx::tma_store_4d(ms, Stg + 8192, kC + h * kHd, j, m * 128, b);
         ptx::bulk_commit();
         ptx::bulk_wait_read_all();           // Stg / Q_m have been read: the tile has left shared memory
         ptx::mbar_arrive(&bars->stage_free[stage]);
@@ -478,9 +494,10 @@ int encode_tokens_2d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int e
   return encode_rank4(out, base, dt, dims, strides, box, swz);
 }
 
+inline int tc_stages(int n_mt) { return n_mt == 1 ? 4 : 2; }
 template <int NSLOT>
 int tc_smem_bytes(int n_mt) {
-  return NSLOT * (3 * n_mt + 1) * kTile + static_cast<int>(sizeof(TcBars<NSLOT>)) + 1024 /*alignment slack*/;
+  return (tc_stages(n_mt) * 3 * n_mt + NSLOT) * kTile + static_cast<int>(sizeof(TcBars<NSLOT>)) + 1024 /*alignment slack*/;
 }
 
 }  // namespace
@@ -501,7 +518,16 @@ int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half*
 }
 
 int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt,
-                              int64_t tokens) {
+                              int64_t tokens, int F) {
+  const int tail_rows = (F % 7) ? (F % 7) * 17 : kSpatialRows;
+  if (encode_tokens_2d(&maps->o_hi_tail, o_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, tokens, tail_rows,
+                       CU_TENSOR_MAP_SWIZZLE_128B))
+    return -1;
+  if (fmt == FMT_F8C ? encode_tokens_2d(&maps->o_second_tail, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 2 * kC, tokens,
+                                        tail_rows, CU_TENSOR_MAP_SWIZZLE_NONE)
+                     : encode_tokens_2d(&maps->o_second_tail, o_second, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, tokens,
+                                        tail_rows, CU_TENSOR_MAP_SWIZZLE_128B))
+    return -1;
   // loads: 128-row boxes (rows beyond the 119 of a unit are read but masked); stores: 119-row boxes
   if (encode_tokens_2d(&maps->qkv, const_cast<__half*>(qkv), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kQkvRow, tokens, 128,
                        CU_TENSOR_MAP_SWIZZLE_128B))
@@ -541,8 +567,8 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, i
   const int grid = n_units < num_sms ? n_units : num_sms;
   const int smem = tc_smem_bytes<2>(n_mt);
 #define D3D_LAUNCH_TC(FMT_, NCH_)                                                                               \
-  attn_temporal_tc_kernel<FMT_, 2, NCH_, false><<<grid, kTcThreads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, qkv, F, J, \
-                                                                  n_units, n_mt, NKp)
+  attn_temporal_tc_kernel<FMT_, 2, NCH_, false><<<grid, kTcThreads, smem, st>>>(                      \
+      maps.qkv, maps.o_hi, maps.o_second, maps.o_hi, maps.o_second, F, J, n_units, n_mt, NKp, tc_stages(n_mt))
   if (fmt == FMT_F8C) {
     if (nch == 8) D3D_LAUNCH_TC(FMT_F8C, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_F8C, 3); else D3D_LAUNCH_TC(FMT_F8C, 0);
   } else {
@@ -552,20 +578,21 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, i
   return cudaGetLastError();
 }
 
-// Spatial mode (J == 17): units of 7 frames x one head
-cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int64_t tokens, int num_sms, cudaStream_t st) {
-  if (tokens <= 0) return cudaSuccess;
-  const int64_t groups = (tokens + kSpatialRows - 1) / kSpatialRows;
-  if (groups * kHeads > 0x7fffffff) return cudaErrorInvalidValue;
-  const int n_units = static_cast<int>(groups) * kHeads;
+// Spatial mode (J == 17): units of (clip, 7-frame group, head)
+cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int B, int F, int num_sms, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  const int G = (F + 6) / 7;
+  const int64_t units64 = static_cast<int64_t>(B) * G * kHeads;
+  if (units64 > 0x7fffffff) return cudaErrorInvalidValue;
+  const int n_units = static_cast<int>(units64);
   const int grid = n_units < num_sms ? n_units : num_sms;
   const int smem = tc_smem_bytes<2>(1);
   if (fmt == FMT_F8C)
-    attn_temporal_tc_kernel<FMT_F8C, 2, 0, true><<<grid, kTcThreads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, nullptr,
-                                                                               kSpatialRows, 17, n_units, 1, 128);
+    attn_temporal_tc_kernel<FMT_F8C, 2, 0, true><<<grid, kTcThreads, smem, st>>>(
+        maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, F, G, n_units, 1, 128, tc_stages(1));
   else
-    attn_temporal_tc_kernel<FMT_SPLIT16, 2, 0, true><<<grid, kTcThreads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second,
-                                                                                   nullptr, kSpatialRows, 17, n_units, 1, 128);
+    attn_temporal_tc_kernel<FMT_SPLIT16, 2, 0, true><<<grid, kTcThreads, smem, st>>>(
+        maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, F, G, n_units, 1, 128, tc_stages(1));
   return cudaGetLastError();
 }
 

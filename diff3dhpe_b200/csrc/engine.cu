@@ -259,7 +259,7 @@ int run_attention(d3d_handle* h, const __half* qkv, __half* o_hi, __half* o_lo, 
     } else if (mode == D3D_ATTN_DEFAULT && h->have_attn_sp && qkv == h->QKV && env_int("D3D_ATTN_TC_SPATIAL", 1)) {
       if (!o_f32 && (o_hi != h->ATT.hi || o_lo != h->ATT.lo)) return fail(h, -2, "attention output must be the ATT operand");
       const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
-      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial_tc(h->attn_sp, h->fmt, T, h->num_sms, st));
+      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial_tc(h->attn_sp, h->fmt, B, h->F, h->num_sms, st));
       if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, o_f32, T, kC, h->fmt, st));
     } else {
       KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial(qkv, o_hi, o_lo, o_f32, h->fmt, static_cast<int64_t>(B) * h->F, h->J, st));
@@ -483,7 +483,7 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
     if ((r = alloc_operand(h, &h->ATT, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->H, h->tok_cap, kHidden))) return r;
     if (h->J == 17) {
-      if (make_attn_tc_maps_spatial(&h->attn_sp, h->QKV, h->ATT.hi, h->ATT.lo, h->fmt, h->tok_cap))
+      if (make_attn_tc_maps_spatial(&h->attn_sp, h->QKV, h->ATT.hi, h->ATT.lo, h->fmt, h->tok_cap, h->F))
         return fail(h, -20, "cuTensorMapEncodeTiled failed for the spatial-attention maps");
       h->have_attn_sp = true;
     }

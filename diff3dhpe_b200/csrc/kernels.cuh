@@ -113,12 +113,14 @@ cudaError_t launch_attn_temporal_mma(const __half* qkv, __half* o_hi, __half* o_
 // qkv array and one output operand (hi + second array in format fmt) of up to max_clips clips.
 struct AttnTcMaps {
   CUtensorMap qkv, o_hi, o_second;
+  CUtensorMap o_hi_tail, o_second_tail;   // spatial mode: store boxes of the last (shorter) frame group of a clip
 };
 int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int F, int J,
                       int64_t max_clips);
-// spatial mode of the same kernel (J == 17): units of 7 frames (119 consecutive tokens) x one head, block-diagonal mask
-int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int64_t tokens);
-cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int64_t tokens, int num_sms, cudaStream_t st);
+// spatial mode of the same kernel (J == 17): units of (clip, 7 frames = 119 consecutive tokens, head), block-diagonal mask
+int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int64_t tokens,
+                              int F);
+cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int B, int F, int num_sms, cudaStream_t st);
 cudaError_t configure_attention_tc();
 cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
                                     cudaStream_t st);
