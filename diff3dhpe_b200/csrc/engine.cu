@@ -238,6 +238,7 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   p.hint_a = env_int("D3D_GEMM_HINT_A", 1);
   p.hint_b = env_int("D3D_GEMM_HINT_B", 1);
   p.stream_out = env_int("D3D_GEMM_STREAM_OUT", 1);
+  p.n_inner = env_int("D3D_GEMM_N_INNER", 0);
   if (mode == D3D_GEMM_SIMT_FP32 || mode == D3D_GEMM_SIMT_F8C) {
     KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, mode_fmt(mode), st));
   } else {

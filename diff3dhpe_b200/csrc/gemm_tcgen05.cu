@@ -129,6 +129,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int n_tiles = n_tiles_m * n_tiles_n;
   const int n_kb = p.K / BK;
   const int n_steps = PASSES == 2 ? 2 * n_kb : n_kb;       // ring stages consumed per tile
+  // q-th tile of this unit (linear index m * n_tiles_n + n), -1 when the unit is done.
+  //   n_inner: the unit walks ALL n-tiles of one m-tile before moving to its next m-tile, so the A tile is re-read
+  //            by the same SMs back to back (L2 hits on the same die) instead of by up to n_tiles_n other CTA pairs;
+  //   else   : tiles are dealt round-robin, n fastest (neighbouring units share the A tile at the same time).
+  auto tile_of = [&](int q) -> int {
+    if (p.n_inner) {
+      const int mt = unit + (q / n_tiles_n) * n_units;
+      return mt < n_tiles_m ? mt * n_tiles_n + q % n_tiles_n : -1;
+    }
+    const int t = unit + q * n_units;
+    return t < n_tiles ? t : -1;
+  };
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tm_a_hi);
@@ -169,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const uint64_t pol_a = ptx::make_l2_policy(p.hint_a), pol_b = ptx::make_l2_policy(p.hint_b);
-      for (int tile = unit; tile < n_tiles; tile += n_units) {
+      for (int q_ = 0, tile; (tile = tile_of(q_)) >= 0; ++q_) {
         const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
         const int n0 = (tile % n_tiles_n) * BN + static_cast<int>(rank) * C::kBRows;
         for (int kb = 0; kb < n_steps; ++kb) {
@@ -246,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = unit; tile < n_tiles; tile += n_units) {
+      for (int q_ = 0, tile; (tile = tile_of(q_)) >= 0; ++q_) {
         ptx::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -327,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int rsub = lane >> 3, gsub = lane & 7;      // coalesced mapping: instruction j covers rows 4j + rsub
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = unit; tile < n_tiles; tile += n_units) {
+    for (int q_ = 0, tile; (tile = tile_of(q_)) >= 0; ++q_) {
       const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
       const int n0 = (tile % n_tiles_n) * BN;
       const int row_w = m0 + q * 32;                    // first row of this warp
