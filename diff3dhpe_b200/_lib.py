@@ -43,6 +43,9 @@ PROTOTYPES = {
                                        C.c_void_p]),
     "d3d_tta_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                 C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+    "d3d_window_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "d3d_window_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "d3d_mpjpe_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_void_p]),
     "d3d_launch_count": (C.c_int64, [C.c_void_p]),

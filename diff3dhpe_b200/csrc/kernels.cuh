@@ -103,6 +103,12 @@ cudaError_t launch_tta_merge(const float* y, const float* yf, const int32_t* per
 cudaError_t launch_mpjpe(const float* pred, const float* gt, const uint8_t* mask, int64_t n_frames, int J,
                          double* acc, cudaStream_t st);
 
+// ------------------------------------------------------------------ windowing (packed sequences <-> F-frame windows)
+cudaError_t launch_window_gather(const float* seq2d, const int64_t* start, const int32_t* perm /*[J] device*/, float* x2d,
+                                 float* x2d_flip /*or null*/, int64_t n_win, int F, int J, cudaStream_t st);
+cudaError_t launch_window_scatter(const float* pred, const int64_t* start, const int32_t* first_valid, float* seq3d,
+                                  int64_t n_win, int F, int J, cudaStream_t st);
+
 // ------------------------------------------------------------------ attention
 // qkv: packed fp16 [T, 2048] rows q | k | v_hi | v_lo (EPI_QKV16).  Output [T,512]: GEMM A operand (o_hi + second
 // array in format fmt, operand.cuh) or fp32.

@@ -154,6 +154,35 @@ class Engine:
                                           y.shape[0] * y.shape[1], self._stream()), self.h, "d3d_tta_merge")
         return out
 
+    def window_gather(self, seq2d: torch.Tensor, win_start: torch.Tensor, joints_left=None, joints_right=None,
+                      flip: bool = True):
+        """Packed sequences [N, J, 2] + first packed frame of every window -> (x2d [n_win, F, J, 2], flipped copy or
+        None), the two inputs of the reference's evaluate() (nosiy_generators.py:264-276), built on the device."""
+        _check_dev(seq2d, self.device, name="seq2d")
+        _check_dev(win_start, self.device, dtype=torch.int64, name="win_start")
+        n_win = win_start.numel()
+        if n_win and int(win_start.max()) + self.F > seq2d.shape[0]:
+            raise ValueError("a window reaches past the end of the packed sequences")
+        x = torch.empty((n_win, self.F, self.J, 2), device=self.device, dtype=torch.float32)
+        xf = torch.empty_like(x) if flip else None
+        n = len(joints_left) if (flip and joints_left is not None) else 0
+        la = (C.c_int32 * max(n, 1))(*(joints_left or [0])[:max(n, 1)])
+        ra = (C.c_int32 * max(n, 1))(*(joints_right or [0])[:max(n, 1)])
+        _lib.check(self.lib.d3d_window_gather(self.h, _ptr(seq2d), _ptr(win_start), n_win, la, ra, n, _ptr(x), _ptr(xf),
+                                              self._stream()), self.h, "d3d_window_gather")
+        return x, xf
+
+    def window_scatter(self, pred: torch.Tensor, win_start: torch.Tensor, first_valid: torch.Tensor, out: torch.Tensor):
+        """pred [n_win, F, J, 3] -> out [N, J, 3] in packed frame order; frames below first_valid[w] are skipped."""
+        n_win = win_start.numel()
+        _check_dev(pred, self.device, (n_win, self.F, self.J, 3), name="pred")
+        _check_dev(win_start, self.device, (n_win,), torch.int64, "win_start")
+        _check_dev(first_valid, self.device, (n_win,), torch.int32, "first_valid")
+        _check_dev(out, self.device, name="out")
+        _lib.check(self.lib.d3d_window_scatter(self.h, _ptr(pred), _ptr(win_start), _ptr(first_valid), n_win, _ptr(out),
+                                               self._stream()), self.h, "d3d_window_scatter")
+        return out
+
     def mpjpe_accumulate(self, pred: torch.Tensor, gt: torch.Tensor, acc: torch.Tensor,
                          frame_mask: Optional[torch.Tensor] = None):
         """acc: fp64[2] on the device: (sum of joint errors, joint count)."""

@@ -40,6 +40,22 @@ def window_starts(n_frames: int, F: int) -> Sequence[Tuple[int, int]]:
     return out
 
 
+def plan_windows(seq_lengths: Sequence[int], F: int):
+    """Window plan of a set of sequences packed back to back: (win_start int64 [n_win] = first PACKED frame of every
+    window, first_valid int32 [n_win], seq_id int32 [n_win]) following `window_starts` per sequence, in the
+    generator's order (sequence by sequence, windows in time order; nosiy_generators.py:27-48)."""
+    starts, valid, sid = [], [], []
+    base = 0
+    for s, n in enumerate(seq_lengths):
+        for st, fv in window_starts(int(n), F):
+            starts.append(base + st)
+            valid.append(fv)
+            sid.append(s)
+        base += int(n)
+    return (torch.tensor(starts, dtype=torch.int64), torch.tensor(valid, dtype=torch.int32),
+            torch.tensor(sid, dtype=torch.int32))
+
+
 class DeviceSampler:
     """Adapter: (x2d [n,F,J,2] device, y_T, step_noise) -> y0, running GaussianDiffusion.ddim_sample_loop."""
 
@@ -89,6 +105,38 @@ def evaluate_shard(sampler, x2d: torch.Tensor, gt: Optional[torch.Tensor], noise
             mb = None if frame_mask is None else frame_mask[s:e].to(device).reshape(-1).contiguous()
             sampler.mpjpe(out.contiguous(), gb.contiguous(), acc, mb)
     return {"pred": pred, "acc": acc}
+
+
+def evaluate_sequences(sampler, seq2d: torch.Tensor, gt3d: Optional[torch.Tensor], seq_lengths: Sequence[int],
+                       noise_fn: Callable, *, device, F: int, batch_clips: int = 256,
+                       left=synthetic.H36M_JOINTS_LEFT, right=synthetic.H36M_JOINTS_RIGHT, scale: float = 1.0,
+                       window_offset: int = 0) -> Dict[str, torch.Tensor]:
+    """The evaluate() inner loop from RAW packed sequences: seq2d [N, J, 2] / gt3d [N, J, 3] are HOST
+    tensors holding this rank's sequences back to back.  The F-frame windows and their flipped copies
+    (nosiy_generators.py:27-48, 264-276) are built on the device, sampled with flip-TTA, merged (RUN:583-588) and written
+    back into packed frame order with the overlap of each back-shifted last window masked (RUN:589-596).
+    Returns {'pred': [N, J, 3] (device), 'acc': fp64[2] (device), 'n_windows': int}."""
+    ws, fv, _ = plan_windows(seq_lengths, F)
+    n_win = ws.numel()
+    N, J, _ = seq2d.shape
+    eng = sampler.diffusion.model.engine(2 * min(batch_clips, n_win))
+    seq_d = seq2d.to(device, non_blocking=True)
+    ws_d, fv_d = ws.to(device), fv.to(device)
+    out = torch.zeros((N, J, 3), device=device, dtype=torch.float32)
+    for s in range(0, n_win, batch_clips):
+        e = min(n_win, s + batch_clips)
+        ids = torch.arange(window_offset + s, window_offset + e)
+        xb, xf = eng.window_gather(seq_d, ws_d[s:e].contiguous(), left, right)
+        y_T, sn = noise_fn(ids, False)
+        yf_T, snf = noise_fn(ids, True)
+        y_all = sampler(torch.cat([xb, xf]), torch.cat([y_T, yf_T]), None if sn is None else torch.cat([sn, snf], dim=1))
+        b = e - s
+        merged = sampler.merge(y_all[:b].contiguous(), y_all[b:].contiguous(), left, right, scale)
+        eng.window_scatter(merged, ws_d[s:e].contiguous(), fv_d[s:e].contiguous(), out)
+    acc = torch.zeros(2, device=device, dtype=torch.float64)
+    if gt3d is not None:
+        sampler.mpjpe(out, gt3d.to(device, non_blocking=True).contiguous(), acc, None)
+    return {"pred": out, "acc": acc, "n_windows": n_win}
 
 
 def gather_results(local_pred: torch.Tensor, acc: torch.Tensor, n_total: int, group=None):

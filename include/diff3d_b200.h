@@ -127,6 +127,20 @@ D3D_API int d3d_tta_merge(d3d_handle* h, const float* y_dev, const float* y_flip
                   const int32_t* joints_right, int32_t n_lr, float scale, float* out_dev, int64_t n_frames,
                   void* stream);
 
+/* Windowing on the device (common/nosiy_generators.py:27-48, 264-276; "next" row N3 of SURVEY.md 8f).
+ * seq2d_dev: packed sequences [n_frames_total, J, 2]; win_start_dev[w] = first packed frame of window w.  Writes
+ * x2d_out_dev [n_win, F, J, 2] and, when x2d_flip_out_dev != NULL, the horizontally flipped copy (x negated, joints
+ * left[i] <-> right[i] swapped) that the reference's generator hands to evaluate() as inputs_2d_flip. */
+D3D_API int d3d_window_gather(d3d_handle* h, const float* seq2d_dev, const int64_t* win_start_dev, int64_t n_win,
+                      const int32_t* joints_left, const int32_t* joints_right, int32_t n_lr, float* x2d_out_dev,
+                      float* x2d_flip_out_dev, void* stream);
+
+/* The inverse: writes pred_dev [n_win, F, J, 3] into packed per-sequence frame order seq3d_out_dev
+ * [n_frames_total, J, 3], skipping the first first_valid_dev[w] frames of window w (target_mask of the back-shifted
+ * last window of a sequence, nosiy_generators.py:264-271, applied by RUN:589-596). */
+D3D_API int d3d_window_scatter(d3d_handle* h, const float* pred_dev, const int64_t* win_start_dev,
+                       const int32_t* first_valid_dev, int64_t n_win, float* seq3d_out_dev, void* stream);
+
 /* Replaces mpjpe (LOSS:15-27) + the N-weighted accumulation of RUN:602-606: adds sum_j ||pred-gt||_2 over the
  * frames whose mask byte is non-zero (mask NULL = all) to acc_dev[0] and the joint count to acc_dev[1]
  * (two fp64 on the device; MPJPE = acc[0]/acc[1]). */

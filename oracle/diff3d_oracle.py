@@ -11,6 +11,7 @@ algorithm, not an import of it.  Citations are ``file:line`` into the reference 
   DIFF  = common/conditional_diffusion_ddim_normal_directPredict_variableLoss_both_crossFrames.py
   RUN   = run_conditionalDiffusionDDIM3dhpeNormalDirectPredictVariableLoss.py
   LOSS  = common/loss.py
+  GEN   = common/nosiy_generators.py   (sic)
 
 Parity pinning: the reference ships no tests or golden vectors for this path, so the
 oracle is pinned against the *imported, unmodified reference* run in the build container:
@@ -267,3 +268,34 @@ def sample_tta(sd, x2d, noise_pair, flip_noise_pair, **kw) -> Tensor:
     y = ddim_sample_loop(sd, x2d, *noise_pair, **kw)
     yf = ddim_sample_loop(sd, flip_2d(x2d), *flip_noise_pair, **kw)
     return tta_merge(y, yf, scale)
+
+
+# ----------------------------------------------------------------------------------------------- windowing (N3)
+def chunk_windows(n_seq_frame: int, chunk_length: int) -> Tuple[List[int], List[int]]:
+    """Window bounds of one sequence for the seq2seq (`out_all`) generator, GEN:27-40: non-overlapping chunks, the
+    last one shifted back to end at the sequence end.  Returns (start_index_chunk, start_index_chunk_target); the
+    first `start - start_target` frames of a window are masked out of the targets (GEN:264-271)."""
+    n_chunks = (n_seq_frame + chunk_length - 1) // chunk_length
+    bounds = [c * chunk_length for c in range(n_chunks)]
+    start_last = n_seq_frame - chunk_length
+    target_offset = start_last - bounds[-1]
+    start_chunk = bounds[:-1] + [start_last]
+    start_target = bounds[:-1] + [start_last + target_offset]
+    return start_chunk, start_target
+
+
+def window_batch(seq_2d: Tensor, start: int, chunk_length: int, start_target: int, flip: bool,
+                 kps_left=H36M_JOINTS_LEFT, kps_right=H36M_JOINTS_RIGHT) -> Tuple[Tensor, Tensor]:
+    """One window of the generator (GEN:247-276, pad = causal_shift = 0, no edge padding: start >= 0): the 2D slice
+    (flipped: x negated, left/right keypoints swapped) and its target_mask."""
+    assert start >= 0 and start + chunk_length <= seq_2d.shape[0]
+    batch_2d = seq_2d[start:start + chunk_length].clone()
+    target_mask = torch.ones(chunk_length, dtype=torch.bool)
+    n_unused = start - start_target
+    assert n_unused >= 0
+    if n_unused > 0:
+        target_mask[:n_unused] = False
+    if flip:
+        batch_2d[:, :, 0] *= -1
+        batch_2d[:, list(kps_left) + list(kps_right)] = batch_2d[:, list(kps_right) + list(kps_left)]
+    return batch_2d, target_mask

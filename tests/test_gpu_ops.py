@@ -141,6 +141,48 @@ def test_attention_tcgen05_operand(F, B, spatial, gemm_mode):
         assert (lo8.abs() <= 2 ** -11 * hi.abs() * 1.13 + 1e-7).all()
 
 
+def test_window_gather_scatter_golden(golden):
+    """Device windowing (d3d_window_gather / d3d_window_scatter) against the reference generator's windows, bit for
+    bit: 2D slices, flipped copies, and the masked write-back of a prediction tensor into packed frame order."""
+    from diff3dhpe_b200 import evaluate
+    g = golden("windows_f9")
+    F, lens = int(g["F"]), g["lens"].tolist()
+    eng = Engine(F, max_clips=2)
+    ws, fv, _ = evaluate.plan_windows(lens, F)
+    x, xf = eng.window_gather(torch.from_numpy(g["seq2d"]).cuda(), ws.cuda(), synthetic.H36M_JOINTS_LEFT,
+                              synthetic.H36M_JOINTS_RIGHT)
+    assert np.array_equal(x.cpu().numpy(), g["x2d"]) and np.array_equal(xf.cpu().numpy(), g["x2d_flip"])
+    pred = _rand((ws.numel(), F, 17, 3), 90)
+    out = torch.full((sum(lens), 17, 3), float("nan"), device="cuda")
+    eng.window_scatter(pred.cuda(), ws.cuda(), fv.cuda(), out)
+    ref = torch.full((sum(lens), 17, 3), float("nan"))
+    for w in range(ws.numel()):
+        m = torch.from_numpy(g["mask"][w])
+        ref[int(ws[w]):int(ws[w]) + F][m] = pred[w][m]
+    eng.close()
+    assert not torch.isnan(ref).any() and torch.equal(out.cpu(), ref)
+
+
+def test_window_gather_scatter_large():
+    """240 sequences x 2250 frames (the cfg5 sweep), F = 243: gather equals torch indexing, scatter(gather(x)) is the
+    identity on every frame (each frame is owned by exactly one window)."""
+    from diff3dhpe_b200 import evaluate
+    F, n_seq, n = 243, 24, 2250
+    eng = Engine(F, max_clips=1)
+    ws, fv, _ = evaluate.plan_windows([n] * n_seq, F)
+    seq = _rand((n_seq * n, 17, 2), 91).cuda()
+    x, xf = eng.window_gather(seq, ws.cuda(), synthetic.H36M_JOINTS_LEFT, synthetic.H36M_JOINTS_RIGHT)
+    idx = (ws.cuda()[:, None] + torch.arange(F, device="cuda")[None]).reshape(-1)
+    ref = seq[idx].view(-1, F, 17, 2)
+    assert torch.equal(x, ref) and torch.equal(xf, synthetic.flip_2d(ref))
+    seq3 = _rand((n_seq * n, 17, 3), 92).cuda()
+    pred = seq3[idx].view(-1, F, 17, 3).contiguous()
+    out = torch.zeros_like(seq3)
+    eng.window_scatter(pred, ws.cuda(), fv.cuda(), out)
+    eng.close()
+    assert torch.equal(out, seq3)
+
+
 def test_time_table_golden(golden):
     g = golden("denoise_f27_b3")
     eng = Engine(27, max_clips=3)

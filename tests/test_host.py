@@ -78,6 +78,26 @@ def test_shard_range_partitions():
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
 
 
+def test_plan_windows_matches_generator_rule(golden):
+    """evaluate.plan_windows (host side of the device windowing) against the oracle restatement of the generator rule
+    for every length up to 5 windows, and against the reference generator's golden windows."""
+    for F in (1, 9, 27):
+        for n in range(F, 5 * F + 2):
+            starts, targets = oracle.chunk_windows(n, F)
+            ws, fv, sid = evaluate.plan_windows([n], F)
+            assert ws.tolist() == starts and fv.tolist() == [s - t for s, t in zip(starts, targets)]
+            covered = torch.zeros(n, dtype=torch.int32)             # every frame predicted exactly once
+            for s, v in zip(ws.tolist(), fv.tolist()):
+                covered[s + v:s + F] += 1
+            assert bool((covered == 1).all())
+    g = golden("windows_f9")
+    ws, fv, sid = evaluate.plan_windows(g["lens"].tolist(), int(g["F"]))
+    assert ws.tolist() == g["win_start"].tolist() and sid.tolist() == g["seq_id"].tolist()
+    assert fv.tolist() == [int((~m).sum()) for m in g["mask"]]
+    with pytest.raises(ValueError):
+        evaluate.plan_windows([5], 9)
+
+
 def test_window_rule():
     """ChunkedGenerator windowing (nosiy_generators.py:27-48): 2250 frames, F=243 -> 10 windows, last shifted back."""
     w = evaluate.window_starts(2250, 243)

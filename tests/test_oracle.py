@@ -113,3 +113,23 @@ def test_flip_is_involution_and_uses_h36m_lists():
     assert torch.equal(oracle.flip_2d(oracle.flip_2d(x)), x)
     assert oracle.H36M_JOINTS_LEFT == [4, 5, 6, 11, 12, 13] and oracle.H36M_JOINTS_RIGHT == [1, 2, 3, 14, 15, 16]
     assert torch.equal(oracle.flip_2d(x), synthetic.flip_2d(x))
+
+
+def test_windowing_golden(golden):
+    """Window bounds, 2D slices, flipped copies and target masks against the reference ChunkedGenerator's own output
+    (tools/make_golden_windows.py): three sequences of 9 / 20 / 31 frames, F = 9."""
+    g = golden("windows_f9")
+    F, lens = int(g["F"]), g["lens"].tolist()
+    seq = torch.from_numpy(g["seq2d"])
+    w, base = 0, 0
+    for n in lens:
+        starts, targets = oracle.chunk_windows(n, F)
+        for st, tg in zip(starts, targets):
+            assert base + st == int(g["win_start"][w])
+            x, m = oracle.window_batch(seq[base:base + n], st, F, tg, False)
+            xf, _ = oracle.window_batch(seq[base:base + n], st, F, tg, True)
+            assert np.array_equal(x.numpy(), g["x2d"][w]) and np.array_equal(xf.numpy(), g["x2d_flip"][w])
+            assert np.array_equal(m.numpy(), g["mask"][w])
+            w += 1
+        base += n
+    assert w == g["x2d"].shape[0]

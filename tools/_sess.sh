@@ -1,20 +1,15 @@
 mkdir -p gpurun_out
-T=r01q
-timeout 200 python -m pytest tests/test_gpu_ops.py -k "linear or gelu or matches" -x -q > gpurun_out/${T}_pytest_gemm_default.log 2>&1; tail -2 gpurun_out/${T}_pytest_gemm_default.log
-D3D_GEMM_N_INNER=1 timeout 400 python -m pytest tests/test_gpu_ops.py -k "linear or gelu or matches" -x -q > gpurun_out/${T}_pytest_gemm_ninner.log 2>&1; tail -2 gpurun_out/${T}_pytest_gemm_ninner.log
-run_bench() {  # name, env...
-  name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err
-  python - <<PY
+T=r01r
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${T}_pytest.log
+timeout 400 python bench.py --steps 3 --warmup 3 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"
+python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/${T}_bench_$name.json"))
-    print("$name", round(d["value"]), d["ms_per_step"], d["clocks"]["sm_mhz"], d["roofline"]["per_class_ms"])
+    d=json.load(open("gpurun_out/${T}_bench.json"))
+    print(round(d["value"]), d["ms_per_step"], round(d["e2e"]["value"]), d["clocks"], d["roofline"]["per_class_ms"], d["roofline"]["frac"], d["cpu_baseline"])
 except Exception as e:
-    print("bench $name failed", e)
+    print("bench failed", e)
 PY
-}
-run_bench ninner1 D3D_GEMM_N_INNER=1
-run_bench ninner0 D3D_GEMM_N_INNER=0
-D3D_GEMM_N_INNER=1 timeout 400 ncu --set full --clock-control none -k regex:gemm_tc -s 40 -c 4 -o gpurun_out/${T}_full_gemm_ninner1 -f python bench.py --steps 1 --warmup 3 --clips 128 --no-cpu-baseline > gpurun_out/${T}_full_gemm_ninner1.log 2>&1
-echo "ncu rc=$?"
+timeout 600 python tools/run_configs.py cfg2 cfg4 > gpurun_out/${T}_configs.jsonl 2> gpurun_out/${T}_configs.err; echo "configs rc=$?"; cut -c1-250 gpurun_out/${T}_configs.jsonl
+timeout 400 python tools/run_configs.py cfg5 --raw-sequences --cfg5-sequences 48 > gpurun_out/${T}_cfg5_raw48.jsonl 2> gpurun_out/${T}_cfg5_raw48.err; echo "cfg5 raw rc=$?"; cut -c1-400 gpurun_out/${T}_cfg5_raw48.jsonl
+timeout 400 python tools/run_configs.py cfg5 --cfg5-sequences 48 > gpurun_out/${T}_cfg5_48.jsonl 2> gpurun_out/${T}_cfg5_48.err; echo "cfg5 rc=$?"; cut -c1-400 gpurun_out/${T}_cfg5_48.jsonl

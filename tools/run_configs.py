@@ -115,7 +115,51 @@ def cfg4(args, world, rank, dev):
         model._engine.close()
 
 
+def cfg5_raw(args, world, rank, dev):
+    """cfg5 from RAW packed sequences: windowing, flipping and the masked write-back run on the device (N3); sequences
+    (not windows) are sharded contiguously over the ranks."""
+    F, S = 243, 9
+    n_seq, seq_len = args.cfg5_sequences, 2250
+    assert n_seq % world == 0, "raw-sequence mode shards whole sequences: --cfg5-sequences must divide by the world size"
+    start, count = evaluate.shard_range(n_seq, rank, world)
+    g = torch.Generator().manual_seed(2000 + rank)
+    seq2d = (0.3 * torch.randn(count * seq_len, J, 2, generator=g)).clamp_(-1, 1).pin_memory()
+    gt = 0.3 * torch.randn(count * seq_len, J, 3, generator=g)
+    gt = (gt - gt[:, :1]).pin_memory()
+    model = synthetic.make_model(F).to(dev)
+    model.max_clips_hint = 2 * args.batch
+    diff = synthetic.make_diffusion(model, sampling_timesteps=S).to(dev).eval()
+    sampler = evaluate.DeviceSampler(diff)
+
+    def noise_fn(ids, flip):
+        return diff.draw_noise([len(ids), F, J, 3], dev)
+
+    def once():
+        res = evaluate.evaluate_sequences(sampler, seq2d, gt, [seq_len] * count, noise_fn, device=dev, F=F,
+                                          batch_clips=args.batch)
+        pred, mp = evaluate.gather_results(res["pred"], res["acc"], n_seq * seq_len)      # gathered in units of frames
+        return pred, mp, res["n_windows"]
+
+    pred, mp, n_win = once()
+    sync(world, dev)
+    t0 = time.perf_counter()
+    pred, mp, n_win = once()
+    sync(world, dev)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    frames = n_seq * seq_len
+    emit(rank, config="cfg5_raw_sequences", F=F, sequences=n_seq, frames=frames, windows_per_rank=n_win, S=S, tta=True,
+         n_gpus=world, seconds=dt, pose_frames_per_s=frames / dt, mpjpe_vs_synthetic_gt=mp,
+         gathered_shape=list(pred.shape), windowing="device (d3d_window_gather / d3d_window_scatter)")
+    model._engine.close()
+
+
 def cfg5(args, world, rank, dev):
+    if args.raw_sequences:
+        return cfg5_raw(args, world, rank, dev)
     F, S = 243, 9
     n_seq, seq_len = args.cfg5_sequences, 2250
     wins = evaluate.window_starts(seq_len, F)                      # 10 windows per sequence, last one back-shifted
@@ -149,6 +193,8 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--batch", type=int, default=256, help="clips per sampler batch for cfg5 (x2 with the flip copies)")
     ap.add_argument("--cfg5-sequences", type=int, default=240)
+    ap.add_argument("--raw-sequences", action="store_true",
+                    help="cfg5 from raw packed sequences: windowing / flipping / write-back on the device")
     args = ap.parse_args()
     world, rank, dev = setup()
     for c in args.configs:
