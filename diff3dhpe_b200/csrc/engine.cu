@@ -220,10 +220,29 @@ int pick_bn(const d3d_handle* h, int64_t M, int N) {
   return tiles256 >= 2 * h->num_sms ? 256 : 128;
 }
 
+struct LnFuse {           // LayerNorm fused behind an EPI_F32 GEMM (EPI_F32_LN): parameters and destination operand
+  const float* gamma;
+  const float* beta;
+  float eps;
+  OperandBuf* dst;
+};
+
+// proj + norm2 in one kernel: CTA-pair F8C tcgen05 GEMM with the n-inner tile order only
+bool can_fuse_ln(const d3d_handle* h, int mode) {
+  return mode == D3D_GEMM_TC_F8C && h->fmt == FMT_F8C && pick_cg(kC) == 2 && env_int("D3D_GEMM_N_INNER", 1) == 1 &&
+         env_int("D3D_GEMM_FUSE_LN", 1) == 1;
+}
+
 // out = epilogue(Aop . W^T + bias)
 int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int epi, const float* residual,
-             float* out_f32, __half* out_hi, __half* out_lo, __half* out_qkv, int mode, cudaStream_t st) {
-  GemmParams p;
+             float* out_f32, __half* out_hi, __half* out_lo, __half* out_qkv, int mode, cudaStream_t st,
+             const LnFuse* ln = nullptr) {
+  GemmParams p{};
+  if (ln) {
+    epi = EPI_F32_LN;
+    p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_eps = ln->eps;
+    p.ln_hi = ln->dst->hi; p.ln_second = ln->dst->lo;
+  }
   p.M = static_cast<int>(M);
   p.N = w.N;
   p.K = w.K;
@@ -330,8 +349,13 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
     const bool spatial = (b % 2) == 0;
     if ((r = run_gemm(h, h->A, k.qkv, T, EPI_QKV16, nullptr, nullptr, nullptr, nullptr, h->QKV, gm, st))) return r;
     if ((r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial, am, st))) return r;
-    if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
-    KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, h->fmt, T, st));
+    if (can_fuse_ln(h, gm)) {        // proj + residual + norm2 (MODEL:127-128) in one kernel
+      const LnFuse ln2{k.n2g, k.n2b, 1e-6f, &h->A};
+      if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st, &ln2))) return r;
+    } else {
+      if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
+      KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, h->fmt, T, st));
+    }
     if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, nullptr, gm, st))) return r;
     if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
     if (b + 1 < n_blocks) {
@@ -1004,6 +1028,30 @@ int d3d_op_linear(d3d_handle* h, const float* a, const float* w, const float* bi
   } else {
     if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, out, nullptr, nullptr, nullptr, gemm_mode, st))) return r;
   }
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int d3d_op_linear_ln(d3d_handle* h, const float* a, const float* w, const float* bias, const float* residual,
+                     const float* gamma, const float* beta, float eps, float* x_out, float* ln_out, int64_t M, int32_t K,
+                     void* stream) {
+  if (!h || !a || !w || !bias || !residual || !gamma || !beta || !x_out || !ln_out) return -1;
+  if (M < 1 || K % 64 != 0 || K < 64) return fail(h, -2, "need M>=1, K%64==0");
+  if (!can_fuse_ln(h, D3D_GEMM_TC_F8C)) return fail(h, -3, "the fused GEMM + LayerNorm epilogue needs the F8C CTA-pair kernel");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  OpLinearBufs b;
+  int r = prep_op_linear(h, b, M, kC, K, 1 /*allocates o_hi / o_lo [M, 512]*/, FMT_F8C);
+  if (r) return r;
+  b.w.bias = const_cast<float*>(bias);
+  KL(launch_split(a, b.a.hi, b.a.lo, M, K, FMT_F8C, 0, st));
+  KL(launch_split(w, b.w.hi, b.w.lo, kC, K, FMT_F8C, 1, st));
+  OperandBuf dst;
+  dst.hi = b.o_hi;
+  dst.lo = b.o_lo;
+  const LnFuse ln{gamma, beta, eps, &dst};
+  if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, x_out, nullptr, nullptr, nullptr, D3D_GEMM_TC_F8C, st, &ln))) return r;
+  KL(launch_merge(b.o_hi, b.o_lo, ln_out, M, kC, FMT_F8C, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -339,12 +339,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int rsub = lane >> 3, gsub = lane & 7;      // coalesced mapping: instruction j covers rows 4j + rsub
     int acc = 0;
     uint32_t acc_phase = 0;
+    // EPI_F32_LN: running (mean, M2) of this lane's row over the 128 columns this warp owns in each accumulator
+    float ln_mean[2] = {0.f, 0.f}, ln_m2[2] = {0.f, 0.f};
     for (int q_ = 0, tile; (tile = tile_of(q_)) >= 0; ++q_) {
       const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
       const int n0 = (tile % n_tiles_n) * BN;
       const int row_w = m0 + q * 32;                    // first row of this warp
       const int colbase = n0 + half * kColsW;
-      const bool has_res = EPI == EPI_F32 && p.residual != nullptr;
+      const bool has_res = (EPI == EPI_F32 || EPI == EPI_F32_LN) && p.residual != nullptr;
       float4 resv[8];
       auto load_res = [&](int ci) {                     // residual chunk ci, coalesced (row 4j + rsub, granule gsub)
 #pragma unroll
@@ -374,7 +376,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
         for (int v = 0; v < 8; ++v) bias4[v] = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + v);
         ptx::tmem_ld_wait();
-        if (EPI == EPI_F32) {
+        if (EPI == EPI_F32 || EPI == EPI_F32_LN) {
+          float csum = 0.f;
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
             const float4 b = bias4[v];
@@ -389,6 +392,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
             }
             *reinterpret_cast<float4*>(cell) = o;
+            if (EPI == EPI_F32_LN) {           // keep x for the statistics and the TMEM write-back
+              r[4 * v + 0] = __float_as_uint(o.x); r[4 * v + 1] = __float_as_uint(o.y);
+              r[4 * v + 2] = __float_as_uint(o.z); r[4 * v + 3] = __float_as_uint(o.w);
+              csum += (o.x + o.y) + (o.z + o.w);
+            }
+          }
+          if (EPI == EPI_F32_LN) {
+            // x goes back into the accumulator columns (pass 2 normalises it without re-reading the residual), and the
+            // chunk's (mean, M2) joins the lane's running pair (Chan et al.: no E[x^2] - mean^2 cancellation)
+            ptx::tmem_st_32x32(tmem_base + acc * BN + col0 + (static_cast<uint32_t>(q * 32) << 16), r);
+            const float cmean = csum * (1.0f / 32.0f);
+            float cm2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float d = __uint_as_float(r[e]) - cmean;
+              cm2 = fmaf(d, d, cm2);
+            }
+            const float cnt = 32.0f * ci, tot = cnt + 32.0f;
+            const float delta = cmean - ln_mean[acc];
+            if (ci == 0) { ln_mean[acc] = cmean; ln_m2[acc] = cm2; }
+            else {
+              ln_mean[acc] += delta * (32.0f / tot);
+              ln_m2[acc] += cm2 + delta * delta * (cnt * 32.0f / tot);
+            }
           }
           __syncwarp();
           uint4 vals[8];                       // all shared loads first, then all global stores (distinct registers)
@@ -483,11 +510,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
         __syncwarp();          // the buffer is rewritten by the next chunk
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[acc]), leader));
-        else ptx::mbar_arrive(&bars->tmem_empty[acc]);
+      if (EPI == EPI_F32_LN) {
+        // The two n-tiles of a row tile land in accumulators 0 and 1 back to back (n-inner order, N == 2 BN).  After
+        // pass 1 of the second one the full 512-wide rows are known: exchange the partial statistics with the warp that
+        // owns the other 128 columns of these rows, then pass 2 re-reads x from TMEM, normalises and writes the next
+        // GEMM's A operand.  Accumulator 0 is released only here (x lives in it between the passes).
+        if (acc == 1) {
+          ptx::tmem_st_wait();
+          *reinterpret_cast<float4*>(stg + lane * 16) = make_float4(ln_mean[0], ln_m2[0], ln_mean[1], ln_m2[1]);
+          ptx::bar_sync(1, EW * 32);
+          const float4 oth = *reinterpret_cast<const float4*>(staging + ((warp - 4) ^ 4) * 4096 + lane * 16);
+          ptx::bar_sync(1, EW * 32);                       // every partner row is read: the buffers may be reused
+          // Chan combination of equal-sized groups: mean = (a + b) / 2, M2 = M2a + M2b + (b - a)^2 n / 2
+          const float d0 = oth.x - ln_mean[0], d1 = oth.z - ln_mean[1];
+          const float mean0 = ln_mean[0] + 0.5f * d0, m20 = ln_m2[0] + oth.y + d0 * d0 * 64.0f;     // 256 columns each
+          const float mean1 = ln_mean[1] + 0.5f * d1, m21 = ln_m2[1] + oth.w + d1 * d1 * 64.0f;
+          const float dd = mean1 - mean0;
+          const float mean = mean0 + 0.5f * dd;
+          const float var = (m20 + m21 + dd * dd * 128.0f) * (1.0f / 512.0f);
+          const float rstd = 1.0f / sqrtf(var + p.ln_eps);      // as ln_rows() of rowwise.cu
+          uint8_t* c8 = reinterpret_cast<uint8_t*>(p.ln_second);
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+#pragma unroll
+            for (int ci = 0; ci < kChunks; ++ci) {
+              const int col0 = half * kColsW + ci * 32;
+              const int gcol = a * BN + col0;
+              uint32_t r[32];
+              ptx::tmem_ld_32x32(tmem_base + a * BN + col0 + (static_cast<uint32_t>(q * 32) << 16), r);
+              ptx::tmem_ld_wait();
+              uint32_t a8w[8], l8w[8];
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + gcol) + 2 * v);
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + gcol) + 2 * v + 1);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + gcol) + 2 * v);
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + gcol) + 2 * v + 1);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t hw[4], a16[4], l16[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float x0 = fmaf((__uint_as_float(r[8 * v + 2 * e]) - mean) * rstd, gg[2 * e], bb[2 * e]);
+                  const float x1 = fmaf((__uint_as_float(r[8 * v + 2 * e + 1]) - mean) * rstd, gg[2 * e + 1], bb[2 * e + 1]);
+                  const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                  hw[e] = pack_h2(h0, h1);
+                  a16[e] = op_e5m2x2(x0 * kActHiScale, x1 * kActHiScale);
+                  l16[e] = op_e5m2x2((x0 - __half2float(h0)) * kActLoScale, (x1 - __half2float(h1)) * kActLoScale);
+                }
+                *stg_at(stg, lane, v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                a8w[2 * v] = a16[0] | (a16[1] << 16); a8w[2 * v + 1] = a16[2] | (a16[3] << 16);
+                l8w[2 * v] = l16[0] | (l16[1] << 16); l8w[2 * v + 1] = l16[2] | (l16[3] << 16);
+              }
+              *stg_at(stg, lane, 4) = make_uint4(a8w[0], a8w[1], a8w[2], a8w[3]);
+              *stg_at(stg, lane, 5) = make_uint4(a8w[4], a8w[5], a8w[6], a8w[7]);
+              *stg_at(stg, lane, 6) = make_uint4(l8w[0], l8w[1], l8w[2], l8w[3]);
+              *stg_at(stg, lane, 7) = make_uint4(l8w[4], l8w[5], l8w[6], l8w[7]);
+              __syncwarp();
+              uint4 vals[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int rr = row_w + 4 * j + rsub;
+                if (rr >= p.M) continue;
+                void* dst = gsub < 4 ? static_cast<void*>(p.ln_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8)
+                                     : static_cast<void*>(c8 + static_cast<size_t>(rr) * (2 * p.N) + (gsub < 6 ? 0 : p.N) +
+                                                          gcol + (gsub & 1) * 16);
+                if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
+              }
+              __syncwarp();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[a]), leader));
+              else ptx::mbar_arrive(&bars->tmem_empty[a]);
+            }
+          }
+        }
+      } else {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[acc]), leader));
+          else ptx::mbar_arrive(&bars->tmem_empty[acc]);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -584,6 +692,7 @@ cudaError_t configure_gemm_tc() {
   if ((e = configure_one<2, 256, 2, EPI_QKV16, 2>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 2, EPI_GELU_SPLIT, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 2, EPI_QKV16, 1, 16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 2, EPI_F32_LN>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -591,6 +700,13 @@ cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, i
                            int pair_cluster, int epi_warps, int num_sms, cudaStream_t st) {
   if (p.M <= 0) return cudaSuccess;
   if (cta_group == 2 || passes == 2) bn = 256;
+  if (epi == EPI_F32_LN) {
+    // needs: both 256-column halves of a row tile on the same CTA pair, back to back, in accumulators 0 and 1
+    if (cta_group != 2 || passes != 2 || p.N != 2 * 256 || !p.n_inner || !p.residual || !p.ln_gamma || !p.ln_beta ||
+        !p.ln_hi || !p.ln_second)
+      return cudaErrorInvalidValue;
+    return launch_one<2, 256, 2, EPI_F32_LN>(maps, p, num_sms, st);
+  }
   if (epi_warps == 16 && cta_group == 2 && passes == 2 && pair_cluster != 2) {
     if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 2, EPI_GELU_SPLIT, 1, 16>(maps, p, num_sms, st);
     if (epi == EPI_QKV16) return launch_one<2, 256, 2, EPI_QKV16, 1, 16>(maps, p, num_sms, st);

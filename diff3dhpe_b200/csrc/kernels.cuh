@@ -17,7 +17,11 @@ constexpr int kHidden = 1024;  // mlp hidden
 // EPI_GELU_SPLIT out_hi/out_lo[M,N] = split_fp16(gelu_erf(acc + bias))            (fc1 -> A operand of fc2)
 // EPI_QKV16      N == 1536: out_qkv[M, 2048] fp16 rows = q(512) | k(512) | v_hi(512) | v_lo(512)
 //                (q, k rounded to fp16; v kept as a hi/lo pair so that the GRAND "- V" term stays exact)
-enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_QKV16 = 2 };
+// EPI_F32_LN     EPI_F32 with a residual, N == 512, PLUS the following LayerNorm fused (proj + norm2, MODEL:127-128):
+//                out_f32 = x = acc + bias + residual;  ln_hi/ln_second[M,512] = operand(LN(x; ln_gamma, ln_beta, ln_eps)).
+//                CTA-pair F8C tcgen05 kernel only (both 256-column halves of a row tile finish back to back on the
+//                same CTA pair with the n-inner tile order, so the full rows sit in the two TMEM accumulators).
+enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_QKV16 = 2, EPI_F32_LN = 3 };
 
 constexpr int kQkvRow = 4 * kC;   // halves per token row of the packed q|k|v_hi|v_lo tensor
 
@@ -33,6 +37,11 @@ struct GemmParams {
   // activation (A) and weight (B) operand loads (0 normal, 1 evict_last, 2 evict_first) and streaming (evict-first)
   // output stores / residual loads
   int hint_a, hint_b, stream_out;
+  const float* ln_gamma;  // EPI_F32_LN
+  const float* ln_beta;
+  float ln_eps;
+  __half* ln_hi;          // A operand of the next GEMM (FMT_F8C: hi fp16 [M,512] + c8 bytes [M,1024])
+  __half* ln_second;
   int n_inner;            // tile order of the persistent tcgen05 kernel: 1 = all n-tiles of an m-tile on the same CTA pair
 };
 

@@ -195,6 +195,13 @@ D3D_API int d3d_op_time_table(d3d_handle* h, const float* t_host, int32_t R, flo
 D3D_API int d3d_debug_forward_blocks(d3d_handle* h, const float* x5_dev, const int64_t* t_dev, int32_t B,
                              int32_t n_blocks, float* x_out_dev, void* stream);
 
+/* The fused "proj + residual + norm2" kernel (MODEL:127-128) on explicit operands: x_out = a . w^T + bias + residual
+ * ([M,512], K = columns of a), ln_out = LayerNorm(x_out; gamma, beta, eps) read back from the operand format it is
+ * written in (fp16 hi + e5m2 lo).  Needs gemm_mode D3D_GEMM_TC_F8C. */
+D3D_API int d3d_op_linear_ln(d3d_handle* h, const float* a_dev, const float* w_dev, const float* bias_dev,
+                     const float* residual_dev, const float* gamma_dev, const float* beta_dev, float eps,
+                     float* x_out_dev, float* ln_out_dev, int64_t M, int32_t K, void* stream);
+
 /* Runs one attention core like d3d_op_attention but returns the result in the raw GEMM A-operand format the proj
  * GEMM consumes: hi_out_dev [T, C] fp16 and second_out_dev [T, 2*C] bytes (operand format of the handle's gemm_mode:
  * fp16 lo[C], or uint8 e5m2(x * 2^-8)[C] | e5m2((x - hi) * 2^4)[C]). */

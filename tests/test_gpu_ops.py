@@ -59,6 +59,26 @@ def test_linear_gelu_split_epilogue(eng27, mode, tol):
     assert (out.double() - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("M", [128, 200, 1377, 256 * 74 * 2 + 300])
+def test_linear_layernorm_fused_epilogue(M):
+    """proj + residual + norm2 in one tcgen05 kernel (EPI_F32_LN): x against fp64, and the LayerNorm of x -- computed
+    in the epilogue from the two TMEM accumulators of a row tile -- against torch's layer_norm of the fp64 x.  Sizes:
+    one CTA, a ragged last tile, the F = 27 test batch, and more row tiles than CTA pairs (persistent loop)."""
+    K, N = 512, 512
+    eng = Engine(27, max_clips=1, gemm_mode=_lib.GEMM_TC_F8C)
+    a, w, b = _rand((M, K), 31), _rand((N, K), 32, 0.05), _rand((N,), 33, 0.1)
+    res = _rand((M, N), 34, 2.0) + 0.3
+    gam, bet = _rand((N,), 35) * 0.2 + 1.0, _rand((N,), 36, 0.1)
+    x_ref = a.double() @ w.double().T + b.double() + res.double()
+    ln_ref = torch.nn.functional.layer_norm(x_ref, (N,), gam.double(), bet.double(), 1e-6)
+    x, ln = eng.op_linear_ln(a.cuda(), w.cuda(), b.cuda(), res.cuda(), gam.cuda(), bet.cuda(), 1e-6)
+    eng.close()
+    scale = (a.double().abs() @ w.double().abs().T).max().item()
+    assert (x.cpu().double() - x_ref).abs().max().item() / scale < 2e-4
+    # operand read-back: hi + e5m2(lo) keeps ~14 bits of a value of magnitude <= ~5
+    assert (ln.cpu().double() - ln_ref).abs().max().item() < 1.5e-3
+
+
 @pytest.mark.parametrize("cs", [1, 2])
 def test_f8c_tc_matches_simt_elementwise(eng27, monkeypatch, cs):
     """Same hi / e5m2 operands in: the tensor-core F8C kernel and the CUDA-core kernel form the same products, so
