@@ -229,9 +229,13 @@ struct LnFuse {           // LayerNorm fused behind an EPI_F32 GEMM (EPI_F32_LN)
 
 // proj + norm2 in one kernel: CTA-pair F8C tcgen05 GEMM with the n-inner tile order only
 bool can_fuse_ln(const d3d_handle* h, int mode) {
-  return mode == D3D_GEMM_TC_F8C && h->fmt == FMT_F8C && pick_cg(kC) == 2 && env_int("D3D_GEMM_N_INNER", 1) == 1 &&
-         env_int("D3D_GEMM_FUSE_LN", 1) == 1;
+  return mode == D3D_GEMM_TC_F8C && h->fmt == FMT_F8C && pick_cg(kC) == 2 && env_int("D3D_GEMM_N_INNER", 1) == 1;
 }
+// OFF by default.  Measured on B200 at cfg3 (profiles/r01s_bench_fuse*.json): correct, but SLOWER -- GEMM class
+// 2727 -> 3069 ms per step for 198 ms of LayerNorm kernels saved (3802 -> 3943 ms per step).  Between its two passes
+// the epilogue holds BOTH accumulators, so its residual loads / operand stores are no longer hidden behind the next
+// tile's mainloop (~15 us per 128 x 256 pass with 8 warps, against 17 us of mainloop per row tile).
+bool fuse_ln_enabled() { return env_int("D3D_GEMM_FUSE_LN", 0) == 1; }
 
 // out = epilogue(Aop . W^T + bias)
 int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int epi, const float* residual,
@@ -349,7 +353,7 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
     const bool spatial = (b % 2) == 0;
     if ((r = run_gemm(h, h->A, k.qkv, T, EPI_QKV16, nullptr, nullptr, nullptr, nullptr, h->QKV, gm, st))) return r;
     if ((r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial, am, st))) return r;
-    if (can_fuse_ln(h, gm)) {        // proj + residual + norm2 (MODEL:127-128) in one kernel
+    if (fuse_ln_enabled() && can_fuse_ln(h, gm)) {        // proj + residual + norm2 (MODEL:127-128) in one kernel
       const LnFuse ln2{k.n2g, k.n2b, 1e-6f, &h->A};
       if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st, &ln2))) return r;
     } else {
