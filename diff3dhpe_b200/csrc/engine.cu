@@ -899,6 +899,15 @@ int d3d_mpjpe_accumulate(d3d_handle* h, const float* pred, const float* gt, cons
   return 0;
 }
 
+int d3d_pose_metrics_accumulate(d3d_handle* h, const float* pred, const float* gt, const int64_t* frame_index,
+                                int64_t n_sel, double* acc, void* stream) {
+  if (!h || !pred || !gt || !acc) return -1;
+  if (n_sel < 0) return fail(h, -2, "n_sel < 0");
+  DeviceGuard guard(h->cfg.device);
+  KL(launch_pose_metrics(pred, gt, frame_index, n_sel, h->J, acc, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int d3d_profile_begin(d3d_handle* h) {
   if (!h) return -1;
   h->prof = true;

@@ -112,6 +112,10 @@ cudaError_t launch_tta_merge(const float* y, const float* yf, const int32_t* per
 cudaError_t launch_mpjpe(const float* pred, const float* gt, const uint8_t* mask, int64_t n_frames, int J,
                          double* acc, cudaStream_t st);
 
+// Protocol #1/#2/#3 + velocity sums (metrics.cu): acc[6] fp64 = sum mpjpe, sum n_mpjpe, sum p_mpjpe, joints, sum vel, vel joints
+cudaError_t launch_pose_metrics(const float* pred, const float* gt, const int64_t* sel /*or null*/, int64_t n_sel, int J,
+                                double* acc, cudaStream_t st);
+
 // ------------------------------------------------------------------ windowing (packed sequences <-> F-frame windows)
 cudaError_t launch_window_gather(const float* seq2d, const int64_t* start, const int32_t* perm /*[J] device*/, float* x2d,
                                  float* x2d_flip /*or null*/, int64_t n_win, int F, int J, cudaStream_t st);

@@ -196,6 +196,28 @@ class Engine:
                                                  self._stream()), self.h, "d3d_mpjpe_accumulate")
         return acc
 
+    def pose_metrics_accumulate(self, pred: torch.Tensor, gt: torch.Tensor, acc: torch.Tensor,
+                                frame_index: Optional[torch.Tensor] = None):
+        """acc: fp64[6] on the device: sums / counts of MPJPE, N-MPJPE, P-MPJPE and the velocity error over the
+        frames listed in frame_index (None = all, in order); see include/diff3d_b200.h."""
+        _check_dev(pred, self.device, name="pred")
+        _check_dev(gt, self.device, tuple(pred.shape), name="gt")
+        _check_dev(acc, self.device, (6,), torch.float64, "acc")
+        n = pred.numel() // (self.J * 3)
+        if frame_index is not None:
+            _check_dev(frame_index, self.device, dtype=torch.int64, name="frame_index")
+            n = frame_index.numel()
+        _lib.check(self.lib.d3d_pose_metrics_accumulate(self.h, _ptr(pred), _ptr(gt), _ptr(frame_index), n, _ptr(acc),
+                                                        self._stream()), self.h, "d3d_pose_metrics_accumulate")
+        return acc
+
+    @staticmethod
+    def pose_metrics(acc: torch.Tensor):
+        """(mpjpe, p_mpjpe, n_mpjpe, velocity) from an accumulated fp64[6], in the reference's order e1, e2, e3, ev."""
+        a = acc.tolist()
+        n, nv = max(a[3], 1.0), max(a[5], 1.0)
+        return a[0] / n, a[2] / n, a[1] / n, a[4] / nv
+
     def profile_begin(self):
         _lib.check(self.lib.d3d_profile_begin(self.h), self.h, "d3d_profile_begin")
 

@@ -127,6 +127,17 @@ D3D_API int d3d_tta_merge(d3d_handle* h, const float* y_dev, const float* y_flip
                   const int32_t* joints_right, int32_t n_lr, float scale, float* out_dev, int64_t n_frames,
                   void* stream);
 
+/* The remaining metrics of evaluate() (RUN:602-614) on the device ("next" row N4): for the n_sel frames listed in
+ * frame_index_dev (NULL = frames 0..n_sel-1 in order) adds to acc_dev (six fp64 on the device)
+ *   [0] sum_j ||pred - gt||                       mpjpe   (common/loss.py:15-27)
+ *   [1] sum_j ||s pred - gt||, s per frame        n_mpjpe (common/loss.py:84-94)
+ *   [2] sum_j ||procrustes(pred) - gt||           p_mpjpe (common/loss.py:43-82; 3x3 SVD per frame in fp64)
+ *   [3] joints counted
+ *   [4] sum_j ||d pred - d gt|| over consecutive listed frames, [5] their joint count   (mean_velocity_error, :133-142)
+ * pred_dev / gt_dev: [n_frames, J, 3].  Each error is sum / count, as the reference's per-batch means are. */
+D3D_API int d3d_pose_metrics_accumulate(d3d_handle* h, const float* pred_dev, const float* gt_dev,
+                                const int64_t* frame_index_dev, int64_t n_sel, double* acc_dev, void* stream);
+
 /* Windowing on the device (common/nosiy_generators.py:27-48, 264-276; "next" row N3 of SURVEY.md 8f).
  * seq2d_dev: packed sequences [n_frames_total, J, 2]; win_start_dev[w] = first packed frame of window w.  Writes
  * x2d_out_dev [n_win, F, J, 2] and, when x2d_flip_out_dev != NULL, the horizontally flipped copy (x negated, joints

@@ -299,3 +299,43 @@ def window_batch(seq_2d: Tensor, start: int, chunk_length: int, start_target: in
         batch_2d[:, :, 0] *= -1
         batch_2d[:, list(kps_left) + list(kps_right)] = batch_2d[:, list(kps_right) + list(kps_left)]
     return batch_2d, target_mask
+
+
+# ----------------------------------------------------------------------------------------------- metrics (N4)
+def n_mpjpe(predicted: Tensor, target: Tensor) -> Tensor:
+    """Protocol #3, LOSS:84-94: per-frame least-squares scale, then MPJPE.  Inputs [N, 1, J, 3]."""
+    norm_predicted = torch.mean(torch.sum(predicted ** 2, dim=3, keepdim=True), dim=2, keepdim=True)
+    norm_target = torch.mean(torch.sum(target * predicted, dim=3, keepdim=True), dim=2, keepdim=True)
+    return mpjpe(norm_target / norm_predicted * predicted, target)
+
+
+def p_mpjpe(predicted, target) -> float:
+    """Protocol #2, LOSS:43-82 (numpy, float64 if the inputs are): Procrustes alignment per frame.  Inputs [N, J, 3]."""
+    import numpy as np
+    predicted, target = np.asarray(predicted), np.asarray(target)
+    muX = np.mean(target, axis=1, keepdims=True)
+    muY = np.mean(predicted, axis=1, keepdims=True)
+    X0, Y0 = target - muX, predicted - muY
+    normX = np.sqrt(np.sum(X0 ** 2, axis=(1, 2), keepdims=True))
+    normY = np.sqrt(np.sum(Y0 ** 2, axis=(1, 2), keepdims=True))
+    X0, Y0 = X0 / normX, Y0 / normY
+    H = np.matmul(X0.transpose(0, 2, 1), Y0)
+    U, s, Vt = np.linalg.svd(H)
+    V = Vt.transpose(0, 2, 1)
+    R = np.matmul(V, U.transpose(0, 2, 1))
+    sign_detR = np.sign(np.expand_dims(np.linalg.det(R), axis=1))
+    V[:, :, -1] *= sign_detR
+    s[:, -1] *= sign_detR.flatten()
+    R = np.matmul(V, U.transpose(0, 2, 1))
+    tr = np.expand_dims(np.sum(s, axis=1, keepdims=True), axis=2)
+    a = tr * normX / normY
+    t = muX - a * np.matmul(muY, R)
+    aligned = a * np.matmul(predicted, R) + t
+    return float(np.mean(np.linalg.norm(aligned - target, axis=2)))
+
+
+def mean_velocity_error(predicted, target) -> float:
+    """LOSS:133-142: mean norm of the difference of the first temporal differences.  Inputs [N, J, 3]."""
+    import numpy as np
+    vp, vt = np.diff(np.asarray(predicted), axis=0), np.diff(np.asarray(target), axis=0)
+    return float(np.mean(np.linalg.norm(vp - vt, axis=2)))

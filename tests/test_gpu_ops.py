@@ -203,6 +203,35 @@ def test_window_gather_scatter_large():
     assert torch.equal(out, seq3)
 
 
+def test_pose_metrics_golden(golden):
+    """d3d_pose_metrics_accumulate (MPJPE, N-MPJPE, P-MPJPE with a Jacobi 3x3 SVD, velocity error) against the
+    reference's common/loss.py values; then with a frame selection (the masked frames of evaluate()) against the oracle
+    on the compacted arrays, and accumulated over two calls."""
+    g = golden("metrics")
+    eng = Engine(9, max_clips=1)
+    pred, gt = torch.from_numpy(g["pred"]).cuda(), torch.from_numpy(g["gt"]).cuda()
+    acc = torch.zeros(6, dtype=torch.float64, device="cuda")
+    eng.pose_metrics_accumulate(pred, gt, acc)
+    e1, e2, e3, ev = Engine.pose_metrics(acc)
+    assert abs(e1 - float(g["mpjpe"])) < 2e-7 and abs(e3 - float(g["n_mpjpe"])) < 2e-7
+    assert abs(e2 - float(g["p_mpjpe"])) < 2e-7 and abs(ev - float(g["velocity"])) < 2e-7
+    assert acc[3].item() == 300 * 17 and acc[5].item() == 299 * 17
+    sel = torch.tensor([i for i in range(300) if i % 7 != 3], dtype=torch.int64)
+    acc2 = torch.zeros(6, dtype=torch.float64, device="cuda")
+    eng.pose_metrics_accumulate(pred, gt, acc2, sel[:100].cuda().contiguous())
+    eng.pose_metrics_accumulate(pred, gt, acc2, sel[100:].cuda().contiguous())
+    eng.close()
+    p, t = g["pred"][sel.numpy()], g["gt"][sel.numpy()]
+    tp, tg = torch.from_numpy(p).unsqueeze(1), torch.from_numpy(t).unsqueeze(1)
+    e1, e2, e3, _ = Engine.pose_metrics(acc2)
+    assert abs(e1 - oracle.mpjpe(tp, tg).item()) < 2e-7 and abs(e3 - oracle.n_mpjpe(tp, tg).item()) < 2e-7
+    assert abs(e2 - oracle.p_mpjpe(p, t)) < 2e-7
+    # velocity is per call (np.diff inside one batch): the two calls see 100 and 157 frames
+    n_a, n_b = 100, sel.numel() - 100
+    v = (oracle.mean_velocity_error(p[:n_a], t[:n_a]) * (n_a - 1) + oracle.mean_velocity_error(p[n_a:], t[n_a:]) * (n_b - 1))
+    assert abs(acc2[4].item() / 17 - v) < 1e-5 and acc2[5].item() == (n_a - 1 + n_b - 1) * 17
+
+
 def test_time_table_golden(golden):
     g = golden("denoise_f27_b3")
     eng = Engine(27, max_clips=3)

@@ -133,3 +133,14 @@ def test_windowing_golden(golden):
             w += 1
         base += n
     assert w == g["x2d"].shape[0]
+
+
+def test_metrics_golden(golden):
+    """mpjpe / n_mpjpe / p_mpjpe / velocity restatements against the reference's own common/loss.py outputs
+    (tools/make_golden_metrics.py; the first 7 frames are mirrored to exercise the reflection branch of p_mpjpe)."""
+    g = golden("metrics")
+    tp, tg = torch.from_numpy(g["pred"]).unsqueeze(1), torch.from_numpy(g["gt"]).unsqueeze(1)
+    assert oracle.mpjpe(tp, tg).item() == float(g["mpjpe"])
+    assert oracle.n_mpjpe(tp, tg).item() == float(g["n_mpjpe"])
+    assert oracle.p_mpjpe(g["pred"], g["gt"]) == float(g["p_mpjpe"])
+    assert oracle.mean_velocity_error(g["pred"], g["gt"]) == float(g["velocity"])

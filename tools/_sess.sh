@@ -1,19 +1,3 @@
 mkdir -p gpurun_out
-T=r01s
-timeout 200 python -m pytest tests/test_gpu_ops.py -k "layernorm_fused" -x -q > gpurun_out/${T}_pytest_ln.log 2>&1; echo "ln test rc=$?"; tail -15 gpurun_out/${T}_pytest_ln.log | cut -c1-300
-timeout 300 python -m pytest tests/test_gpu_ops.py -k "residual_stream or linear" -x -q > gpurun_out/${T}_pytest_ops.log 2>&1; tail -3 gpurun_out/${T}_pytest_ops.log
-timeout 300 python -m pytest tests/test_gpu_sampler.py -x -q > gpurun_out/${T}_pytest_sampler.log 2>&1; tail -3 gpurun_out/${T}_pytest_sampler.log
-run_bench() {  # name, env...
-  name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err
-  python - <<PY
-import json
-try:
-    d=json.load(open("gpurun_out/${T}_bench_$name.json"))
-    print("$name", round(d["value"]), d["ms_per_step"], d["clocks"]["sm_mhz"], d["roofline"]["per_class_ms"])
-except Exception as e:
-    print("bench $name failed", e)
-PY
-}
-run_bench fuse1 D3D_GEMM_FUSE_LN=1
-run_bench fuse0 D3D_GEMM_FUSE_LN=0
+T=r01t
+timeout 200 python -m pytest tests/test_gpu_ops.py -k "metrics or window" -x -q > gpurun_out/${T}_pytest_n4.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/${T}_pytest_n4.log | cut -c1-300
