@@ -264,6 +264,9 @@ def run_ours(args):
         "share_of_step": gemm_ms / total_prof_ms,
         "per_class_ms": {k: round(v[0], 3) for k, v in prof.items()},
         "algorithmic_flops_per_launch": gemm_flops / max(gemm_n, 1),
+        "note": "frac = ALGORITHMIC FLOPs over the measured sustained bf16 peak; the shipped precision mode executes 2 tensor-pipe "
+                "units per algorithmic FLOP (ceiling 0.5) and moves 4 B per operand element, so the qkv / fc2 launches sit at "
+                "the L2->SM cap (ncu lts2xbar ~8.6 TB/s), proj at HBM (DESIGN.md 4.1)",
     }
     total_flops = tokens * flops_per_token_call(F_FRAMES) * S_STEPS
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), if it matches the mode
