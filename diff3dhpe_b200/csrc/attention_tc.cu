@@ -74,13 +74,6 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {      // one
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-// Barrier wait of a whole warp: one lane polls, the others park at the warp barrier instead of spinning (ncu: the
-// try_wait loops of the 256 softmax threads were ~10 % of all issued instructions, taken from the other slot's softmax).
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-  if (lane == 0) ptx::mbar_wait(bar, parity);
-  __syncwarp();
-}
-
 // MN-major SWIZZLE_128B operand (V as B of P.V: rows = keys = contraction index, 64 head channels contiguous):
 // canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> 8 keys x 128 B per swizzle atom, next 8 keys
 // SBO = 1024 B further; one atom wide in N (64 halves), so LBO is unused.
@@ -372,7 +365,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       uint8_t* Qs = smem + stage * stage_bytes;
       const uint8_t* Vs = Qs + 2 * n_mt * kTile;
       const int r = m * 128 + row_l;
-      mbar_wait_warp(&bars->s_full[slot], i & 1, lane);
+      ptx::mbar_wait(&bars->s_full[slot], i & 1);
       ptx::tc_fence_after();
       if (issuer) {      // Q_m is dead once S is complete: it receives the v_lo rows of the tile (exact "- V" term)
         ptx::mbar_arrive_expect_tx(&bars->vlo_full[slot], kTile);
@@ -383,7 +376,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       ptx::mbar_arrive(&bars->p_full[slot]);
 
       // ---- O row out of TMEM, then the columns are free for the next S
-      mbar_wait_warp(&bars->o_full[slot], i & 1, lane);
+      ptx::mbar_wait(&bars->o_full[slot], i & 1);
       ptx::tc_fence_after();
       uint32_t o0[32], o1[32];
       ptx::tmem_ld_32x32(taddr + kOCol, o0);
@@ -394,7 +387,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
       // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
       ptx::bar_sync(1 + slot, 128);          // the issuer is past the read-wait of the previous tile's stores: Stg is free
-      mbar_wait_warp(&bars->vlo_full[slot], i & 1, lane);
+      ptx::mbar_wait(&bars->vlo_full[slot], i & 1);
       uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // v_lo row in, hi row out (same thread, same 16 bytes)
       const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
 #pragma unroll
