@@ -154,8 +154,14 @@ def run_ours(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    stdout_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
+        # stdout must carry exactly ONE JSON line: NCCL prints its version banner on fd 1 from C (NCCL_DEBUG_FILE does not
+        # catch it on this image), so fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = args.clips
     gemm_mode = {"split3": _lib.GEMM_TC_SPLIT3, "fp16": _lib.GEMM_TC_FP16, "f8c": _lib.GEMM_TC_F8C}[args.gemm]
@@ -300,6 +306,10 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        os.close(stdout_fd)
     if rank != 0:
         return
     print(json.dumps({
