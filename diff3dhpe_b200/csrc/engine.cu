@@ -65,7 +65,6 @@ struct d3d_handle {
 
   // workspace
   float* X = nullptr;
-  float2* nr_stats = nullptr;   // (mean, rstd) of the deferred post-norm, [tok_cap]
   __half* QKV = nullptr;     // packed fp16 q | k | v_hi | v_lo, [tok_cap, 2048]
   OperandBuf A, ATT, H;
   AttnTcMaps attn_tc;        // tcgen05 temporal attention: maps bound to QKV -> ATT
@@ -221,14 +220,6 @@ int pick_bn(const d3d_handle* h, int64_t M, int N) {
   return tiles256 >= 2 * h->num_sms ? 256 : 128;
 }
 
-struct NormRes {          // deferred post-norm of the residual (GemmParams::nr_*)
-  const float* gamma;
-  const float* beta;
-  const float* tpos;
-  const float* tvec;
-  int64_t tvec_stride;
-};
-
 struct LnFuse {           // LayerNorm fused behind an EPI_F32 GEMM (EPI_F32_LN): parameters and destination operand
   const float* gamma;
   const float* beta;
@@ -249,12 +240,8 @@ bool fuse_ln_enabled() { return env_int("D3D_GEMM_FUSE_LN", 0) == 1; }
 // out = epilogue(Aop . W^T + bias)
 int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int epi, const float* residual,
              float* out_f32, __half* out_hi, __half* out_lo, __half* out_qkv, int mode, cudaStream_t st,
-             const LnFuse* ln = nullptr, const NormRes* nr = nullptr) {
+             const LnFuse* ln = nullptr) {
   GemmParams p{};
-  if (nr) {
-    p.nr_stats = h->nr_stats; p.nr_gamma = nr->gamma; p.nr_beta = nr->beta; p.nr_tpos = nr->tpos; p.nr_tvec = nr->tvec;
-    p.nr_tvec_stride = nr->tvec_stride; p.nr_J = h->J; p.nr_F = h->F;
-  }
   if (ln) {
     epi = EPI_F32_LN;
     p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_eps = ln->eps;
@@ -361,41 +348,26 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
   KLP(D3D_PROF_LIFT, st, launch_lift_ln(x2d, y, x5, h->wf_t, h->bf, h->spos, tv, tv_stride,
                                         LnParams{h->blk[0].n1g, h->blk[0].n1b}, h->X, h->A.hi, h->A.lo, h->fmt, T, h->J,
                                         h->F * h->J, st));
-  // Deferred post-norm (tcgen05 GEMM modes): the post-norm kernel after block b leaves X = x (pre-norm) and writes only
-  // (mean, rstd) per row; the proj epilogue of block b + 1 rebuilds LN(x) + pos-embed + time vector as its residual.
-  // Saves the post-norm kernel's 2 KB/token write of X (LN class 488 -> see profiles/r01x).
-  const bool defer = (gm == D3D_GEMM_TC_F8C || gm == D3D_GEMM_TC_SPLIT3 || gm == D3D_GEMM_TC_FP16) &&
-                     env_int("D3D_DEFER_POSTNORM", 1) == 1;
-  NormRes nr{};
-  bool have_nr = false;
   for (int b = 0; b < n_blocks; ++b) {
     const Blk& k = h->blk[b];
     const bool spatial = (b % 2) == 0;
     if ((r = run_gemm(h, h->A, k.qkv, T, EPI_QKV16, nullptr, nullptr, nullptr, nullptr, h->QKV, gm, st))) return r;
     if ((r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial, am, st))) return r;
-    const NormRes* nrp = have_nr ? &nr : nullptr;
     if (fuse_ln_enabled() && can_fuse_ln(h, gm)) {        // proj + residual + norm2 (MODEL:127-128) in one kernel
       const LnFuse ln2{k.n2g, k.n2b, 1e-6f, &h->A};
-      if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st, &ln2, nrp))) return r;
+      if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st, &ln2))) return r;
     } else {
-      if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st, nullptr, nrp))) return r;
+      if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
       KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, h->fmt, T, st));
     }
-    have_nr = false;
     if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, nullptr, gm, st))) return r;
     if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
     if (b + 1 < n_blocks) {
       const LnParams post = spatial ? LnParams{h->sn_g, h->sn_b} : LnParams{h->tn_g, h->tn_b};
       const Blk& nx = h->blk[b + 1];
-      const float* tpos = (b + 1 == 1) ? h->tpos : nullptr;
-      const float* tvb = tv ? tv + (b + 1) * kC : nullptr;
       KLP(D3D_PROF_LN, st,
-          launch_postnorm_add_ln(h->X, post, tpos, tvb, tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo,
-                                 defer ? h->nr_stats : nullptr, h->fmt, T, h->J, h->F, st));
-      if (defer) {
-        nr = NormRes{post.gamma, post.beta, tpos, tvb, tv_stride};
-        have_nr = true;
-      }
+          launch_postnorm_add_ln(h->X, post, (b + 1 == 1) ? h->tpos : nullptr, tv ? tv + (b + 1) * kC : nullptr,
+                                 tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo, h->fmt, T, h->J, h->F, st));
     }
   }
   return 0;
@@ -536,7 +508,6 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
     if ((r = dev_alloc(h, &h->perm_dev, 64))) return r;
 
     if ((r = dev_alloc(h, &h->X, h->tok_cap * kC))) return r;
-    if ((r = dev_alloc(h, &h->nr_stats, h->tok_cap))) return r;
     if ((r = dev_alloc(h, &h->QKV, h->tok_cap * kQkvRow))) return r;
     if ((r = alloc_operand(h, &h->A, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->ATT, h->tok_cap, kC))) return r;

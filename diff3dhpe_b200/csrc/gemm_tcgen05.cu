@@ -358,18 +358,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
       };
       if (has_res) load_res(0);              // in flight while the accumulator is still being computed
-      // deferred post-norm of the residual: statistics and pos-embed / time-vector rows of THIS lane's row
-      float nr_mean = 0.f, nr_rstd = 1.f;
-      const float* nr_tpos_row = nullptr;
-      const float* nr_tvec_row = nullptr;
-      if ((EPI == EPI_F32 || EPI == EPI_F32_LN) && p.nr_stats) {
-        const int rr = row_w + lane < p.M ? row_w + lane : p.M - 1;
-        const float2 st = __ldg(p.nr_stats + rr);
-        nr_mean = st.x; nr_rstd = st.y;
-        const int frame_tok = rr / p.nr_J;
-        if (p.nr_tpos) nr_tpos_row = p.nr_tpos + static_cast<size_t>(frame_tok % p.nr_F) * p.N;
-        if (p.nr_tvec) nr_tvec_row = p.nr_tvec + static_cast<size_t>(frame_tok / p.nr_F) * p.nr_tvec_stride;
-      }
       ptx::mbar_wait(&bars->tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll
@@ -400,21 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             o.w = __uint_as_float(r[4 * v + 3]) + b.w;
             uint4* cell = stg_at(stg, lane, v);
             if (has_res) {
-              float4 rr = *reinterpret_cast<const float4*>(cell);
-              if (p.nr_stats) {          // deferred post-norm: rebuild LN(x) + pos-embed + time vector from x
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.nr_gamma + gcol) + v);
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.nr_beta + gcol) + v);
-                rr.x = fmaf((rr.x - nr_mean) * nr_rstd, g4.x, b4.x); rr.y = fmaf((rr.y - nr_mean) * nr_rstd, g4.y, b4.y);
-                rr.z = fmaf((rr.z - nr_mean) * nr_rstd, g4.z, b4.z); rr.w = fmaf((rr.w - nr_mean) * nr_rstd, g4.w, b4.w);
-                if (nr_tpos_row) {
-                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(nr_tpos_row + gcol) + v);
-                  rr.x += t4.x; rr.y += t4.y; rr.z += t4.z; rr.w += t4.w;
-                }
-                if (nr_tvec_row) {
-                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(nr_tvec_row + gcol) + v);
-                  rr.x += t4.x; rr.y += t4.y; rr.z += t4.z; rr.w += t4.w;
-                }
-              }
+              const float4 rr = *reinterpret_cast<const float4*>(cell);
               o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
             }
             *reinterpret_cast<float4*>(cell) = o;

@@ -37,16 +37,6 @@ struct GemmParams {
   // activation (A) and weight (B) operand loads (0 normal, 1 evict_last, 2 evict_first) and streaming (evict-first)
   // output stores / residual loads
   int hint_a, hint_b, stream_out;
-  // EPI_F32 with a "deferred post-norm" residual (tcgen05 kernels only): residual holds the PRE-norm row x and the
-  // epilogue adds  (x - mean) * rstd * nr_gamma + nr_beta (+ nr_tpos[frame]) (+ nr_tvec[clip])  instead of x
-  // (Spatial_norm / Temporal_norm + Temporal_pos_embed + the per-block time vector, MODEL:236-245, 113-116)
-  const float2* nr_stats; // [M] (mean, rstd) or null
-  const float* nr_gamma;
-  const float* nr_beta;
-  const float* nr_tpos;   // [F][512] or null
-  const float* nr_tvec;   // or null
-  int64_t nr_tvec_stride;
-  int nr_J, nr_F;
   const float* ln_gamma;  // EPI_F32_LN
   const float* ln_beta;
   float ln_eps;
@@ -97,11 +87,9 @@ cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, co
                            LnParams ln1, float* X, __half* a_hi, __half* a_lo, int fmt, int64_t T, int J,
                            int tokens_per_clip, cudaStream_t st);
 // X = LN(X; post) (+ tpos[f]) (+ tvec[sample]);  A = LN(X; ln1)   (MODEL:236/245, 239-242, 113-116, 127)
-// stats_out != null: X is left untouched and (mean, rstd) of the post-norm go to stats_out[T] instead -- the proj GEMM
-// of the next block rebuilds the post-norm row in its epilogue (GemmParams::nr_*).
 cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos /*[F][512] or null*/,
                                    const float* tvec, int64_t tvec_stride, LnParams ln1, __half* a_hi,
-                                   __half* a_lo, float2* stats_out, int fmt, int64_t T, int J, int F, cudaStream_t st);
+                                   __half* a_lo, int fmt, int64_t T, int J, int F, cudaStream_t st);
 // A = LN(X; ln)  (MODEL:128 norm2)
 cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int fmt, int64_t T,
                             cudaStream_t st);

@@ -52,10 +52,8 @@ __device__ __forceinline__ void store_operand(__half* __restrict__ hi, __half* _
 }
 
 // y = (x - mean) * rstd * gamma + beta over 512 columns held by the warp (two-pass variance in registers).
-// stats (optional) receives (mean, rstd).
 __device__ __forceinline__ void layernorm_row(const float (&x)[16], const float* __restrict__ gamma,
-                                              const float* __restrict__ beta, float eps, int lane, float (&y)[16],
-                                              float2* stats = nullptr) {
+                                              const float* __restrict__ beta, float eps, int lane, float (&y)[16]) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += x[i];
@@ -65,7 +63,6 @@ __device__ __forceinline__ void layernorm_row(const float (&x)[16], const float*
   for (int i = 0; i < 16; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
   const float var = warp_sum(q) * (1.0f / kC);
   const float rstd = 1.0f / sqrtf(var + eps);
-  if (stats) *stats = make_float2(mean, rstd);
   float g[16], b[16];
   load_row_ldg(gamma, lane, g);
   load_row_ldg(beta, lane, b);
@@ -121,14 +118,13 @@ template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __restrict__ tpos,
                        const float* __restrict__ tvec, int64_t tvec_stride, LnParams ln1, __half* __restrict__ a_hi,
-                       __half* __restrict__ a_lo, float2* __restrict__ stats_out, int64_t T, int J, int F) {
+                       __half* __restrict__ a_lo, int64_t T, int J, int F) {
   const int lane = threadIdx.x & 31;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   if (t >= T) return;
   float x[16], z[16], w[16];
   load_row(X + t * kC, lane, x);
-  float2 st;
-  layernorm_row(x, post.gamma, post.beta, 1e-6f, lane, z, &st);
+  layernorm_row(x, post.gamma, post.beta, 1e-6f, lane, z);
   if (tpos) {
     load_row_ldg(tpos + ((t / J) % F) * kC, lane, w);
 #pragma unroll
@@ -139,10 +135,7 @@ postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __rest
 #pragma unroll
     for (int i = 0; i < 16; ++i) z[i] += w[i];
   }
-  // stats_out != null: X keeps the PRE-norm row; the next proj epilogue rebuilds the post-norm row from it and
-  // (mean, rstd) (GemmParams::nr_*), which saves this kernel's 2 KB/token write of X
-  if (stats_out) { if (lane == 0) stats_out[t] = st; }
-  else store_row(X + t * kC, lane, z);
+  store_row(X + t * kC, lane, z);
   layernorm_row(z, ln1.gamma, ln1.beta, 1e-6f, lane, x);
   store_operand<FMT>(a_hi + t * kC, a_lo + t * kC, lane, x);
 }
@@ -335,11 +328,11 @@ cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, co
   return cudaGetLastError();
 }
 cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos, const float* tvec,
-                                   int64_t tvec_stride, LnParams ln1, __half* a_hi, __half* a_lo, float2* stats_out,
-                                   int fmt, int64_t T, int J, int F, cudaStream_t st) {
+                                   int64_t tvec_stride, LnParams ln1, __half* a_hi, __half* a_lo, int fmt, int64_t T,
+                                   int J, int F, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
   auto kern = fmt == FMT_F8C ? postnorm_add_ln_kernel<FMT_F8C> : postnorm_add_ln_kernel<FMT_SPLIT16>;
-  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, tpos, tvec, tvec_stride, ln1, a_hi, a_lo, stats_out, T, J, F);
+  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, tpos, tvec, tvec_stride, ln1, a_hi, a_lo, T, J, F);
   return cudaGetLastError();
 }
 cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int fmt, int64_t T,

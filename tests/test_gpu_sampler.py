@@ -68,21 +68,6 @@ def test_sampler_golden(golden, name, use_graph, gemm_mode):
     assert _mpjpe_delta(pred, ref, gt) < MPJPE_BAR / MARGIN
 
 
-def test_deferred_postnorm_matches_materialised(monkeypatch):
-    """Default: the post-norm kernel leaves X pre-norm and the next proj epilogue rebuilds LN(x) + pos-embed + time
-    vector from (mean, rstd).  Must agree with the materialised form (D3D_DEFER_POSTNORM=0) to rounding."""
-    F, B, S = 27, 3, 3
-    x2d, _ = synthetic.make_inputs(B, F)
-    y_T, _ = synthetic.make_noise(B, F, S)
-    outs = []
-    for flag in ("1", "0"):
-        monkeypatch.setenv("D3D_DEFER_POSTNORM", flag)
-        diff = _diffusion(F, S, clip=False, max_clips=B, use_graph=False)
-        outs.append(diff.ddim_sample_loop(x2d.cuda(), [B, F, 17, 3], noise=(y_T.cuda(), None)).cpu())
-        diff.model._engine.close()
-    assert (outs[0] - outs[1]).abs().max().item() < 2e-5
-
-
 def test_fp16_fast_mode_is_within_maxabs_bar(golden):
     g = golden("sampler_f27_b2_s3_clip")
     diff = _diffusion(27, 3, gemm_mode=_lib.GEMM_TC_FP16, max_clips=2)
