@@ -1,5 +1,7 @@
-// G-tattn on the 5th-generation tensor cores: the temporal GRAND attention core (MODEL:76-83 with the rearranges of
-// MODEL:121,133 folded into the addressing) for F > 64 frames, as a persistent tcgen05 / TMEM / TMA kernel.
+// G-tattn / G-sattn on the 5th-generation tensor cores: the GRAND attention core (MODEL:76-83) as ONE persistent
+// tcgen05 / TMEM / TMA kernel with two modes -- temporal (F > 64 frames per sequence, the rearranges of MODEL:121,133
+// folded into the addressing) and spatial (17 joints per frame, 7 frames per 128-row tile with a block-diagonal mask,
+// see softmax_row_spatial).  The description below is the temporal mode.
 //
 //     O = softmax(Q K^T * hd^-0.5) V  -  V[query]            ((P - I) V == P V - V)
 //
@@ -15,10 +17,11 @@
 //     same TMEM columns (tcgen05.st) -- P never touches shared memory;
 //   * O = P V is a second tcgen05.mma chain with A = P from TMEM and B = V from shared memory as an MN-major
 //     operand (V rows are keys, the contraction index), accumulating into the (dead) upper half of S;
-//   * the epilogue normalises, subtracts the exact V row (v_hi from shared memory + v_lo from global), packs the
-//     GEMM A-operand format and leaves through TMA stores (rows >= F are clipped by the hardware).
-// One CTA per SM keeps two 128-query tiles ("slots", 256 TMEM columns each) and two units (shared-memory stages) in
-// flight: while one slot runs its softmax on the CUDA cores the other is in its tensor-core phase, and the next
+//   * the epilogue normalises, subtracts the exact V row (v_hi from shared memory + v_lo, which a TMA load drops into
+//     the Q tile once S is complete), packs the GEMM A-operand format in place and leaves through TMA stores (rows
+//     >= F are clipped by the hardware).
+// One CTA per SM keeps two 128-query tiles ("slots", 256 TMEM columns each) and two or four units (shared-memory
+// stages) in flight: while one slot runs its softmax on the CUDA cores the other is in its tensor-core phase, and the next
 // unit's Q/K/V are already landing.  Measured history and ncu evidence: DESIGN.md section 4.2.
 //
 // Warp roles (384 threads): 0..3 softmax + epilogue of slot 0 (TMEM lane quadrant = warp & 3), 4..7 of slot 1,
@@ -43,8 +46,7 @@ constexpr int kSlotCols = 256;            // TMEM columns of one slot: S up to 2
 constexpr int kOCol = 128;
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;   // head_dim ** -0.5 (MODEL:65) in the exp2 domain
 
-// NSLOT = 128-query tiles in flight per CTA (each with its own 4 softmax warps and 256 TMEM columns) = shared-memory
-// stages (units resident per CTA).  Shipped: 2.  (A first version with one slot and two CTAs per SM measured 430 ms
+// NSLOT = 128-query tiles in flight per CTA (each with its own 4 softmax warps and 256 TMEM columns).  Shipped: 2.  (A first version with one slot and two CTAs per SM measured 430 ms
 // per cfg3 step against 398 ms, profiles/r01m_bench_slots*.json.)
 constexpr int kMaxStages = 4;
 template <int NSLOT>
