@@ -90,6 +90,13 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 
+__device__ __forceinline__ float row_sum(const ptx::f32x2 (&ls)[2]) {
+  float a, b, c, d;
+  ptx::unpack2(ls[0], a, b);
+  ptx::unpack2(ls[1], c, d);
+  return (a + b) + (c + d);
+}
+
 // One query row (= this thread's TMEM lane) of S -> P, two passes over tensor memory:
 //   pass 1: m = max over the F real keys;   pass 2: P = exp2(S c - m c) as packed fp16 into columns [0, n/2) of the
 //   same slot (column k/2 is written after S columns <= k+1 were read), row sum in fp32.  Returns 1 / sum.
@@ -136,26 +143,21 @@ __device__ __forceinline__ float softmax_row(uint32_t taddr, int F, int n_chunks
   ptx::tmem_ld_32x32(taddr, a0);
   if (1 < n) ptx::tmem_ld_32x32(taddr + 32, a1);
   const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
-  float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  // packed pairs (FFMA2 / FADD2): the scale-and-shift and the row sum cost one fma-pipe slot per TWO keys
+  ptx::f32x2 ls[2] = {ptx::splat2(0.f), ptx::splat2(0.f)};
+  const ptx::f32x2 sc2 = ptx::splat2(kScaleLog2e), nm2 = ptx::splat2(nmxs);
   auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
     uint32_t pk[16];
-    if (full(c)) {
+    const bool whole = full(c);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs));
-        ls[e & 3] += e0 + e1;
-        pk[e] = pack_f16x2(e0, e1);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int col = c * 32 + 2 * e;
-        const float e0 = col < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs)) : 0.f;
-        const float e1 = col + 1 < F ? ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs)) : 0.f;
-        ls[e & 3] += e0 + e1;
-        pk[e] = pack_f16x2(e0, e1);
-      }
+    for (int e = 0; e < 16; ++e) {
+      float t0, t1;
+      ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(rr[2 * e]), __uint_as_float(rr[2 * e + 1])), sc2, nm2), t0, t1);
+      const int col = c * 32 + 2 * e;
+      const float e0 = (whole || col < F) ? ex2_approx(t0) : 0.f;
+      const float e1 = (whole || col + 1 < F) ? ex2_approx(t1) : 0.f;
+      ls[e & 1] = ptx::add2(ls[e & 1], ptx::pack2(e0, e1));
+      pk[e] = pack_f16x2(e0, e1);
     }
     ptx::tmem_st_32x16(taddr + c * 16, pk);
   };
@@ -177,7 +179,7 @@ __device__ __forceinline__ float softmax_row(uint32_t taddr, int F, int n_chunks
     }
   }
   ptx::tmem_st_wait();
-  return rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
+  return rcp_approx(row_sum(ls));
 }
 
 // Spatial mode: the 128-row tile holds 7 frames x 17 joints (rows 119..127 belong to the next unit and are never
@@ -202,15 +204,18 @@ __device__ __forceinline__ float softmax_row_spatial(uint32_t taddr, int row_l, 
     if (static_cast<unsigned>(e + 64) - lo < 17u) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(c[e]));
   }
   const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
-  float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  ptx::f32x2 ls[2] = {ptx::splat2(0.f), ptx::splat2(0.f)};
+  const ptx::f32x2 sc2 = ptx::splat2(kScaleLog2e), nm2 = ptx::splat2(nmxs);
   auto exp_chunk = [&](const uint32_t (&rr)[32], int base) {
     uint32_t pk[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const bool in0 = static_cast<unsigned>(base + 2 * e) - lo < 17u, in1 = static_cast<unsigned>(base + 2 * e + 1) - lo < 17u;
-      const float e0 = in0 ? ex2_approx(fmaf(__uint_as_float(rr[2 * e]), kScaleLog2e, nmxs)) : 0.f;
-      const float e1 = in1 ? ex2_approx(fmaf(__uint_as_float(rr[2 * e + 1]), kScaleLog2e, nmxs)) : 0.f;
-      ls[e & 3] += e0 + e1;
+      float t0, t1;
+      ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(rr[2 * e]), __uint_as_float(rr[2 * e + 1])), sc2, nm2), t0, t1);
+      const float e0 = in0 ? ex2_approx(t0) : 0.f;
+      const float e1 = in1 ? ex2_approx(t1) : 0.f;
+      ls[e & 1] = ptx::add2(ls[e & 1], ptx::pack2(e0, e1));
       pk[e] = pack_f16x2(e0, e1);
     }
     ptx::tmem_st_32x16(taddr + cs * 16 + (base >> 1), pk);
@@ -225,7 +230,7 @@ __device__ __forceinline__ float softmax_row_spatial(uint32_t taddr, int row_l, 
     ptx::tmem_st_32x16(taddr + (cs == 0 ? 48 : 0), z);      // the 32 keys this warp did not load
   }
   ptx::tmem_st_wait();
-  return rcp_approx((ls[0] + ls[1]) + (ls[2] + ls[3]));
+  return rcp_approx(row_sum(ls));
 }
 
 // Work items of a CTA, in order: w = 0, 1, 2, ... ; unit n = w / n_mt (the CTA's n-th unit), 128-query tile
@@ -390,6 +395,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
       ptx::bar_sync(1 + slot, 128);          // the issuer is past the read-wait of the previous tile's stores: Stg is free
       ptx::mbar_wait(&bars->vlo_full[slot], i & 1);
+      const ptx::f32x2 inv2 = ptx::splat2(inv);
       uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // v_lo row in, hi row out (same thread, same 16 bytes)
       const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
 #pragma unroll
@@ -398,36 +404,39 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         const uint4 vl = *reinterpret_cast<const uint4*>(hi_row + ((g << 4) ^ sw));
         const uint32_t vhw[4] = {vh.x, vh.y, vh.z, vh.w};
         const uint32_t vlw[4] = {vl.x, vl.y, vl.z, vl.w};
-        float x[8];
+        // packed pairs: x = O inv - (v_hi + v_lo), lo = x - fp16(x) and the two e5m2 scalings as FFMA2 / FADD2 / FMUL2
+        uint32_t hw[4], lw[4], a8[4], l8[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const __half2 a = *reinterpret_cast<const __half2*>(&vhw[e]);
-          const __half2 c = *reinterpret_cast<const __half2*>(&vlw[e]);
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vhw[e]));
+          const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&vlw[e]));
           const float oa = __uint_as_float(g < 4 ? o0[8 * g + 2 * e] : o1[8 * (g & 3) + 2 * e]);
           const float ob = __uint_as_float(g < 4 ? o0[8 * g + 2 * e + 1] : o1[8 * (g & 3) + 2 * e + 1]);
-          x[2 * e] = fmaf(oa, inv, -(__low2float(a) + __low2float(c)));
-          x[2 * e + 1] = fmaf(ob, inv, -(__high2float(a) + __high2float(c)));
-        }
-        uint32_t hw[4], lw[4];
-        float lo[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __half h0 = __float2half_rn(x[2 * e]), h1 = __float2half_rn(x[2 * e + 1]);
-          hw[e] = op_pack_h2(h0, h1);
-          lo[2 * e] = x[2 * e] - __half2float(h0);
-          lo[2 * e + 1] = x[2 * e + 1] - __half2float(h1);
-          if (FMT == FMT_SPLIT16) lw[e] = op_pack_h2(__float2half_rn(lo[2 * e]), __float2half_rn(lo[2 * e + 1]));
+          float s0, s1, x0, x1, l0, l1;
+          ptx::unpack2(ptx::add2(ptx::pack2(a.x, a.y), ptx::pack2(c.x, c.y)), s0, s1);
+          const ptx::f32x2 xp = ptx::fma2(ptx::pack2(oa, ob), inv2, ptx::pack2(-s0, -s1));
+          ptx::unpack2(xp, x0, x1);
+          const __half2 h01 = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h01);
+          const ptx::f32x2 lp = ptx::sub2(xp, ptx::pack2(hf.x, hf.y));
+          hw[e] = *reinterpret_cast<const uint32_t*>(&h01);
+          if (FMT == FMT_SPLIT16) {
+            ptx::unpack2(lp, l0, l1);
+            const __half2 l01 = __floats2half2_rn(l0, l1);
+            lw[e] = *reinterpret_cast<const uint32_t*>(&l01);
+          } else {
+            ptx::unpack2(ptx::mul2(xp, ptx::splat2(kActHiScale)), x0, x1);
+            ptx::unpack2(ptx::mul2(lp, ptx::splat2(kActLoScale)), l0, l1);
+            a8[e] = op_e5m2x2(x0, x1);
+            l8[e] = op_e5m2x2(l0, l1);
+          }
         }
         *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         if (FMT == FMT_SPLIT16) {            // lo rows: 128 B, swizzled like hi
           *reinterpret_cast<uint4*>(Stg + row_l * 128 + ((g << 4) ^ sw)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         } else {                             // c8: [128 rows][64 B] e5m2(x 2^-8), then [128 rows][64 B] e5m2(lo 2^4)
-          *reinterpret_cast<uint2*>(Stg + row_l * 64 + g * 8) =
-              make_uint2(op_e5m2x4(x[0] * kActHiScale, x[1] * kActHiScale, x[2] * kActHiScale, x[3] * kActHiScale),
-                         op_e5m2x4(x[4] * kActHiScale, x[5] * kActHiScale, x[6] * kActHiScale, x[7] * kActHiScale));
-          *reinterpret_cast<uint2*>(Stg + 8192 + row_l * 64 + g * 8) =
-              make_uint2(op_e5m2x4(lo[0] * kActLoScale, lo[1] * kActLoScale, lo[2] * kActLoScale, lo[3] * kActLoScale),
-                         op_e5m2x4(lo[4] * kActLoScale, lo[5] * kActLoScale, lo[6] * kActLoScale, lo[7] * kActLoScale));
+          *reinterpret_cast<uint2*>(Stg + row_l * 64 + g * 8) = make_uint2(a8[0] | (a8[1] << 16), a8[2] | (a8[3] << 16));
+          *reinterpret_cast<uint2*>(Stg + 8192 + row_l * 64 + g * 8) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
         }
       }
       ptx::fence_proxy_async();

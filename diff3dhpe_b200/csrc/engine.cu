@@ -270,7 +270,10 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
     m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
     m.b_hi64 = w.m_hi64; m.b_lo64 = w.m_lo64;
     const int passes = mode == D3D_GEMM_TC_FP16 ? 1 : (mode == D3D_GEMM_TC_F8C ? 2 : 3);
-    const int ew = env_int(epi == EPI_GELU_SPLIT ? "D3D_GEMM_EW_GELU" : "D3D_GEMM_EW_QKV", epi == EPI_GELU_SPLIT ? 16 : 8);
+    // epilogue warps per CTA: 16 pays where the epilogue, not the mainloop, sets the tile time
+    const int ew = epi == EPI_GELU_SPLIT ? env_int("D3D_GEMM_EW_GELU", 16)
+                 : epi == EPI_QKV16    ? env_int("D3D_GEMM_EW_QKV", 8)
+                                        : env_int("D3D_GEMM_EW_F32", 8);
     KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), pick_cs(M), ew, h->num_sms, st));
   }
   return 0;

@@ -89,6 +89,35 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return fmaxf(v, 0.0f) - (0.70710678118654752440f * z) * (poly * t * e);
 }
 
+// The same function on a PACKED pair (FFMA2 / FMUL2: two IEEE-rn operations per fma-pipe slot).  The scalar form costs
+// 16 fma-pipe instructions per activation incl. bias and operand split; a 3-register FFMA issues every other cycle per
+// scheduler, so 32 768 activations per CTA tile kept the fma pipe busy for ~8 200 cycles -- longer than the tile's
+// mainloop.  Constants are folded so that no scaling multiply is left: with a = |v|,
+//   t = 1 / (1 + (p / sqrt 2) a),  e = exp2(-(log2 e / 2) a^2),  q(t) = -(a1 + t (a2 + ...)) / 2   (exact scaling),
+//   gelu(v) = max(v, 0) + a (q(t) t e).
+#ifndef D3D_EPI_PACKED
+#define D3D_EPI_PACKED 1
+#endif
+__device__ __forceinline__ ptx::f32x2 gelu_erf2(ptx::f32x2 v) {
+  float v0, v1;
+  ptx::unpack2(v, v0, v1);
+  const ptx::f32x2 a = ptx::pack2(fabsf(v0), fabsf(v1));
+  float d0, d1, t0, t1, g0, g1, e0, e1;
+  ptx::unpack2(ptx::fma2(a, ptx::splat2(0.3275911f * 0.70710678118654752440f), ptx::splat2(1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const ptx::f32x2 t = ptx::pack2(t0, t1);
+  ptx::f32x2 q = ptx::fma2(t, ptx::splat2(-0.5f * 1.061405429f), ptx::splat2(0.5f * 1.453152027f));
+  q = ptx::fma2(q, t, ptx::splat2(-0.5f * 1.421413741f));
+  q = ptx::fma2(q, t, ptx::splat2(0.5f * 0.284496736f));
+  q = ptx::fma2(q, t, ptx::splat2(-0.5f * 0.254829592f));
+  ptx::unpack2(ptx::mul2(ptx::mul2(a, a), ptx::splat2(-0.5f * 1.4426950408889634f)), g0, g1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  const ptx::f32x2 w = ptx::mul2(ptx::mul2(q, t), ptx::pack2(e0, e1));
+  return ptx::fma2(a, w, ptx::pack2(fmaxf(v0, 0.0f), fmaxf(v1, 0.0f)));
+}
+
 // Epilogue transpose buffer: 32 rows x 128 B; the 16-byte granule g of row r lives at r*128 + ((g ^ (r&7)) << 4)
 // (the 128-byte swizzle), so "lane = row" accesses and "8 lanes = one row" accesses are both conflict-free.
 __device__ __forceinline__ uint4* stg_at(uint8_t* stg, int r, int g) {
@@ -442,6 +471,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float4 b = bias4[2 * v + (e >> 1)];
+#if D3D_EPI_PACKED
+              ptx::f32x2 xp = ptx::add2(ptx::pack2(__uint_as_float(r[8 * v + 2 * e + 0]), __uint_as_float(r[8 * v + 2 * e + 1])),
+                                        (e & 1) ? ptx::pack2(b.z, b.w) : ptx::pack2(b.x, b.y));
+              if (gelu) xp = gelu_erf2(xp);
+              float x0, x1, l0, l1;
+              ptx::unpack2(xp, x0, x1);
+              const __half2 h01 = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h01);
+              const ptx::f32x2 lp = ptx::sub2(xp, ptx::pack2(hf.x, hf.y));
+              ptx::unpack2(lp, l0, l1);
+              hw[e] = *reinterpret_cast<const uint32_t*>(&h01);
+              if (f8out) {
+                ptx::unpack2(ptx::mul2(xp, ptx::splat2(kActHiScale)), x0, x1);
+                ptx::unpack2(ptx::mul2(lp, ptx::splat2(kActLoScale)), l0, l1);
+                a16[e] = op_e5m2x2(x0, x1);
+                l16[e] = op_e5m2x2(l0, l1);
+              } else {
+                const __half2 l01 = __floats2half2_rn(l0, l1);
+                lw[e] = *reinterpret_cast<const uint32_t*>(&l01);
+              }
+#else
               float x0 = __uint_as_float(r[8 * v + 2 * e + 0]) + ((e & 1) ? b.z : b.x);
               float x1 = __uint_as_float(r[8 * v + 2 * e + 1]) + ((e & 1) ? b.w : b.y);
               if (gelu) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); }
@@ -454,6 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               } else {
                 lw[e] = pack_h2(__float2half_rn(l0), __float2half_rn(l1));
               }
+#endif
             }
             *stg_at(stg, lane, v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             if (f8out) {
@@ -693,6 +744,7 @@ cudaError_t configure_gemm_tc() {
   if ((e = configure_one<2, 256, 2, EPI_GELU_SPLIT, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 2, EPI_QKV16, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 2, EPI_F32_LN>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 2, EPI_F32, 1, 16>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -708,6 +760,7 @@ cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, i
     return launch_one<2, 256, 2, EPI_F32_LN>(maps, p, num_sms, st);
   }
   if (epi_warps == 16 && cta_group == 2 && passes == 2 && pair_cluster != 2) {
+    if (epi == EPI_F32) return launch_one<2, 256, 2, EPI_F32, 1, 16>(maps, p, num_sms, st);
     if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 2, EPI_GELU_SPLIT, 1, 16>(maps, p, num_sms, st);
     if (epi == EPI_QKV16) return launch_one<2, 256, 2, EPI_QKV16, 1, 16>(maps, p, num_sms, st);
   }
