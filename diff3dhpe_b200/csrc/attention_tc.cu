@@ -185,52 +185,86 @@ __device__ __forceinline__ float softmax_row(uint32_t taddr, int F, int n_chunks
 // Spatial mode: the 128-row tile holds 7 frames x 17 joints (rows 119..127 belong to the next unit and are never
 // stored); query row r attends only the 17 keys of its own frame, columns [17 (r / 17), +17) of S.  A warp's 32 rows
 // touch at most 3 frames, i.e. a 51-column window inside the three aligned 32-column chunks starting at chunk
-// wq >> 1 (wq = TMEM lane quadrant); each thread masks its own 17 columns out of those 96.  P is written for all
-// 128 keys (zero outside the window), so the P.V chain is the same as in the temporal mode.
+// CS = wq >> 1 (wq = TMEM lane quadrant).  P is written for all 128 keys (zero outside the window), so the P.V chain
+// is the same as in the temporal mode.
+//
+// spatial_window<CS, FR>: the 17 keys of frame FR with COMPILE-TIME register indices -- no per-column masks or selects
+// (the masked form over all 96 loaded columns cost ~7 instructions per column, 665 per row; this one ~70 per frame, and
+// a warp runs at most three of them divergently).  Writes the packed fp16 P pairs of its window into pk (zero elsewhere)
+// and returns the row sum.
+template <int CS, int FR>
+__device__ __forceinline__ float spatial_window(const uint32_t (&a)[32], const uint32_t (&b)[32], const uint32_t (&c)[32],
+                                                uint32_t (&pk0)[16], uint32_t (&pk1)[16], uint32_t (&pk2)[16]) {
+  constexpr int L = 17 * FR - 32 * CS;          // first window column among the 96 loaded ones
+  static_assert(L >= 0 && L + 17 <= 96, "frame window outside the loaded chunks");
+  float sv[18];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) {
+    const int li = L + k;
+    sv[k] = __uint_as_float(li < 32 ? a[li & 31] : li < 64 ? b[li & 31] : c[li & 31]);
+  }
+  sv[17] = sv[16];                              // pads the last pair; never stored or summed
+  float mx = sv[0];
+#pragma unroll
+  for (int k = 1; k < 17; k += 2) mx = fmaxf(mx, fmaxf(sv[k], sv[k + 1]));
+  const ptx::f32x2 sc2 = ptx::splat2(kScaleLog2e), nm2 = ptx::splat2(-mx * kScaleLog2e);
+  float ev[18];
+  ptx::f32x2 ls = ptx::splat2(0.f);
+#pragma unroll
+  for (int k = 0; k < 18; k += 2) {
+    float t0, t1;
+    ptx::unpack2(ptx::fma2(ptx::pack2(sv[k], sv[k + 1]), sc2, nm2), t0, t1);
+    ev[k] = ex2_approx(t0);
+    ev[k + 1] = k + 1 < 17 ? ex2_approx(t1) : 0.f;
+    ls = ptx::add2(ls, ptx::pack2(ev[k], ev[k + 1]));
+  }
+#pragma unroll
+  for (int pi = L / 2; pi <= (L + 16) / 2; ++pi) {
+    const int k0 = 2 * pi - L, k1 = k0 + 1;
+    const uint32_t v = pack_f16x2(k0 >= 0 && k0 < 17 ? ev[k0 < 0 ? 0 : k0] : 0.f, k1 >= 0 && k1 < 17 ? ev[k1] : 0.f);
+    if (pi < 16) pk0[pi & 15] = v;
+    else if (pi < 32) pk1[pi & 15] = v;
+    else pk2[pi & 15] = v;
+  }
+  float s0, s1;
+  ptx::unpack2(ls, s0, s1);
+  return s0 + s1;
+}
+
 __device__ __forceinline__ float softmax_row_spatial(uint32_t taddr, int row_l, int wq) {
   const int cs = wq >> 1;
   uint32_t a[32], b[32], c[32];
   ptx::tmem_ld_32x32(taddr + cs * 32, a);
   ptx::tmem_ld_32x32(taddr + cs * 32 + 32, b);
   ptx::tmem_ld_32x32(taddr + cs * 32 + 64, c);
+  uint32_t pk0[16], pk1[16], pk2[16], z[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) pk0[e] = pk1[e] = pk2[e] = z[e] = 0u;
   ptx::tmem_ld_wait();
-  const int fr = row_l < 119 ? row_l / 17 : 6;
-  const unsigned lo = static_cast<unsigned>(17 * fr - 32 * cs);      // first column of the window, in loaded columns
-  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    if (static_cast<unsigned>(e) - lo < 17u) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(a[e]));
-    if (static_cast<unsigned>(e + 32) - lo < 17u) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(b[e]));
-    if (static_cast<unsigned>(e + 64) - lo < 17u) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(c[e]));
-  }
-  const float nmxs = -fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * kScaleLog2e;
-  ptx::f32x2 ls[2] = {ptx::splat2(0.f), ptx::splat2(0.f)};
-  const ptx::f32x2 sc2 = ptx::splat2(kScaleLog2e), nm2 = ptx::splat2(nmxs);
-  auto exp_chunk = [&](const uint32_t (&rr)[32], int base) {
-    uint32_t pk[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const bool in0 = static_cast<unsigned>(base + 2 * e) - lo < 17u, in1 = static_cast<unsigned>(base + 2 * e + 1) - lo < 17u;
-      float t0, t1;
-      ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(rr[2 * e]), __uint_as_float(rr[2 * e + 1])), sc2, nm2), t0, t1);
-      const float e0 = in0 ? ex2_approx(t0) : 0.f;
-      const float e1 = in1 ? ex2_approx(t1) : 0.f;
-      ls[e & 1] = ptx::add2(ls[e & 1], ptx::pack2(e0, e1));
-      pk[e] = pack_f16x2(e0, e1);
+  const int fr = row_l < 119 ? row_l / 17 : 6;    // rows 119..127 (next unit's tokens, never stored) ride along with frame 6
+  float sum;
+  if (cs == 0) {
+    switch (fr) {
+      case 0: sum = spatial_window<0, 0>(a, b, c, pk0, pk1, pk2); break;
+      case 1: sum = spatial_window<0, 1>(a, b, c, pk0, pk1, pk2); break;
+      case 2: sum = spatial_window<0, 2>(a, b, c, pk0, pk1, pk2); break;
+      default: sum = spatial_window<0, 3>(a, b, c, pk0, pk1, pk2); break;
     }
-    ptx::tmem_st_32x16(taddr + cs * 16 + (base >> 1), pk);
-  };
-  exp_chunk(a, 0);
-  exp_chunk(b, 32);
-  exp_chunk(c, 64);
-  {
-    uint32_t z[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) z[e] = 0u;
-    ptx::tmem_st_32x16(taddr + (cs == 0 ? 48 : 0), z);      // the 32 keys this warp did not load
+  } else {
+    switch (fr) {
+      case 3: sum = spatial_window<1, 3>(a, b, c, pk0, pk1, pk2); break;
+      case 4: sum = spatial_window<1, 4>(a, b, c, pk0, pk1, pk2); break;
+      case 5: sum = spatial_window<1, 5>(a, b, c, pk0, pk1, pk2); break;
+      default: sum = spatial_window<1, 6>(a, b, c, pk0, pk1, pk2); break;
+    }
   }
+  __syncwarp();                                   // tcgen05.st is .sync.aligned: the frames of the warp reconverge here
+  ptx::tmem_st_32x16(taddr + cs * 16, pk0);
+  ptx::tmem_st_32x16(taddr + cs * 16 + 16, pk1);
+  ptx::tmem_st_32x16(taddr + cs * 16 + 32, pk2);
+  ptx::tmem_st_32x16(taddr + (cs == 0 ? 48 : 0), z);      // the 32 keys this warp did not load
   ptx::tmem_st_wait();
-  return rcp_approx(row_sum(ls));
+  return rcp_approx(sum);
 }
 
 // Work items of a CTA, in order: w = 0, 1, 2, ... ; unit n = w / n_mt (the CTA's n-th unit), 128-query tile
@@ -382,6 +416,35 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->p_full[slot]);
 
+      // ---- while the P.V chain runs: this row's exact "- V" term, -(v_hi + v_lo), as 32 packed fp32 pairs (the v_lo row
+      // landed in the dead Q tile long ago; ncu had 15 % of the softmax warps' samples idle on o_full and another 10 % on
+      // the shared-memory loads below when they sat inside the epilogue loop, profiles/r01p_full_attn_tc.md)
+      ptx::mbar_wait(&bars->vlo_full[slot], i & 1);
+      uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // v_lo row in, hi row out (same thread, same 16 bytes)
+      const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
+      ptx::f32x2 nv[32];
+      {
+        uint4 vh[8], vl[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          vh[g] = *reinterpret_cast<const uint4*>(v_row + ((g << 4) ^ sw));
+          vl[g] = *reinterpret_cast<const uint4*>(hi_row + ((g << 4) ^ sw));
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t vhw[4] = {vh[g].x, vh[g].y, vh[g].z, vh[g].w};
+          const uint32_t vlw[4] = {vl[g].x, vl[g].y, vl[g].z, vl[g].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vhw[e]));
+            const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&vlw[e]));
+            float s0, s1;
+            ptx::unpack2(ptx::add2(ptx::pack2(a.x, a.y), ptx::pack2(c.x, c.y)), s0, s1);
+            nv[4 * g + e] = ptx::pack2(-s0, -s1);
+          }
+        }
+      }
+
       // ---- O row out of TMEM, then the columns are free for the next S
       ptx::mbar_wait(&bars->o_full[slot], i & 1);
       ptx::tc_fence_after();
@@ -394,27 +457,17 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
       // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
       ptx::bar_sync(1 + slot, 128);          // the issuer is past the read-wait of the previous tile's stores: Stg is free
-      ptx::mbar_wait(&bars->vlo_full[slot], i & 1);
       const ptx::f32x2 inv2 = ptx::splat2(inv);
-      uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // v_lo row in, hi row out (same thread, same 16 bytes)
-      const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const uint4 vh = *reinterpret_cast<const uint4*>(v_row + ((g << 4) ^ sw));
-        const uint4 vl = *reinterpret_cast<const uint4*>(hi_row + ((g << 4) ^ sw));
-        const uint32_t vhw[4] = {vh.x, vh.y, vh.z, vh.w};
-        const uint32_t vlw[4] = {vl.x, vl.y, vl.z, vl.w};
         // packed pairs: x = O inv - (v_hi + v_lo), lo = x - fp16(x) and the two e5m2 scalings as FFMA2 / FADD2 / FMUL2
         uint32_t hw[4], lw[4], a8[4], l8[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vhw[e]));
-          const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&vlw[e]));
           const float oa = __uint_as_float(g < 4 ? o0[8 * g + 2 * e] : o1[8 * (g & 3) + 2 * e]);
           const float ob = __uint_as_float(g < 4 ? o0[8 * g + 2 * e + 1] : o1[8 * (g & 3) + 2 * e + 1]);
-          float s0, s1, x0, x1, l0, l1;
-          ptx::unpack2(ptx::add2(ptx::pack2(a.x, a.y), ptx::pack2(c.x, c.y)), s0, s1);
-          const ptx::f32x2 xp = ptx::fma2(ptx::pack2(oa, ob), inv2, ptx::pack2(-s0, -s1));
+          float x0, x1, l0, l1;
+          const ptx::f32x2 xp = ptx::fma2(ptx::pack2(oa, ob), inv2, nv[4 * g + e]);
           ptx::unpack2(xp, x0, x1);
           const __half2 h01 = __floats2half2_rn(x0, x1);
           const float2 hf = __half22float2(h01);
