@@ -28,6 +28,10 @@
 // 8 = TMA producer, 9 = MMA issuer and TMEM allocator, 10..11 idle (they complete the control warpgroup).
 #include "kernels.cuh"
 #include "operand.cuh"
+// The barrier waits of this kernel sit on a per-item latency chain (MMA -> softmax -> MMA -> epilogue): the sleeping
+// wait of ptx.cuh costs +4 % here (wake-up latency; profiles/r01zd_bench_*.json: 489 -> 501 ms per cfg3 step for both
+// modes) while it gains 0.5 % in the GEMM, whose waits have slack.  Busy try_wait polling in this file.
+#define D3D_MBAR_SUSPEND_NS 0
 #include "ptx.cuh"
 
 namespace d3d {

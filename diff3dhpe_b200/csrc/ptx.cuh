@@ -43,11 +43,36 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 // Blocking wait with a watchdog: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
+// try_wait carries a suspend-time hint, so a waiting warp SLEEPS in hardware (NANOSLEEP.SYNCS) until the barrier's
+// phase completes or the hint expires, instead of re-issuing try_wait every ~50 cycles: ncu on the hint-less form
+// counted 17 % of all executed instructions of the attention kernel in these spin loops and showed the XU pipe (which
+// MUFU.EX2 / RCP and the float conversions of the epilogues need) at 87-120 % in the GEMM kernels
+// (profiles/r01zc_full_gemm.md).  D3D_MBAR_SUSPEND_NS = 0 restores the busy spin.
+#ifndef D3D_MBAR_SUSPEND_NS
+#define D3D_MBAR_SUSPEND_NS 1000000
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
   long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
+#if D3D_MBAR_SUSPEND_NS > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(static_cast<uint32_t>(D3D_MBAR_SUSPEND_NS))
+        : "memory");
+    if (ok) return;
+    if (spin >= 4) {                                  // a handful of expired 1 ms hints: start the clock
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+    }
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
@@ -63,6 +88,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
     }
+#endif
   }
 }
 
