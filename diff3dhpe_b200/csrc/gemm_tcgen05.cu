@@ -72,11 +72,17 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+// D3D_EPI_PACKED = 0 compiles the scalar epilogue math (the A/B baseline of profiles/r01z_bench_scalar_epilogue.json)
+#ifndef D3D_EPI_PACKED
+#define D3D_EPI_PACKED 1
+#endif
+
 // Exact-erf GELU (MODEL:52, nn.GELU()) without the branchy library erff: the epilogue is instruction-issue bound
 // (32 768 activations per 128 x 256 tile), so the form below is branch- and call-free, 2 MUFU + ~14 FP32 ops:
 //   gelu(v) = max(v, 0) - |v|/2 * erfc(|v| / sqrt 2),   erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),
 //   t = 1 / (1 + p z)   (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 on erfc; using erfc for BOTH signs avoids the
 //   1 + erf cancellation in the negative tail).  Absolute error on gelu <= |v| * 1e-7.
+#if !D3D_EPI_PACKED
 __device__ __forceinline__ float gelu_erf(float v) {
   const float z = fabsf(v) * 0.70710678118654752440f;
   float t, e;
@@ -88,6 +94,7 @@ __device__ __forceinline__ float gelu_erf(float v) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));   // MUFU, rel. error 2^-22
   return fmaxf(v, 0.0f) - (0.70710678118654752440f * z) * (poly * t * e);
 }
+#endif
 
 // The same function on a PACKED pair (FFMA2 / FMUL2: two IEEE-rn operations per fma-pipe slot).  The scalar form costs
 // 16 fma-pipe instructions per activation incl. bias and operand split; a 3-register FFMA issues every other cycle per
@@ -95,9 +102,7 @@ __device__ __forceinline__ float gelu_erf(float v) {
 // mainloop.  Constants are folded so that no scaling multiply is left: with a = |v|,
 //   t = 1 / (1 + (p / sqrt 2) a),  e = exp2(-(log2 e / 2) a^2),  q(t) = -(a1 + t (a2 + ...)) / 2   (exact scaling),
 //   gelu(v) = max(v, 0) + a (q(t) t e).
-#ifndef D3D_EPI_PACKED
-#define D3D_EPI_PACKED 1
-#endif
+#if D3D_EPI_PACKED
 __device__ __forceinline__ ptx::f32x2 gelu_erf2(ptx::f32x2 v) {
   float v0, v1;
   ptx::unpack2(v, v0, v1);
@@ -117,6 +122,7 @@ __device__ __forceinline__ ptx::f32x2 gelu_erf2(ptx::f32x2 v) {
   const ptx::f32x2 w = ptx::mul2(ptx::mul2(q, t), ptx::pack2(e0, e1));
   return ptx::fma2(a, w, ptx::pack2(fmaxf(v0, 0.0f), fmaxf(v1, 0.0f)));
 }
+#endif
 
 // Epilogue transpose buffer: 32 rows x 128 B; the 16-byte granule g of row r lives at r*128 + ((g ^ (r&7)) << 4)
 // (the 128-byte swizzle), so "lane = row" accesses and "8 lanes = one row" accesses are both conflict-free.

@@ -11,6 +11,8 @@ Linear modes:
   split3    a_hi.b_hi + a_hi.b_lo + a_lo.b_hi                     (3 fp16 passes)
   f8corr    a_hi.b_hi + 2^-16 (e4m3(a).e4m3(2^16 b_lo) + e4m3(2^12 a_lo).e4m3(2^4 b))   (1 fp16 + 2 fp8 passes, 2 accumulators)
   f8c52     a_hi.b_hi + e5m2(2^-8 a).e5m2(2^8 b_lo) + e5m2(2^4 a_lo).e5m2(2^-4 b)       (same, ONE accumulator)
+  f4c       a_hi.b_hi + q4(a).q4(b_lo) + q4(a_lo).q4(b), q4 = e2m1 with one power-of-two scale per 32 elements of K
+            (kind::mxf4, 4x the fp16 rate: 1.5 tensor-pipe units);  f4c_nv: e4m3 scale per 16 elements (nvfp4)
 Attention modes: fp32 | fp16 | split3 | qk3pv1 (QK^T split3, PV single fp16 pass)
 """
 import os
@@ -42,6 +44,35 @@ def e5m2(x):
     return x.clamp(-57344.0, 57344.0).to(torch.float8_e5m2).float()
 
 
+_E2M1 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
+
+
+def e2m1(x):
+    """Round-to-nearest onto the e2m1 grid {0, .5, 1, 1.5, 2, 3, 4, 6} (saturating)."""
+    ax = x.abs().clamp(max=6.0)
+    idx = torch.bucketize(ax, (_E2M1[1:] + _E2M1[:-1]) * 0.5)
+    return torch.sign(x) * _E2M1[idx]
+
+
+def blockq4(x, dim, block, scale):
+    """Block-scaled e2m1 along `dim` (the contraction index), as tcgen05.mma kind::mxf4 / mxf4nvf4 consumes it:
+    scale = "ue8m0": one power-of-two scale per `block` elements (mxfp4, block 32), chosen so that the block maximum
+    lands in (3, 6]; "ue4m3": one e4m3 scale per block (nvfp4, block 16), amax / 6 rounded to e4m3."""
+    xm = x.movedim(dim, -1)
+    K = xm.shape[-1]
+    pad = (-K) % block
+    if pad:
+        xm = F.pad(xm, (0, pad))
+    xb = xm.reshape(*xm.shape[:-1], -1, block)
+    amax = xb.abs().amax(dim=-1, keepdim=True).clamp(min=1e-30)
+    if scale == "ue8m0":
+        sf = torch.exp2(torch.ceil(torch.log2(amax / 6.0)))
+    else:
+        sf = (amax / 6.0).clamp(min=2.0 ** -9).to(torch.float8_e4m3fn).float()
+    q = (e2m1(xb / sf) * sf).reshape(xm.shape)[..., :K]
+    return q.movedim(-1, dim)
+
+
 def mm_mode(a, bt, mode):
     """a [.., M, K] @ bt [.., K, N] with operand rounding per mode, fp32 accumulate."""
     if mode == "fp32":
@@ -60,6 +91,15 @@ def mm_mode(a, bt, mode):
     if mode == "f8c52":            # single accumulator: scale products are 1, all four fp8 operands e5m2
         return (torch.matmul(ah, bh) + torch.matmul(e5m2(a * 2.0 ** -8), e5m2(bl * 2.0 ** 8)) +
                 torch.matmul(e5m2(al * 2.0 ** 4), e5m2(bt * 2.0 ** -4)))
+    if mode.startswith("f4c"):      # fp16 main + BOTH correction products in block-scaled e2m1 (1.5 tensor-pipe units)
+        block, sc = (16, "ue4m3") if mode == "f4c_nv" else (32, "ue8m0")
+        qa = lambda t: blockq4(t, -1, block, sc)      # noqa: E731  (A operands: K is the last dim)
+        qb = lambda t: blockq4(t, -2, block, sc)      # noqa: E731  (B^T operands: K is dim -2)
+        return torch.matmul(ah, bh) + torch.matmul(qa(a), qb(bl)) + torch.matmul(qa(al), qb(bt))
+    if mode.startswith("f84c"):     # A side e5m2 as shipped, B side (weights) block-scaled e2m1 -- bytes, not rate
+        qb = lambda t: blockq4(t, -2, 32, "ue8m0")    # noqa: E731
+        return torch.matmul(ah, bh) + torch.matmul(e5m2(a * 2.0 ** -8) * 2.0 ** 8, qb(bl)) + torch.matmul(
+            e5m2(al * 2.0 ** 4) * 2.0 ** -4, qb(bt))
     if mode == "f8c43":            # a, a_lo in e4m3 (x 2^-4 / x 2^8), b_lo, b in e5m2 (x 2^4 / x 2^-8)
         return (torch.matmul(ah, bh) + torch.matmul(e4m3(a * 2.0 ** -4), e5m2(bl * 2.0 ** 4)) +
                 torch.matmul(e4m3(al * 2.0 ** 8), e5m2(bt * 2.0 ** -8)))
