@@ -91,6 +91,29 @@ def test_f8c_tc_matches_simt_elementwise(eng27, monkeypatch, cs):
     assert (x - y).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("ew", [8, 16])
+@pytest.mark.parametrize("act", [0, 1])
+def test_f8c_epilogue_warp_variants(eng27, monkeypatch, ew, act):
+    """8 or 16 epilogue warps per CTA (D3D_GEMM_EW_*; shipped: 16 for the GELU epilogue, 8 for the fp32 one) over more
+    row tiles than CTA pairs and a ragged last tile: the fp32 + residual epilogue against the CUDA-core kernel on the
+    same operands, the packed-pair GELU epilogue against fp64."""
+    monkeypatch.setenv("D3D_GEMM_EW_F32", str(ew))
+    monkeypatch.setenv("D3D_GEMM_EW_GELU", str(ew))
+    M, K = 74 * 256 + 300, 512
+    N = 1024 if act else 512
+    a, w, b = _rand((M, K), 41), _rand((N, K), 42, 0.05), _rand((N,), 43, 0.1)
+    if act:
+        ref = torch.nn.functional.gelu(a.double() @ w.double().T + b.double())
+        out = eng27.op_linear(a.cuda(), w.cuda(), b.cuda(), act=1, gemm_mode=_lib.GEMM_TC_F8C).cpu()
+        assert (out.double() - ref).abs().max().item() < 1.5e-3
+    else:
+        res = _rand((M, N), 44).cuda()
+        x = eng27.op_linear(a.cuda(), w.cuda(), b.cuda(), residual=res, gemm_mode=_lib.GEMM_TC_F8C)
+        y = eng27.op_linear(a.cuda(), w.cuda(), b.cuda(), residual=res, gemm_mode=_lib.GEMM_SIMT_F8C)
+        # same operands and products, different fp32 accumulation order (measured: 2.0e-5 over 19 244 x 512 outputs)
+        assert (x - y).abs().max().item() < 1e-4
+
+
 def test_tc_matches_simt_elementwise(eng27):
     """Same split operands in, so tensor-core and CUDA-core results differ only by accumulation order and the
     dropped lo*lo term (2^-22 relative)."""
