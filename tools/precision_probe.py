@@ -68,7 +68,10 @@ def blockq4(x, dim, block, scale):
     if scale == "ue8m0":
         sf = torch.exp2(torch.ceil(torch.log2(amax / 6.0)))
     else:
-        sf = (amax / 6.0).clamp(min=2.0 ** -9).to(torch.float8_e4m3fn).float()
+        # per-tensor power-of-two pre-scale (a compile-time constant per operand in a kernel, as kActHiScale is today)
+        # puts the largest block scale at 256 < 448; smaller ones use e4m3's 2^15 range, then subnormals, then flush
+        pre = torch.exp2(torch.floor(torch.log2(256.0 / (amax.max() / 6.0))))
+        sf = (amax / 6.0 * pre).to(torch.float8_e4m3fn).float().clamp(min=2.0 ** -9) / pre
     q = (e2m1(xb / sf) * sf).reshape(xm.shape)[..., :K]
     return q.movedim(-1, dim)
 
@@ -85,6 +88,8 @@ def mm_mode(a, bt, mode):
         return torch.matmul(ah, bh) + torch.matmul(ah, bl) + torch.matmul(al, bh)
     if mode == "split2a":           # activations exact-ish, weights rounded
         return torch.matmul(ah, bh) + torch.matmul(al, bh)
+    if mode == "split2b":           # weights exact-ish, activations rounded
+        return torch.matmul(ah, bh) + torch.matmul(ah, bl)
     if mode == "f8corr":
         corr = torch.matmul(e4m3(a), e4m3(bl * 65536.0)) + torch.matmul(e4m3(al * 4096.0), e4m3(bt * 16.0))
         return torch.matmul(ah, bh) + corr * (1.0 / 65536.0)
