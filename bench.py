@@ -97,7 +97,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_sample(n_clips=1, threads=None):
+def cpu_sample(n_clips=1, threads=None, keep=None):
     """The reference algorithm's CPU path (oracle port: fp32 torch-CPU restatement, bit-identical to the imported
     reference in the build container) on a bounded sample of the SAME workload: n_clips clips of F=243, S=9, flip
     TTA (two sampler passes + merge).  Returns (pose-frames/s, seconds, threads)."""
@@ -107,13 +107,34 @@ def cpu_sample(n_clips=1, threads=None):
     torch.set_num_threads(threads)
     m = synthetic.make_model(F_FRAMES)
     sd = {k: v.detach() for k, v in m.state_dict().items()}
-    x2d, _ = synthetic.make_inputs(n_clips, F_FRAMES)
+    x2d, gt = synthetic.make_inputs(n_clips, F_FRAMES)
     n1, n2 = synthetic.make_noise(n_clips, F_FRAMES, S_STEPS, seed=1), synthetic.make_noise(n_clips, F_FRAMES, S_STEPS, seed=2)
     t0 = time.perf_counter()
     with torch.no_grad():
-        oracle.sample_tta(sd, x2d, n1, n2, sampling_timesteps=S_STEPS)
+        ref = oracle.sample_tta(sd, x2d, n1, n2, sampling_timesteps=S_STEPS)
     dt = time.perf_counter() - t0
+    if keep is not None:
+        keep.update(ref=ref, x2d=x2d, gt=gt, n1=n1, n2=n2)
     return n_clips * F_FRAMES / dt, dt, threads
+
+
+def parity_on_sample(keep, gemm_mode):
+    """The CPU sample's clip through the CUDA path (same weights, 2D input and noise seeds; drop-in module -> C ABI) and
+    the two numbers BASELINE.json's metric asks for next to the throughput: per-joint max-abs error (pose scale 1,
+    bar 1e-2) and |MPJPE(ours) - MPJPE(reference port)| (bar 1e-4 = 0.1 mm).  The oracle is the checker here."""
+    from diff3dhpe_b200 import synthetic
+    from oracle import diff3d_oracle as oracle
+    n = keep["x2d"].shape[0]
+    model = synthetic.make_model(F_FRAMES).cuda()
+    model.gemm_mode, model.max_clips_hint = gemm_mode, 2 * n
+    diff = synthetic.make_diffusion(model, sampling_timesteps=S_STEPS).cuda().eval()
+    x = torch.cat([keep["x2d"], synthetic.flip_2d(keep["x2d"])]).cuda()
+    y = diff.ddim_sample_loop(x, [2 * n, F_FRAMES, 17, 3], noise=(torch.cat([keep["n1"][0], keep["n2"][0]]).cuda(), None))
+    merged = diff._engine(2 * n).tta_merge(y[:n], y[n:], synthetic.H36M_JOINTS_LEFT, synthetic.H36M_JOINTS_RIGHT, 1.0).cpu()
+    ref, gt = keep["ref"], keep["gt"]
+    return {"max_abs_err": (merged - ref).abs().max().item(), "max_abs_bar": 1e-2,
+            "mpjpe_delta": abs(oracle.mpjpe(merged, gt).item() - oracle.mpjpe(ref, gt).item()), "mpjpe_delta_bar": 1e-4,
+            "sample": f"{n} clip x {F_FRAMES} frames, S={S_STEPS}, flip-TTA, same weights / inputs / noise seeds as the CPU arm"}
 
 
 def run_reference(args):
@@ -298,10 +319,16 @@ def run_ours(args):
     roofline["hbm_peak_gbs"] = peaks["hbm_gbs"]
 
     cpu_baseline = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, dt, threads = cpu_sample(1)
+        keep = {}
+        fps, dt, threads = cpu_sample(1, keep=keep)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"1 clip x {F_FRAMES} frames, S={S_STEPS}, flip-TTA, fp32 torch-CPU oracle, {dt:.1f} s"}
+        try:
+            parity = parity_on_sample(keep, gemm_mode)
+        except Exception as e:      # the throughput line must survive a failure of the checker
+            parity = {"error": f"{type(e).__name__}: {e}"}
 
     if world > 1:
         dist.barrier()
@@ -331,6 +358,7 @@ def run_ours(args):
         "gpu_launches": int(gpu_launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "parity": parity,
     }), flush=True)
 
 
