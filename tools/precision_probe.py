@@ -12,7 +12,10 @@ Linear modes:
   f8corr    a_hi.b_hi + 2^-16 (e4m3(a).e4m3(2^16 b_lo) + e4m3(2^12 a_lo).e4m3(2^4 b))   (1 fp16 + 2 fp8 passes, 2 accumulators)
   f8c52     a_hi.b_hi + e5m2(2^-8 a).e5m2(2^8 b_lo) + e5m2(2^4 a_lo).e5m2(2^-4 b)       (same, ONE accumulator)
   f4c       a_hi.b_hi + q4(a).q4(b_lo) + q4(a_lo).q4(b), q4 = e2m1 with one power-of-two scale per 32 elements of K
-            (kind::mxf4, 4x the fp16 rate: 1.5 tensor-pipe units);  f4c_nv: e4m3 scale per 16 elements (nvfp4)
+            (kind::mxf4, 4x the fp16 rate: 1.5 tensor-pipe units);  f4c_16: power-of-two scale per 16 elements
+            (kind::mxf4nvf4 with ue8m0 scales);  f4c_nv: e4m3 scale per 16 elements (nvfp4) -- NOTE its emulation
+            applies a free per-tensor power of two, which one shared accumulator cannot give: the a . w_lo product
+            would need scale values 21 binades apart and ue4m3 spans 17
 Attention modes: fp32 | fp16 | split3 | qk3pv1 (QK^T split3, PV single fp16 pass)
 """
 import os
@@ -97,7 +100,7 @@ def mm_mode(a, bt, mode):
         return (torch.matmul(ah, bh) + torch.matmul(e5m2(a * 2.0 ** -8), e5m2(bl * 2.0 ** 8)) +
                 torch.matmul(e5m2(al * 2.0 ** 4), e5m2(bt * 2.0 ** -4)))
     if mode.startswith("f4c"):      # fp16 main + BOTH correction products in block-scaled e2m1 (1.5 tensor-pipe units)
-        block, sc = (16, "ue4m3") if mode == "f4c_nv" else (32, "ue8m0")
+        block, sc = {"f4c": (32, "ue8m0"), "f4c_16": (16, "ue8m0"), "f4c_nv": (16, "ue4m3")}[mode]
         qa = lambda t: blockq4(t, -1, block, sc)      # noqa: E731  (A operands: K is the last dim)
         qb = lambda t: blockq4(t, -2, block, sc)      # noqa: E731  (B^T operands: K is dim -2)
         return torch.matmul(ah, bh) + torch.matmul(qa(a), qb(bl)) + torch.matmul(qa(al), qb(bt))
