@@ -12,8 +12,10 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-LIB = PKG / "libdiff3d_b200.so"
-STAMP = PKG / ".libdiff3d_b200.stamp"
+# A/B builds: D3D_LIB_OUT=<path>.so D3D_NVCC_EXTRA="-DFOO=1 ..." python -m diff3dhpe_b200.build   (load it with D3D_LIB=<path>.so)
+LIB = Path(os.environ.get("D3D_LIB_OUT", PKG / "libdiff3d_b200.so"))
+STAMP = LIB.with_name("." + LIB.stem + ".stamp")
+EXTRA = os.environ.get("D3D_NVCC_EXTRA", "").split()
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -30,7 +32,7 @@ def _digest() -> str:
     for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "diff3d_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA).encode())
     return h.hexdigest()
 
 
@@ -46,12 +48,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     objs = []
-    build_dir = PKG / "build"
+    build_dir = PKG / ("build" if "D3D_LIB_OUT" not in os.environ else "build_" + LIB.stem)
     build_dir.mkdir(exist_ok=True)
     procs = []
     for src in _sources():
         obj = build_dir / (src.stem + ".o")
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc_path(), *NVCC_FLAGS, *EXTRA, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

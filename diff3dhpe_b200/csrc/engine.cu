@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -98,6 +99,10 @@ struct d3d_handle {
   std::map<int, cudaGraphExec_t> graphs;
   std::map<int, int64_t> graph_launches;
   cudaStream_t cap_stream = nullptr;
+  cudaEvent_t table_event = nullptr;   // recorded after the time table of the current schedule was computed
+  int64_t qkv_rows_dirty = 0;          // high-water mark of token rows ever written into QKV (see prep_batch)
+  float* absmax_dev = nullptr;         // load-time |w| maximum of the last split weight (range guard)
+  double* vel_tmp = nullptr;           // per-call (sum, count) of the velocity error (d3d_pose_metrics_accumulate)
   std::vector<void*> allocs;
 };
 
@@ -159,6 +164,9 @@ int dev_alloc(d3d_handle* h, T** p, int64_t n, bool zero = true) {
   *p = static_cast<T*>(q);
   return 0;
 }
+
+// fp16 main operand: finite up to 65504; the e5m2 images (w 2^-4, (w - hi) 2^8 <= |w| / 8) stay below e5m2's 57344
+constexpr float kMaxWeightAbs = 65504.0f;
 
 int mode_fmt(int gemm_mode) {
   return (gemm_mode == D3D_GEMM_TC_F8C || gemm_mode == D3D_GEMM_SIMT_F8C) ? FMT_F8C : FMT_SPLIT16;
@@ -385,15 +393,40 @@ int run_head(d3d_handle* h, const DdimStep& s, float* y, const float* noise, flo
 }
 
 int ensure_table(d3d_handle* h, cudaStream_t st) {
-  if (!h->cfg.with_time_emb || h->table_valid) return 0;
+  if (!h->cfg.with_time_emb) return 0;
+  if (h->table_valid) {
+    // computed on an earlier caller's stream: order this stream behind it
+    CK(cudaStreamWaitEvent(st, h->table_event, 0));
+    return 0;
+  }
   std::vector<float> tf(h->S);
   for (int i = 0; i < h->S; ++i) tf[i] = static_cast<float>(h->times[i]);
   CK(cudaMemcpyAsync(h->t_f32, tf.data(), sizeof(float) * h->S, cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));   // tf is a stack vector
   int r = compute_time_table(h, h->t_f32, h->S, h->tv_steps, st);
   if (r) return r;
+  CK(cudaEventRecord(h->table_event, st));
   h->table_valid = true;
   return 0;
+}
+
+// Per-call preparation outside any graph: the spatial tcgen05 attention loads 128-row boxes for 119-token units, so
+// the last unit of a batch reads up to 9 rows past T.  They are masked (P = 0), but 0 * Inf/NaN would still poison
+// P.V if those rows held non-finite leftovers of an earlier, larger batch: zero them whenever the batch shrank.
+int prep_batch(d3d_handle* h, int B, cudaStream_t st) {
+  const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  if (T < h->qkv_rows_dirty) {
+    const int64_t rows = std::min<int64_t>(128, h->tok_cap - T);
+    if (rows > 0) CK(cudaMemsetAsync(h->QKV + T * kQkvRow, 0, static_cast<size_t>(rows) * kQkvRow * sizeof(__half), st));
+  }
+  if (T > h->qkv_rows_dirty) h->qkv_rows_dirty = T;
+  return 0;
+}
+
+// per-sample timesteps (int64, device) -> general time table [B, nblk, 512]; everything stays on the stream
+int general_time_table(d3d_handle* h, const int64_t* t_dev, int B, cudaStream_t st) {
+  KL(launch_t_to_f32(t_dev, B, h->t_f32, st));
+  return compute_time_table(h, h->t_f32, B, h->tv_general, st);
 }
 
 int run_sampler(d3d_handle* h, int B, float* trace_y, float* trace_x0, cudaStream_t st) {
@@ -484,6 +517,9 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
   auto body = [&]() -> int {
     int r;
     CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->table_event, cudaEventDisableTiming));
+    if ((r = dev_alloc(h, &h->absmax_dev, 2))) return r;
+    if ((r = dev_alloc(h, &h->vel_tmp, 2))) return r;
     CK(configure_gemm_tc());
     CK(configure_attention());
     CK(configure_attention_mma());
@@ -554,12 +590,14 @@ void d3d_destroy(d3d_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->table_event) cudaEventDestroy(h->table_event);
   delete h;
 }
 
 int d3d_load_weights(d3d_handle* h, const d3d_tensor* tensors, int32_t n) {
   if (!h || !tensors) return -1;
   DeviceGuard guard(h->cfg.device);
+  CK(cudaDeviceSynchronize());   // in-flight work on any (non-blocking) stream may still read the packed weights
   drop_graphs(h);
   h->table_valid = false;
   float* stage = nullptr;   // device staging for tensors that need a transform
@@ -577,8 +615,18 @@ int d3d_load_weights(d3d_handle* h, const d3d_tensor* tensors, int32_t n) {
   auto load_lin_w = [&](Lin& l, const d3d_tensor& t) -> int {
     int r = copy_to(stage, t, static_cast<int64_t>(l.N) * l.K);
     if (r) return r;
-    CK(launch_split(stage, l.hi, l.lo, l.N, l.K, h->fmt, 1, 0));
+    CK(cudaMemset(h->absmax_dev, 0, 2 * sizeof(float)));
+    CK(launch_split(stage, l.hi, l.lo, l.N, l.K, h->fmt, 1, 0, h->absmax_dev));
     CK(cudaDeviceSynchronize());
+    // range guard: the main operand is fp16 and the correction operands are scaled images of it, so a
+    // weight beyond the fp16 range (or a non-finite one) would silently become Inf inside every GEMM.  [0] = max |w|
+    // over finite values, [1] = 1 when a NaN / Inf was seen.
+    float am[2] = {0.f, 0.f};
+    CK(cudaMemcpy(am, h->absmax_dev, sizeof(am), cudaMemcpyDeviceToHost));
+    if (am[1] != 0.f) return fail(h, -12, std::string("tensor '") + t.name + "' holds NaN / Inf");
+    if (am[0] > kMaxWeightAbs)
+      return fail(h, -12, std::string("tensor '") + t.name + "': max |w| = " + std::to_string(am[0]) +
+                              " exceeds the fp16 operand range (" + std::to_string(kMaxWeightAbs) + ")");
     l.have_w = true;
     return 0;
   };
@@ -650,12 +698,13 @@ int d3d_set_schedule(d3d_handle* h, int32_t S, const int32_t* times, const float
   if (!h || !times || !ac || !s1m) return -1;
   if (S < 1 || S > 1024) return fail(h, -2, "sampling_timesteps out of range [1,1024]");
   DeviceGuard guard(h->cfg.device);
+  // a failed call must not leave a half-written schedule behind: nothing is usable until everything validated
+  h->have_schedule = false;
   drop_graphs(h);
   h->table_valid = false;
-  h->S = S;
-  h->times.assign(times, times + S + 1);
-  h->steps.resize(S);
-  h->need_noise = false;
+  if (S > h->t_rows_cap) return fail(h, -2, "sampling_timesteps exceeds the time-MLP scratch rows");
+  std::vector<DdimStep> steps(S);
+  bool need_noise = false;
   for (int i = 0; i < S; ++i) {
     const int t = times[i], tn = times[i + 1];
     if (t < 0 || t >= T || tn >= T) return fail(h, -2, "time index outside the schedule buffers");
@@ -680,16 +729,20 @@ int d3d_set_schedule(d3d_handle* h, int32_t S, const int32_t* times, const float
       s.alpha = alpha;
       s.sqrt_alpha_next = sqrtf(alpha_next);
       s.sqrt_one_minus = s1m[t];
-      if (s.sigma != 0.0f) h->need_noise = true;
+      if (s.sigma != 0.0f) need_noise = true;
     }
-    h->steps[i] = s;
+    steps[i] = s;
   }
   if (S > h->tv_cap) {
+    CK(cudaDeviceSynchronize());     // the old table may still be read by in-flight work
     int r = dev_alloc(h, &h->tv_steps, static_cast<int64_t>(S) * h->nblk * kC);
     if (r) return r;
     h->tv_cap = S;
   }
-  if (S > h->t_rows_cap) return fail(h, -2, "sampling_timesteps exceeds the time-MLP scratch rows");
+  h->S = S;
+  h->times.assign(times, times + S + 1);
+  h->steps.swap(steps);
+  h->need_noise = need_noise;
   h->have_schedule = true;
   return 0;
 }
@@ -701,16 +754,10 @@ int d3d_forward_denoise(d3d_handle* h, const float* x5, const int64_t* t_dev, fl
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float* tv = nullptr;
+  if ((r = prep_batch(h, B, st))) return r;
   if (h->cfg.with_time_emb) {
-    // per-sample t: int64 -> fp32 on the host side of the stream (B values), then the general table
-    std::vector<int64_t> ti(B);
-    CK(cudaMemcpyAsync(ti.data(), t_dev, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    std::vector<float> tf(B);
-    for (int i = 0; i < B; ++i) tf[i] = static_cast<float>(ti[i]);
-    CK(cudaMemcpyAsync(h->t_f32, tf.data(), sizeof(float) * B, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    if ((r = compute_time_table(h, h->t_f32, B, h->tv_general, st))) return r;
+    // per-sample t (the p_losses call of DIFF:392-419): converted and embedded on the device, no host round trip
+    if ((r = general_time_table(h, t_dev, B, st))) return r;
     tv = h->tv_general;
   }
   if ((r = run_blocks(h, nullptr, nullptr, x5, tv, static_cast<int64_t>(h->nblk) * kC, B, h->nblk, st))) return r;
@@ -726,15 +773,10 @@ int d3d_debug_forward_blocks(d3d_handle* h, const float* x5, const int64_t* t_de
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float* tv = nullptr;
+  if ((r = prep_batch(h, B, st))) return r;
   if (h->cfg.with_time_emb) {
-    std::vector<int64_t> ti(B);
-    CK(cudaMemcpyAsync(ti.data(), t_dev, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    std::vector<float> tf(B);
-    for (int i = 0; i < B; ++i) tf[i] = static_cast<float>(ti[i]);
-    CK(cudaMemcpyAsync(h->t_f32, tf.data(), sizeof(float) * B, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    if ((r = compute_time_table(h, h->t_f32, B, h->tv_general, st))) return r;
+    if (!t_dev) return fail(h, -1, "null argument");
+    if ((r = general_time_table(h, t_dev, B, st))) return r;
     tv = h->tv_general;
   }
   if ((r = run_blocks(h, nullptr, nullptr, x5, tv, static_cast<int64_t>(h->nblk) * kC, B, n_blocks, st))) return r;
@@ -793,6 +835,7 @@ int d3d_ddim_sample(d3d_handle* h, const float* x2d, const float* noise0, const 
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  if ((r = prep_batch(h, B, st))) return r;
   CK(cudaMemcpyAsync(h->in_x2d, x2d, sizeof(float) * T * 2, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->y, noise0, sizeof(float) * T * 3, cudaMemcpyDeviceToDevice, st));
   if (h->need_noise && h->S > 1) {
@@ -814,6 +857,7 @@ int d3d_ddim_sample_host(d3d_handle* h, const float* x2d, const float* noise0, c
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  if ((r = prep_batch(h, B, st))) return r;
   CK(cudaMemcpyAsync(h->in_x2d, x2d, sizeof(float) * T * 2, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->y, noise0, sizeof(float) * T * 3, cudaMemcpyHostToDevice, st));
   if (h->need_noise && h->S > 1) {
@@ -907,7 +951,7 @@ int d3d_pose_metrics_accumulate(d3d_handle* h, const float* pred, const float* g
   if (!h || !pred || !gt || !acc) return -1;
   if (n_sel < 0) return fail(h, -2, "n_sel < 0");
   DeviceGuard guard(h->cfg.device);
-  KL(launch_pose_metrics(pred, gt, frame_index, n_sel, h->J, acc, static_cast<cudaStream_t>(stream)));
+  KL(launch_pose_metrics(pred, gt, frame_index, n_sel, h->J, acc, h->vel_tmp, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -952,6 +996,7 @@ int d3d_op_attention(d3d_handle* h, const float* qkv, float* out, int32_t B, int
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // the hot path receives q | k | v_hi | v_lo fp16 rows from the qkv GEMM epilogue; here they are packed from fp32
+  { int r0 = prep_batch(h, B, st); if (r0) return r0; }
   KL(launch_pack_qkv16(qkv, h->QKV, static_cast<int64_t>(B) * h->F * h->J, st));
   return run_attention(h, h->QKV, nullptr, nullptr, out, B, spatial != 0, attn_mode, st);
 }
@@ -963,6 +1008,7 @@ int d3d_debug_attention_operand(d3d_handle* h, const float* qkv, void* hi_out, v
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
+  { int r0 = prep_batch(h, B, st); if (r0) return r0; }
   KL(launch_pack_qkv16(qkv, h->QKV, T, st));
   int r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial != 0, attn_mode, st);
   if (r) return r;

@@ -43,7 +43,10 @@ constexpr int kEpilogueRegs = 104;
 // forever (first attempt: 40 / 112 -> deadlock on the GPU)
 static_assert(4 * 128 * (kEpilogueRegs - 96) <= 128 * (96 - kProducerRegs), "setmaxnreg pool overdrawn");
 constexpr int kTileBytesA = BM * BK * 2;     // 16 KiB
-constexpr int kSmemBudget = 200 * 1024;
+#ifndef D3D_GEMM_SMEM_BUDGET_KB
+#define D3D_GEMM_SMEM_BUDGET_KB 200
+#endif
+constexpr int kSmemBudget = D3D_GEMM_SMEM_BUDGET_KB * 1024;   // ring + epilogue staging (A/B builds: fewer ring stages)
 
 // EW = epilogue warps per CTA: 8 (two warps per TMEM lane quadrant, 128 columns each) or 16 (four per quadrant, 64
 // columns each).  The bias+GELU+split epilogue of fc1 costs ~25 instructions per output element; with 8 warps it, not
@@ -55,7 +58,7 @@ struct Cfg {
   static constexpr int kThreads = 128 + 32 * EW;
   static constexpr int kStageBytes = (PASSES == 3 ? 2 : 1) * (kTileBytesA + kTileBytesB);
   static constexpr int kStagingBytes = EW * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
-  static constexpr int kRing = kSmemBudget + 8 * 4096 - kStagingBytes;
+  static constexpr int kRing = (PASSES == 2 ? kSmemBudget : 200 * 1024) + 8 * 4096 - kStagingBytes;
   static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;   // 256 or 512 (power of two)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;

@@ -76,8 +76,10 @@ struct LnParams {
 
 // fp32 [rows, K] -> GEMM operand arrays (hi + second, see operand.cuh; fmt = OperandFmt; weights at load time,
 // op-level tests) and back (activation operands only).
+// absmax (optional, device float[2], zeroed by the caller): [0] = max |x| over the finite inputs, [1] = 1 if any input
+// was NaN / Inf -- the load-time range guard of d3d_load_weights.
 cudaError_t launch_split(const float* in, __half* hi, __half* second, int64_t rows, int K, int fmt, int is_weight,
-                         cudaStream_t st);
+                         cudaStream_t st, float* absmax = nullptr);
 cudaError_t launch_merge(const __half* hi, const __half* second, float* out, int64_t rows, int K, int fmt,
                          cudaStream_t st);
 
@@ -113,8 +115,9 @@ cudaError_t launch_mpjpe(const float* pred, const float* gt, const uint8_t* mask
                          double* acc, cudaStream_t st);
 
 // Protocol #1/#2/#3 + velocity sums (metrics.cu): acc[6] fp64 = sum mpjpe, sum n_mpjpe, sum p_mpjpe, joints, sum vel, vel joints
+// vel_tmp: device double[2] scratch owned by the handle (per-call velocity sum / count before the reference's weighting)
 cudaError_t launch_pose_metrics(const float* pred, const float* gt, const int64_t* sel /*or null*/, int64_t n_sel, int J,
-                                double* acc, cudaStream_t st);
+                                double* acc, double* vel_tmp, cudaStream_t st);
 
 // ------------------------------------------------------------------ windowing (packed sequences <-> F-frame windows)
 cudaError_t launch_window_gather(const float* seq2d, const int64_t* start, const int32_t* perm /*[J] device*/, float* x2d,
@@ -154,6 +157,8 @@ cudaError_t launch_attn_generic_simt(const __half* qkv, __half* o_hi, __half* o_
 cudaError_t launch_pack_qkv16(const float* qkv_f32, __half* out, int64_t T, cudaStream_t st);
 
 // ------------------------------------------------------------------ time embedding
+// out[r] = float(t[r]): the per-sample timesteps of forward_denoise stay on the device (no host round trip)
+cudaError_t launch_t_to_f32(const int64_t* t, int R, float* out, cudaStream_t st);
 // e[r, 0:256] = sin(t_r * f_i), e[r, 256:512] = cos(t_r * f_i)   (MODEL:29-36)
 cudaError_t launch_sincos(const float* t, int R, float* out, cudaStream_t st);
 // out[r, n] = act_in(in[r, :]) . W[n, :] + b[n];  act_in: 0 none, 1 gelu(erf), 2 silu.  out row stride given.

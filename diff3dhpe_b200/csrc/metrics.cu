@@ -36,9 +36,11 @@ __device__ __forceinline__ void jacobi_rotate(double (&a)[3][3], double (&v)[3][
 }
 
 // acc[0] += sum_j |p - g|, acc[1] += sum_j |s p - g| (n_mpjpe), acc[2] += sum_j |aligned(p) - g| (p_mpjpe),
-// acc[3] += joints counted; acc[4] += sum of velocity-error norms over consecutive SELECTED frames, acc[5] += their count
+// acc[3] += joints counted; vel_tmp[0] += sum of velocity-error norms over consecutive SELECTED frames, vel_tmp[1] +=
+// their count (this call only; vel_finalize_kernel folds them into acc[4], acc[5])
 __global__ void pose_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
-                                    const int64_t* __restrict__ sel, int64_t n_sel, int J, double* __restrict__ acc) {
+                                    const int64_t* __restrict__ sel, int64_t n_sel, int J, double* __restrict__ acc,
+                                    double* __restrict__ vel_tmp) {
   double s_mp = 0.0, s_n = 0.0, s_p = 0.0, s_cnt = 0.0, s_v = 0.0, s_vcnt = 0.0;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_sel;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -165,19 +167,31 @@ __global__ void pose_metrics_kernel(const float* __restrict__ pred, const float*
     double v = vals[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(acc + k, v);
+    // the velocity pair is per CALL: finalised with the reference's weighting by vel_finalize_kernel
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(k < 4 ? acc + k : vel_tmp + (k - 4), v);
   }
+}
+
+// evaluate() weights every batch's mean velocity error by its frame count (RUN:610-614:
+// `epoch_loss_3d_vel += N_b * mean_velocity_error(batch)`, divided by sum N_b at the end), and the mean inside a batch
+// runs over its (N_b - 1) * J frame differences (LOSS:139-142): acc[4] += N_b * tmp[0] / tmp[1], acc[5] += N_b.
+__global__ void vel_finalize_kernel(double* __restrict__ acc, double* __restrict__ vel_tmp, double n_frames) {
+  if (vel_tmp[1] > 0.0) acc[4] += n_frames * (vel_tmp[0] / vel_tmp[1]);
+  acc[5] += n_frames;
+  vel_tmp[0] = 0.0;
+  vel_tmp[1] = 0.0;
 }
 
 }  // namespace
 
 cudaError_t launch_pose_metrics(const float* pred, const float* gt, const int64_t* sel, int64_t n_sel, int J, double* acc,
-                                cudaStream_t st) {
+                                double* vel_tmp, cudaStream_t st) {
   if (n_sel <= 0) return cudaSuccess;
   if (J < 1 || J > kMaxJ) return cudaErrorInvalidValue;
   int64_t g = (n_sel + 127) / 128;
   if (g > 148 * 16) g = 148 * 16;
-  pose_metrics_kernel<<<static_cast<unsigned>(g), 128, 0, st>>>(pred, gt, sel, n_sel, J, acc);
+  pose_metrics_kernel<<<static_cast<unsigned>(g), 128, 0, st>>>(pred, gt, sel, n_sel, J, acc, vel_tmp);
+  vel_finalize_kernel<<<1, 1, 0, st>>>(acc, vel_tmp, static_cast<double>(n_sel));
   return cudaGetLastError();
 }
 

@@ -257,10 +257,13 @@ __global__ void mpjpe_kernel(const float* __restrict__ pred, const float* __rest
 
 // fp32 [rows, K] -> operand arrays.  is_weight selects the weight-side e5m2 scales of FMT_F8C.
 __global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ second,
-                             int64_t n, int K, int fmt, int is_weight) {
+                             int64_t n, int K, int fmt, int is_weight, float* __restrict__ absmax) {
+  float amax = 0.f;
+  bool bad = false;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float v = in[i];
+    if (isfinite(v)) amax = fmaxf(amax, fabsf(v)); else bad = true;
     const __half h = __float2half_rn(v);
     const float l = v - __half2float(h);
     hi[i] = h;
@@ -276,6 +279,12 @@ __global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ 
       c8[col] = static_cast<uint8_t>(op_e5m2x2(first, 0.f) & 0xff);
       c8[K + col] = static_cast<uint8_t>(op_e5m2x2(secnd, 0.f) & 0xff);
     }
+  }
+  if (absmax) {       // non-negative floats order like their bit patterns
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(amax));
+    if (bad) absmax[1] = 1.0f;
   }
 }
 // activation operand -> fp32 (hi + lo); for FMT_F8C the lo term comes back from its e5m2 image
@@ -304,10 +313,10 @@ inline unsigned flat_grid(int64_t n) {
 }  // namespace
 
 cudaError_t launch_split(const float* in, __half* hi, __half* second, int64_t rows, int K, int fmt, int is_weight,
-                         cudaStream_t st) {
+                         cudaStream_t st, float* absmax) {
   const int64_t n = rows * K;
   if (n <= 0) return cudaSuccess;
-  split_kernel<<<flat_grid(n), 256, 0, st>>>(in, hi, second, n, K, fmt, is_weight);
+  split_kernel<<<flat_grid(n), 256, 0, st>>>(in, hi, second, n, K, fmt, is_weight, absmax);
   return cudaGetLastError();
 }
 cudaError_t launch_merge(const __half* hi, const __half* second, float* out, int64_t rows, int K, int fmt,

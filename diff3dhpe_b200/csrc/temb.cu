@@ -21,6 +21,12 @@ __global__ void sincos_kernel(const float* __restrict__ t, int R, float* __restr
   out[r * 512 + 256 + k] = static_cast<float>(cos(static_cast<double>(arg)));
 }
 
+// per-sample timesteps of forward_denoise (int64 on the device, MODEL:33 multiplies them into fp32) -> fp32
+__global__ void t_to_f32_kernel(const int64_t* __restrict__ t, int R, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) out[i] = static_cast<float>(t[i]);
+}
+
 __device__ __forceinline__ float act(float v, int mode) {
   if (mode == 1) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // nn.GELU (erf)
   if (mode == 2) return v / (1.0f + expf(-v));                                   // nn.SiLU
@@ -51,6 +57,12 @@ small_linear_kernel(const float* __restrict__ in, int R, int K, const float* __r
 }
 
 }  // namespace
+
+cudaError_t launch_t_to_f32(const int64_t* t, int R, float* out, cudaStream_t st) {
+  if (R <= 0) return cudaSuccess;
+  t_to_f32_kernel<<<(R + 255) / 256, 256, 0, st>>>(t, R, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_sincos(const float* t, int R, float* out, cudaStream_t st) {
   if (R <= 0) return cudaSuccess;

@@ -66,9 +66,12 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------ weights / schedule
-    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], raw_names: bool = False):
         """Accepts the reference's keys, with or without 'module.' / 'model.' prefixes; schedule buffers
-        (top-level keys such as 'alphas_cumprod') are skipped as RUN:226-235 does."""
+        (top-level keys such as 'alphas_cumprod') are skipped as RUN:226-235 does.  `raw_names=True` hands the
+        checkpoint's own key strings ('module.model.STEblocks.0...') across the ABI and lets d3d_load_weights strip the
+        prefixes itself.  Raises RuntimeError (code -12) when a linear weight is non-finite or outside the fp16
+        operand range."""
         keep, descs = [], []
         for k, v in sd.items():
             name = k
@@ -79,7 +82,7 @@ class Engine:
             elif "." not in name and name not in ("Spatial_pos_embed", "Temporal_pos_embed"):
                 continue                      # GaussianDiffusion buffers
             t = v.detach().to(dtype=torch.float32).contiguous()
-            keep.append((name.encode(), t))
+            keep.append(((k if raw_names else name).encode(), t))
         arr = (_lib.TensorDesc * len(keep))()
         for i, (name, t) in enumerate(keep):
             arr[i].name = name
@@ -198,8 +201,9 @@ class Engine:
 
     def pose_metrics_accumulate(self, pred: torch.Tensor, gt: torch.Tensor, acc: torch.Tensor,
                                 frame_index: Optional[torch.Tensor] = None):
-        """acc: fp64[6] on the device: sums / counts of MPJPE, N-MPJPE, P-MPJPE and the velocity error over the
-        frames listed in frame_index (None = all, in order); see include/diff3d_b200.h."""
+        """acc: fp64[6] on the device: sums / counts of MPJPE, N-MPJPE, P-MPJPE over the frames listed in frame_index
+        (None = all, in order) and the velocity error weighted per call as evaluate() weights its batches
+        (RUN:610-614); one call = one batch; see include/diff3d_b200.h."""
         _check_dev(pred, self.device, name="pred")
         _check_dev(gt, self.device, tuple(pred.shape), name="gt")
         _check_dev(acc, self.device, (6,), torch.float64, "acc")

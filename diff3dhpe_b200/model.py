@@ -89,6 +89,7 @@ class ConditionalDiffusionMixSTES2SGRANDLinLift(nn.Module):
         self._engine: Optional[Engine] = None
         self._engine_key = None
         self._weights_key = None
+        self._weights_epoch = 0
         self.gemm_mode = _lib.GEMM_TC_F8C
         self.attn_mode = _lib.ATTN_DEFAULT
         self.use_graph = True
@@ -96,7 +97,19 @@ class ConditionalDiffusionMixSTES2SGRANDLinLift(nn.Module):
 
     # ------------------------------------------------------------------ engine management
     def _weights_fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self._weights_epoch,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate_weights(self):
+        """Forces a re-upload (re-packing) of the weights at the next call.  The engine notices parameter updates through
+        `(data_ptr, _version)` of every parameter, which covers optimizer steps, `load_state_dict`, `copy_`, `.to()`
+        and in-place ops on the parameter itself -- but NOT writes through `.data` (`p.data.copy_(ema)`, EMA / SWA
+        weight swaps), which do not bump `_version`: call this after such a write.  (A content checksum would need a
+        device -> host synchronisation on every sampler call, which the hot path must not have.)"""
+        self._weights_epoch += 1
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._weights_epoch += 1
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def engine(self, batch: int = 1) -> Engine:
         """Returns the Engine for the device the parameters live on, (re)building it when the device, the

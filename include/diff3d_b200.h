@@ -133,8 +133,11 @@ D3D_API int d3d_tta_merge(d3d_handle* h, const float* y_dev, const float* y_flip
  *   [1] sum_j ||s pred - gt||, s per frame        n_mpjpe (common/loss.py:84-94)
  *   [2] sum_j ||procrustes(pred) - gt||           p_mpjpe (common/loss.py:43-82; 3x3 SVD per frame in fp64)
  *   [3] joints counted
- *   [4] sum_j ||d pred - d gt|| over consecutive listed frames, [5] their joint count   (mean_velocity_error, :133-142)
- * pred_dev / gt_dev: [n_frames, J, 3].  Each error is sum / count, as the reference's per-batch means are. */
+ *   [4] sum over calls of n_sel * mean_velocity_error(this call's listed frames)   (common/loss.py:133-142: the mean runs
+ *       over the (n_sel - 1) * J differences of consecutive listed frames), [5] sum over calls of n_sel -- the
+ *       reference's own weighting, `epoch_loss_3d_vel += N_b * mean_velocity_error(batch)` over `N += N_b` (RUN:610-614)
+ * pred_dev / gt_dev: [n_frames, J, 3].  mpjpe = [0]/[3], n_mpjpe = [1]/[3], p_mpjpe = [2]/[3], velocity = [4]/[5];
+ * one call = one batch of evaluate(). */
 D3D_API int d3d_pose_metrics_accumulate(d3d_handle* h, const float* pred_dev, const float* gt_dev,
                                 const int64_t* frame_index_dev, int64_t n_sel, double* acc_dev, void* stream);
 

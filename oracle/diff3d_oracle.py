@@ -238,6 +238,58 @@ def ddim_sample_loop(sd: Dict[str, Tensor], x2d: Tensor, y_T: Tensor, step_noise
 
 
 # --------------------------------------------------------------------------------------------------
+# forward() eval branch with output_loss / repeat_n (DIFF:360-366, 392-419, 421-449)
+# --------------------------------------------------------------------------------------------------
+def q_sample(bufs: Dict[str, Tensor], x_start: Tensor, t: Tensor, noise: Tensor) -> Tensor:
+    """DIFF:360-366: sqrt(abar_t) x0 + sqrt(1 - abar_t) noise with per-sample t (``extract`` = gather + reshape)."""
+    shape = (t.shape[0],) + (1,) * (x_start.dim() - 1)
+    return (bufs["sqrt_alphas_cumprod"].gather(-1, t).reshape(shape) * x_start +
+            bufs["sqrt_one_minus_alphas_cumprod"].gather(-1, t).reshape(shape) * noise)
+
+
+def p_losses(sd: Dict[str, Tensor], x_start: Tensor, pose_2d: Tensor, t: Tensor, noise: Tensor, *,
+             timesteps: int = 1000, beta_schedule: str = "cosine", loss_type: str = "l2", clip_loss: bool = True,
+             heads: int = 8) -> Tensor:
+    """DIFF:392-419 with the two random draws made explicit: ``t`` is the reference's
+    ``torch.randint(0, T, (b,))`` and ``noise`` its ``randn_like(x_start)`` (drawn in that order).  One denoiser call
+    with a per-sample t, then the un-reduced l1 / l2 error times ``1 + abar_t / sqrt(1 - abar_t)`` (clamped to 3 when
+    ``clipLoss``).  Returns [B,F,J,3]."""
+    sd = strip_prefix(sd) if any(k.startswith(("module.", "model.")) for k in sd) else sd
+    bufs = schedule_buffers(timesteps, beta_schedule)
+    x_noisy = q_sample(bufs, x_start, t, noise)
+    model_out = forward_denoise(sd, torch.cat([pose_2d, x_noisy], dim=-1), t, heads)
+    coef = 1.0 + bufs["alphas_cumprod"][t].view(-1, 1, 1, 1) / bufs["sqrt_one_minus_alphas_cumprod"][t].view(-1, 1, 1, 1)
+    if clip_loss:
+        coef = torch.clamp(coef, max=3.0)
+    if loss_type == "l1":
+        err = F.l1_loss(model_out, x_start, reduction="none")
+    elif loss_type == "l2":
+        err = F.mse_loss(model_out, x_start, reduction="none")
+    else:
+        raise ValueError(f"invalid loss type {loss_type}")
+    return err * coef
+
+
+def forward_eval(sd: Dict[str, Tensor], clean_3d_pose: Tensor, noisy_2d_pose: Tensor, y_T: Tensor,
+                 step_noise: Optional[Tensor], *, repeat_n: int = 1, loss_draws: Optional[Tuple[Tensor, Tensor]] = None,
+                 **kw):
+    """GaussianDiffusion.forward, eval branch (DIFF:427-449).  ``loss_draws = (t, noise)`` selects ``output_loss=True``
+    (the default of the 3DHP evaluate(), RUN3:517-520); the 2D input is tiled ``repeat_n`` times along the batch
+    (DIFF:434), the sampler runs on the ``repeat_n * B`` clips (``y_T`` / ``step_noise`` have that batch) and the
+    prediction is the mean over the repeats (DIFF:448).  Returns (loss or None, pred [B,F,J,3])."""
+    loss_kw = {k: kw.pop(k) for k in ("loss_type", "clip_loss") if k in kw}
+    loss = None
+    if loss_draws is not None:
+        loss = p_losses(sd, clean_3d_pose, noisy_2d_pose, loss_draws[0], loss_draws[1],
+                        timesteps=kw.get("timesteps", 1000), beta_schedule=kw.get("beta_schedule", "cosine"), **loss_kw)
+    b, f, p, _ = clean_3d_pose.shape
+    x = noisy_2d_pose.repeat(repeat_n, 1, 1, 1)
+    pred = ddim_sample_loop(sd, x, y_T, step_noise, **kw)
+    pred = torch.mean(pred.view(repeat_n, b, f, p, -1), dim=0, keepdim=True).squeeze(0)
+    return loss, pred
+
+
+# --------------------------------------------------------------------------------------------------
 # flip-TTA tail and MPJPE (RUN:562-590, LOSS:15-27)
 # --------------------------------------------------------------------------------------------------
 def flip_2d(x2d: Tensor, left=H36M_JOINTS_LEFT, right=H36M_JOINTS_RIGHT) -> Tensor:

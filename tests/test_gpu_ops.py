@@ -238,7 +238,7 @@ def test_pose_metrics_golden(golden):
     e1, e2, e3, ev = Engine.pose_metrics(acc)
     assert abs(e1 - float(g["mpjpe"])) < 2e-7 and abs(e3 - float(g["n_mpjpe"])) < 2e-7
     assert abs(e2 - float(g["p_mpjpe"])) < 2e-7 and abs(ev - float(g["velocity"])) < 2e-7
-    assert acc[3].item() == 300 * 17 and acc[5].item() == 299 * 17
+    assert acc[3].item() == 300 * 17 and acc[5].item() == 300
     sel = torch.tensor([i for i in range(300) if i % 7 != 3], dtype=torch.int64)
     acc2 = torch.zeros(6, dtype=torch.float64, device="cuda")
     eng.pose_metrics_accumulate(pred, gt, acc2, sel[:100].cuda().contiguous())
@@ -249,10 +249,11 @@ def test_pose_metrics_golden(golden):
     e1, e2, e3, _ = Engine.pose_metrics(acc2)
     assert abs(e1 - oracle.mpjpe(tp, tg).item()) < 2e-7 and abs(e3 - oracle.n_mpjpe(tp, tg).item()) < 2e-7
     assert abs(e2 - oracle.p_mpjpe(p, t)) < 2e-7
-    # velocity is per call (np.diff inside one batch): the two calls see 100 and 157 frames
+    # velocity: per call (np.diff inside one batch) and weighted by the batch's frame count, as evaluate() does
+    # (RUN:610-614: epoch_loss_3d_vel += N_b * mean_velocity_error(batch); divided by sum N_b)
     n_a, n_b = 100, sel.numel() - 100
-    v = (oracle.mean_velocity_error(p[:n_a], t[:n_a]) * (n_a - 1) + oracle.mean_velocity_error(p[n_a:], t[n_a:]) * (n_b - 1))
-    assert abs(acc2[4].item() / 17 - v) < 1e-5 and acc2[5].item() == (n_a - 1 + n_b - 1) * 17
+    v = (oracle.mean_velocity_error(p[:n_a], t[:n_a]) * n_a + oracle.mean_velocity_error(p[n_a:], t[n_a:]) * n_b) / (n_a + n_b)
+    assert abs(Engine.pose_metrics(acc2)[3] - v) < 1e-6 and acc2[5].item() == n_a + n_b
 
 
 def test_time_table_golden(golden):
@@ -280,6 +281,19 @@ def test_residual_stream_after_blocks_golden(golden, gemm_mode):
     # q, k (and P, V inside P.V) are fp16 in the attention kernels: 1e-3-level effect on a stream of magnitude ~5
     assert np.abs(x1 - g["x_after_1"]).max() < 4e-3
     assert np.abs(x2 - g["x_after_2"]).max() < 4e-3
+
+
+def test_tta_merge_3dhp_joint_lists_golden(eng27, golden):
+    """The 3DHP evaluate()'s flip-TTA tail (RUN3:522-529) with the MPI-INF-3DHP joint lists
+    (common/mpiinf3dhp_dataset.py:17-18), bit for bit against the reference's own index arithmetic."""
+    g = golden("tta_tail_3dhp")
+    assert g["left"].tolist() == synthetic.MPI3DHP_JOINTS_LEFT and g["right"].tolist() == synthetic.MPI3DHP_JOINTS_RIGHT
+    y, yf = torch.from_numpy(g["y"]).cuda(), torch.from_numpy(g["yf"]).cuda()
+    merged = eng27.tta_merge(y, yf, synthetic.MPI3DHP_JOINTS_LEFT, synthetic.MPI3DHP_JOINTS_RIGHT, float(g["scale"]))
+    assert np.array_equal(merged.cpu().numpy(), g["merged"])
+    # the H36M lists on the same tensors give a different answer (the lists are not interchangeable)
+    other = eng27.tta_merge(y, yf, synthetic.H36M_JOINTS_LEFT, synthetic.H36M_JOINTS_RIGHT, float(g["scale"]))
+    assert not np.array_equal(other.cpu().numpy(), g["merged"])
 
 
 def test_tta_merge_and_mpjpe_golden(eng27, golden):

@@ -81,6 +81,38 @@ def test_tta_tail_golden(golden):
     assert abs(e.item() - float(g["mpjpe"])) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["forward_f27_b3_s2_loss", "forward_f9_b2_s2_rep2_l1"])
+def test_forward_output_loss_and_repeat_n_golden(golden, name):
+    """q_sample / p_losses / the eval branch of forward() with repeat_n (DIFF:360-366, 392-419, 427-449) against the
+    imported reference's loss tensor and prediction (tools/make_golden.py forward_case pins randint and every normal
+    draw)."""
+    g = golden(name)
+    F, B, S, rep = int(g["F"]), int(g["B"]), int(g["S"]), int(g["repeat_n"])
+    sd = _sd(F)
+    x2d, gt = synthetic.make_inputs(B, F)
+    y_T, steps = synthetic.make_noise(rep * B, F, S)
+    loss_noise = torch.randn(B, F, 17, 3, generator=torch.Generator().manual_seed(777))
+    with torch.no_grad():
+        loss, pred = oracle.forward_eval(sd, gt, x2d, y_T, steps, repeat_n=rep,
+                                         loss_draws=(torch.tensor(g["t"], dtype=torch.long), loss_noise),
+                                         sampling_timesteps=S, loss_type=str(g["loss_type"]), clip_loss=bool(g["clip_loss"]))
+    assert pred.shape == (B, F, 17, 3)
+    assert np.abs(pred.numpy() - g["pred"]).max() < 5e-5
+    assert np.abs(loss.numpy() - g["loss"]).max() < 5e-5 * max(1.0, float(np.abs(g["loss"]).max()))
+    # the clamp of DIFF:413-414 is active in the first case (t = 7: 1 + abar / sqrt(1 - abar) > 3) and off in the second
+    bufs = oracle.schedule_buffers(1000)
+    coef = 1.0 + bufs["alphas_cumprod"][torch.tensor(g["t"])] / bufs["sqrt_one_minus_alphas_cumprod"][torch.tensor(g["t"])]
+    assert (coef.max() > 3.0) and bool(g["clip_loss"]) == (name == "forward_f27_b3_s2_loss")
+
+
+def test_tta_tail_3dhp_golden(golden):
+    g = golden("tta_tail_3dhp")
+    merged = oracle.tta_merge(torch.from_numpy(g["y"]), torch.from_numpy(g["yf"]), float(g["scale"]),
+                              oracle.MPI3DHP_JOINTS_LEFT, oracle.MPI3DHP_JOINTS_RIGHT)
+    assert np.array_equal(merged.numpy(), g["merged"])
+    assert g["left"].tolist() == oracle.MPI3DHP_JOINTS_LEFT and g["right"].tolist() == oracle.MPI3DHP_JOINTS_RIGHT
+
+
 def test_draw_order_matches_reference_count():
     y_T, steps = oracle.draw_noise((2, 9, 17, 3), 9, torch.Generator().manual_seed(3))
     assert y_T.shape == (2, 9, 17, 3) and steps.shape == (8, 2, 9, 17, 3)

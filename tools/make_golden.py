@@ -108,6 +108,71 @@ def denoise_case(name, F, B, tvals, with_time_emb=True):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), out=out.numpy(), t=np.array(tvals), F=F, B=B, **extra)
 
 
+class FixedRandint:
+    """Feeds a fixed t tensor to the reference's torch.randint call in p_losses (DIFF:395)."""
+
+    def __init__(self, t):
+        self.t, self.calls = t, 0
+
+    def __enter__(self):
+        self._randint = torch.randint
+
+        def fake(*a, **k):
+            self.calls += 1
+            return self.t.clone()
+        torch.randint = fake
+        return self
+
+    def __exit__(self, *exc):
+        torch.randint = self._randint
+
+
+def forward_case(name, F, B, S, repeat_n, tvals, loss_type="l2", clip_loss=True, with_time_emb=True):
+    """GaussianDiffusion.forward in eval mode with output_loss=True (the 3DHP evaluate() default, RUN3:517-520) and
+    repeat_n (DIFF:434,448): the reference's loss tensor and prediction with every random draw pinned."""
+    mine = synthetic.make_model(F, with_time_emb=with_time_emb)
+    sd = {k: v.detach().clone() for k, v in mine.state_dict().items()}
+    ref = ref_model_from(mine, F, with_time_emb)
+    diff = RefDiffusion(ref, timesteps=1000, sampling_timesteps=S, loss_type=loss_type, clip_denoised=True,
+                        beta_schedule='cosine', ddim_sampling_eta=0.0, clipLoss=clip_loss).eval()
+    x2d, gt = synthetic.make_inputs(B, F)
+    y_T, steps = synthetic.make_noise(repeat_n * B, F, S)
+    g = torch.Generator().manual_seed(777)
+    loss_noise = torch.randn(B, F, 17, 3, generator=g)
+    t = torch.tensor(tvals, dtype=torch.long)
+    # draw order inside forward(): randint (DIFF:395), randn_like (DIFF:397), then the sampler's S draws
+    with torch.no_grad(), FixedRandint(t) as fr, FixedNoise(y_T, steps) as fn:
+        fn.queue.insert(0, loss_noise)
+        loss, pred = diff(clean_3d_pose=gt, noisy_2d_pose=x2d, repeat_n=repeat_n)
+        assert fr.calls == 1 and len(fn.queue) == 0
+    with torch.no_grad():
+        oloss, opred = oracle.forward_eval(sd, gt, x2d, y_T, steps, repeat_n=repeat_n, loss_draws=(t, loss_noise),
+                                           sampling_timesteps=S, loss_type=loss_type, clip_loss=clip_loss)
+    assert torch.equal(oloss, loss) and torch.equal(opred, pred), f"{name}: oracle forward() != reference"
+    print(f"{name}: oracle == reference; mean loss {loss.mean():.5f}, |pred|max {pred.abs().max():.3f}")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), loss=loss.numpy(), pred=pred.numpy(), t=np.array(tvals), F=F,
+                        B=B, S=S, repeat_n=repeat_n, loss_type=loss_type, clip_loss=int(clip_loss),
+                        with_time_emb=int(with_time_emb))
+
+
+def tail_case_3dhp():
+    """The flip-TTA tail of the 3DHP evaluate() (RUN3:522-529) with the MPI-INF-3DHP joint lists imported from the
+    reference (common/mpiinf3dhp_dataset.py:17-18)."""
+    sys.path.insert(0, "/root/reference")
+    from common.mpiinf3dhp_dataset import joints_left, joints_right
+    assert joints_left == synthetic.MPI3DHP_JOINTS_LEFT and joints_right == synthetic.MPI3DHP_JOINTS_RIGHT
+    g = torch.Generator().manual_seed(8)
+    y = torch.randn(2, 27, 17, 3, generator=g)
+    yf = torch.randn(2, 27, 17, 3, generator=g)
+    pf = yf.clone()
+    pf[:, :, :, 0] *= -1
+    pf[:, :, joints_left + joints_right] = pf[:, :, joints_right + joints_left]
+    merged = (y + pf) / 2.0 * 0.9
+    assert torch.equal(oracle.tta_merge(y, yf, 0.9, joints_left, joints_right), merged)
+    np.savez_compressed(os.path.join(OUT, "tta_tail_3dhp.npz"), y=y.numpy(), yf=yf.numpy(), merged=merged.numpy(),
+                        scale=0.9, left=np.array(joints_left), right=np.array(joints_right))
+
+
 def weights_checksum():
     rows = {}
     for F in (27, 81, 243):
@@ -149,17 +214,32 @@ def tail_case():
                         merged=merged.numpy(), mpjpe=e.numpy(), scale=1.7)
 
 
+CASES = [
+    ("weights_checksum", weights_checksum, ()),
+    ("tta_tail", tail_case, ()),
+    ("tta_tail_3dhp", tail_case_3dhp, ()),
+    ("denoise_f27_b3", denoise_case, ("denoise_f27_b3", 27, 3, [999, 500, 3])),
+    ("denoise_f27_b2_notime", denoise_case, ("denoise_f27_b2_notime", 27, 2, [10, 20], False)),
+    ("sampler_f27_b2_s3_clip", sampler_case, ("sampler_f27_b2_s3_clip", 27, 2, 3, 0.0, True)),
+    ("sampler_f27_b2_s3_eta", sampler_case, ("sampler_f27_b2_s3_eta", 27, 2, 3, 0.5, True, True, True)),
+    ("sampler_f27_b2_s2_notime", sampler_case, ("sampler_f27_b2_s2_notime", 27, 2, 2, 0.0, True, False)),
+    ("sampler_f81_b1_s2_noclip", sampler_case, ("sampler_f81_b1_s2_noclip", 81, 1, 2, 0.0, False)),
+    ("sampler_f243_b1_s1_clip", sampler_case, ("sampler_f243_b1_s1_clip", 243, 1, 1, 0.0, True)),
+    ("sampler_f9_b2_s9_clip", sampler_case, ("sampler_f9_b2_s9_clip", 9, 2, 9, 0.0, True)),
+    # the BASELINE configurations' own frame counts at the full 9 DDIM steps (cfg2: F = 81, cfg3 / cfg5: F = 243)
+    ("sampler_f81_b1_s9_clip", sampler_case, ("sampler_f81_b1_s9_clip", 81, 1, 9, 0.0, True)),
+    ("sampler_f243_b1_s9_clip", sampler_case, ("sampler_f243_b1_s9_clip", 243, 1, 9, 0.0, True)),
+    ("sampler_f27_b2_s9_notime", sampler_case, ("sampler_f27_b2_s9_notime", 27, 2, 9, 0.0, True, False)),
+    # forward() with output_loss=True (N1) and repeat_n
+    ("forward_f27_b3_s2_loss", forward_case, ("forward_f27_b3_s2_loss", 27, 3, 2, 1, [999, 431, 7])),
+    ("forward_f9_b2_s2_rep2_l1", forward_case, ("forward_f9_b2_s2_rep2_l1", 9, 2, 2, 2, [650, 12], "l1", False)),
+]
+
 if __name__ == "__main__":
-    weights_checksum()
-    tail_case()
-    denoise_case("denoise_f27_b3", 27, 3, [999, 500, 3])
-    denoise_case("denoise_f27_b2_notime", 27, 2, [10, 20], with_time_emb=False)
-    sampler_case("sampler_f27_b2_s3_clip", 27, 2, 3, 0.0, True)
-    sampler_case("sampler_f27_b2_s3_eta", 27, 2, 3, 0.5, True, trace=True)
-    sampler_case("sampler_f27_b2_s2_notime", 27, 2, 2, 0.0, True, with_time_emb=False)
-    sampler_case("sampler_f81_b1_s2_noclip", 81, 1, 2, 0.0, False)
-    sampler_case("sampler_f243_b1_s1_clip", 243, 1, 1, 0.0, True)
-    sampler_case("sampler_f9_b2_s9_clip", 9, 2, 9, 0.0, True)
+    want = sys.argv[1:]
+    for key, fn, a in CASES:
+        if not want or any(w in key for w in want):
+            fn(*a)
     print("golden vectors written to", OUT)
 # tests/golden/state_dict_keys.txt (the 254 keys + shapes of the reference GaussianDiffusion state dict at F=27) is
 # written by:  python - <<< "see git history / DESIGN.md";  it is regenerated below when run as a script.
