@@ -247,7 +247,8 @@ def run_ours(args):
     else:            # weak scaling: every GPU owns wl["clips"] clips, sampled as one batch
         B = wl["clips"]
         n_total, shard_start, batch = world * B, rank * B, B
-    gemm_mode = {"split3": _lib.GEMM_TC_SPLIT3, "fp16": _lib.GEMM_TC_FP16, "f8c": _lib.GEMM_TC_F8C}[args.gemm]
+    gemm_mode = {"split3": _lib.GEMM_TC_SPLIT3, "fp16": _lib.GEMM_TC_FP16, "f8c": _lib.GEMM_TC_F8C,
+                 "f4c": _lib.GEMM_TC_F4C}[args.gemm]
 
     model = synthetic.make_model(F, with_time_emb=wl["time_emb"]).to(dev)
     model.gemm_mode, model.max_clips_hint = gemm_mode, mult * batch
@@ -376,7 +377,7 @@ def run_ours(args):
     peaks = measured_peaks()
     gemm_flops = tokens * GEMM_FLOPS_PER_TOKEN_CALL * S
     achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12
-    passes = {"split3": 3, "f8c": 2, "fp16": 1}[args.gemm]
+    passes = {"split3": 3, "f8c": 2, "fp16": 1, "f4c": 1.5}[args.gemm]
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma cta_group::2 kind::f16 + kind::f8f6f4, TMA, TMEM)",
         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
@@ -442,6 +443,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
         "dtype": {"split3": "fp16x3-split operands, fp32 accumulate",
                   "f8c": "fp16 main + e5m2 correction products (2 tensor-pipe units), fp32 accumulate",
+                  "f4c": "fp16 main + block-scaled e2m1 (mxfp4) correction products (1.5 tensor-pipe units), fp32 accumulate",
                   "fp16": "fp16 operands, fp32 accumulate"}[args.gemm],
         "data": "synthetic",
         "config": {"workload": wl["name"], "clips_per_gpu": B, "frames": F, "sampling_timesteps": S,
@@ -476,7 +478,7 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="override: clips per GPU (cfg5: total windows)")
     ap.add_argument("--sampling-timesteps", type=int, default=0, help="override: DDIM steps (cfg4 sweep 1/9/25/50)")
     ap.add_argument("--batch", type=int, default=256, help="cfg5: clips per sampler batch (x2 with the flip copies)")
-    ap.add_argument("--gemm", default="f8c", choices=["split3", "f8c", "fp16"],
+    ap.add_argument("--gemm", default="f8c", choices=["split3", "f8c", "fp16", "f4c"],
                     help="GEMM arithmetic: f8c (default; fp16 main + e5m2 correction products), split3 (3 fp16 passes), "
                          "fp16 (1 pass, outside the parity bar)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -286,8 +286,8 @@ template <int FMT, int NSLOT, int NCH, bool SPATIAL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
                         const __grid_constant__ CUtensorMap tm_second, const __grid_constant__ CUtensorMap tm_hi_tail,
-                        const __grid_constant__ CUtensorMap tm_second_tail, int F, int J, int n_units, int n_mt, int NKp,
-                        int n_stage) {
+                        const __grid_constant__ CUtensorMap tm_second_tail, uint8_t* __restrict__ sf_out, int F, int J,
+                        int n_units, int n_mt, int NKp, int n_stage) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = 3 * n_mt * kTile;          // Q tiles | K tiles | V tiles of one unit
@@ -462,6 +462,59 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
       ptx::bar_sync(1 + slot, 128);          // the issuer is past the read-wait of the previous tile's stores: Stg is free
       const ptx::f32x2 inv2 = ptx::splat2(inv);
+      if (FMT == FMT_F4C) {
+        // block-scaled operand (operand.cuh): the row's 64 channels are two 32-element scale blocks of each part.
+        // Pass 1: x = O inv - (v_hi + v_lo) back into the O registers, hi halves into the (dead) Q row, block maxima of
+        // x and of x - hi.  Pass 2: P = q4(x), Q = q4(x - hi) as [128 rows][32 B] tiles for the two TMA stores.
+        float ax[2] = {0.f, 0.f}, al[2] = {0.f, 0.f};
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint32_t hw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t& ra = g < 4 ? o0[8 * g + 2 * e] : o1[8 * (g & 3) + 2 * e];
+            uint32_t& rb = g < 4 ? o0[8 * g + 2 * e + 1] : o1[8 * (g & 3) + 2 * e + 1];
+            float x0, x1;
+            ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(ra), __uint_as_float(rb)), inv2, nv[4 * g + e]), x0, x1);
+            const __half2 h01 = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h01);
+            hw[e] = *reinterpret_cast<const uint32_t*>(&h01);
+            ax[g >> 2] = fmaxf(ax[g >> 2], fmaxf(fabsf(x0), fabsf(x1)));
+            al[g >> 2] = fmaxf(al[g >> 2], fmaxf(fabsf(x0 - hf.x), fabsf(x1 - hf.y)));
+            ra = __float_as_uint(x0);
+            rb = __float_as_uint(x1);
+          }
+          *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        }
+        const uint32_t bp0 = op_ue8m0_of(ax[0]), bp1 = op_ue8m0_of(ax[1]), bq0 = op_ue8m0_of(al[0]), bq1 = op_ue8m0_of(al[1]);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const ptx::f32x2 ip = ptx::splat2(op_ue8m0_inv(g < 4 ? bp0 : bp1)), iq = ptx::splat2(op_ue8m0_inv(g < 4 ? bq0 : bq1));
+          uint32_t pa = 0, qa = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = __uint_as_float(g < 4 ? o0[8 * g + 2 * e] : o1[8 * (g & 3) + 2 * e]);
+            const float x1 = __uint_as_float(g < 4 ? o0[8 * g + 2 * e + 1] : o1[8 * (g & 3) + 2 * e + 1]);
+            const float2 hf = __half22float2(__floats2half2_rn(x0, x1));
+            float a0, a1, l0, l1;
+            ptx::unpack2(ptx::mul2(ptx::pack2(x0, x1), ip), a0, a1);
+            ptx::unpack2(ptx::mul2(ptx::sub2(ptx::pack2(x0, x1), ptx::pack2(hf.x, hf.y)), iq), l0, l1);
+            pa |= op_e2m1x2(a0, a1) << (8 * e);
+            qa |= op_e2m1x2(l0, l1) << (8 * e);
+          }
+          *reinterpret_cast<uint32_t*>(Stg + row_l * 32 + g * 4) = pa;
+          *reinterpret_cast<uint32_t*>(Stg + 4096 + row_l * 32 + g * 4) = qa;
+        }
+        // the row's four scale bytes: k-blocks (2h, 2h+1) of part P and (16 + 2h, 16 + 2h + 1) of part Q are adjacent
+        // bytes of a scale-factor atom.  Rows the TMA stores clip (>= F, or past the unit) must not be written here.
+        const int64_t tok = SPATIAL ? static_cast<int64_t>(j) + row_l
+                                    : (static_cast<int64_t>(b) * F + r) * J + j;
+        const bool live = SPATIAL ? row_l < (tail ? (F % 7) * 17 : kSpatialRows) : r < F;
+        if (live) {
+          *reinterpret_cast<uint16_t*>(sf_out + op_sf_offset(tok, 2 * h, kC / 64)) = static_cast<uint16_t>(bp0 | (bp1 << 8));
+          *reinterpret_cast<uint16_t*>(sf_out + op_sf_offset(tok, 16 + 2 * h, kC / 64)) = static_cast<uint16_t>(bq0 | (bq1 << 8));
+        }
+      } else {
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         // packed pairs: x = O inv - (v_hi + v_lo), lo = x - fp16(x) and the two e5m2 scalings as FFMA2 / FADD2 / FMUL2
@@ -496,14 +549,20 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
           *reinterpret_cast<uint2*>(Stg + 8192 + row_l * 64 + g * 8) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
         }
       }
+      }
       ptx::fence_proxy_async();
       ptx::bar_sync(1 + slot, 128);          // every row is staged, and nobody still reads v_hi rows of this tile
       if (issuer) {
         const CUtensorMap* mh = tail ? &tm_hi_tail : &tm_hi;
         const CUtensorMap* ms = tail ? &tm_second_tail : &tm_second;
         ptx::tma_store_4d(mh, Qs + m * kTile, h * kHd, j, m * 128, b);
-        ptx::tma_store_4d(ms, Stg, h * kHd, j, m * 128, b);
-        if (FMT != FMT_SPLIT16) ptx::tma_store_4d(ms, Stg + 8192, kC + h * kHd, j, m * 128, b);
+        if (FMT == FMT_F4C) {                // c4 row: 256 B of P nibbles | 256 B of Q nibbles; 32 B per head and part
+          ptx::tma_store_4d(ms, Stg, h * 32, j, m * 128, b);
+          ptx::tma_store_4d(ms, Stg + 4096, (kC >> 1) + h * 32, j, m * 128, b);
+        } else {
+          ptx::tma_store_4d(ms, Stg, h * kHd, j, m * 128, b);
+          if (FMT != FMT_SPLIT16) ptx::tma_store_4d(ms, Stg + 8192, kC + h * kHd, j, m * 128, b);
+        }
         ptx::bulk_commit();
         ptx::bulk_wait_read_all();           // Stg / Q_m have been read: the tile has left shared memory
         ptx::mbar_arrive(&bars->stage_free[stage]);
@@ -542,23 +601,23 @@ int encode_rank4(CUtensorMap* out, void* base, CUtensorMapDataType dt, const cuu
 
 // [B, F, J, row] token-major array viewed as a 4-D tensor (channel, j, f, b); box = {64 channels, 1, 128 frames, 1}
 int encode_tokens_4d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int elem_bytes, int64_t row_elems, int J,
-                     int F, int64_t B, CUtensorMapSwizzle swz) {
+                     int F, int64_t B, CUtensorMapSwizzle swz, int box0 = 64) {
   const cuuint64_t row_bytes = static_cast<cuuint64_t>(row_elems) * elem_bytes;
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(J), static_cast<cuuint64_t>(F),
                               static_cast<cuuint64_t>(B)};
   const cuuint64_t strides[3] = {row_bytes, row_bytes * J, row_bytes * J * F};
-  const cuuint32_t box[4] = {64, 1, 128, 1};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(box0), 1, 128, 1};
   return encode_rank4(out, base, dt, dims, strides, box, swz);
 }
 
 // The same array as a plain [tokens, row] matrix (rank 4 with two unit dimensions, so that the kernel's 4-D TMA
 // instructions serve both modes); box = {64 channels, box_rows tokens, 1, 1}
 int encode_tokens_2d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int elem_bytes, int64_t row_elems,
-                     int64_t tokens, int box_rows, CUtensorMapSwizzle swz) {
+                     int64_t tokens, int box_rows, CUtensorMapSwizzle swz, int box0 = 64) {
   const cuuint64_t row_bytes = static_cast<cuuint64_t>(row_elems) * elem_bytes;
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(tokens), 1, 1};
   const cuuint64_t strides[3] = {row_bytes, row_bytes * tokens, row_bytes * tokens};
-  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box_rows), 1, 1};
   return encode_rank4(out, base, dt, dims, strides, box, swz);
 }
 
@@ -581,6 +640,9 @@ int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half*
   if (fmt == FMT_F8C)
     return encode_tokens_4d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 2 * kC, J, F, max_clips,
                             CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (fmt == FMT_F4C)       // c4 rows of K = 512 bytes; {32 B x 128 rows} boxes (one head of one part)
+    return encode_tokens_4d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kC, J, F, max_clips,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, 32);
   return encode_tokens_4d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, J, F, max_clips,
                           CU_TENSOR_MAP_SWIZZLE_128B);
 }
@@ -591,10 +653,12 @@ int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi,
   if (encode_tokens_2d(&maps->o_hi_tail, o_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, tokens, tail_rows,
                        CU_TENSOR_MAP_SWIZZLE_128B))
     return -1;
-  if (fmt == FMT_F8C ? encode_tokens_2d(&maps->o_second_tail, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 2 * kC, tokens,
-                                        tail_rows, CU_TENSOR_MAP_SWIZZLE_NONE)
-                     : encode_tokens_2d(&maps->o_second_tail, o_second, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, tokens,
-                                        tail_rows, CU_TENSOR_MAP_SWIZZLE_128B))
+  if (fmt == FMT_F8C   ? encode_tokens_2d(&maps->o_second_tail, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 2 * kC, tokens,
+                                          tail_rows, CU_TENSOR_MAP_SWIZZLE_NONE)
+      : fmt == FMT_F4C ? encode_tokens_2d(&maps->o_second_tail, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kC, tokens,
+                                          tail_rows, CU_TENSOR_MAP_SWIZZLE_NONE, 32)
+                       : encode_tokens_2d(&maps->o_second_tail, o_second, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, tokens,
+                                          tail_rows, CU_TENSOR_MAP_SWIZZLE_128B))
     return -1;
   // loads: 128-row boxes (rows beyond the 119 of a unit are read but masked); stores: 119-row boxes
   if (encode_tokens_2d(&maps->qkv, const_cast<__half*>(qkv), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kQkvRow, tokens, 128,
@@ -606,6 +670,9 @@ int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi,
   if (fmt == FMT_F8C)
     return encode_tokens_2d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 2 * kC, tokens, kSpatialRows,
                             CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (fmt == FMT_F4C)
+    return encode_tokens_2d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kC, tokens, kSpatialRows,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, 32);
   return encode_tokens_2d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, tokens, kSpatialRows,
                           CU_TENSOR_MAP_SWIZZLE_128B);
 }
@@ -619,12 +686,13 @@ cudaError_t configure_attention_tc() {
   D3D_CFG_TC(FMT_SPLIT16, 0, false) D3D_CFG_TC(FMT_F8C, 0, false) D3D_CFG_TC(FMT_SPLIT16, 3, false)
   D3D_CFG_TC(FMT_F8C, 3, false) D3D_CFG_TC(FMT_SPLIT16, 8, false) D3D_CFG_TC(FMT_F8C, 8, false)
   D3D_CFG_TC(FMT_SPLIT16, 0, true) D3D_CFG_TC(FMT_F8C, 0, true)
+  D3D_CFG_TC(FMT_F4C, 0, false) D3D_CFG_TC(FMT_F4C, 3, false) D3D_CFG_TC(FMT_F4C, 8, false) D3D_CFG_TC(FMT_F4C, 0, true)
 #undef D3D_CFG_TC
   return cudaSuccess;
 }
 
-cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
-                                    cudaStream_t st) {
+cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, uint8_t* o_sf, int fmt, int B, int F, int J,
+                                    int num_sms, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   if (F <= 64 || F > 256) return cudaErrorInvalidValue;
   const int n_mt = (F + 127) / 128;
@@ -636,8 +704,11 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, i
   const int smem = tc_smem_bytes<2>(n_mt);
 #define D3D_LAUNCH_TC(FMT_, NCH_)                                                                               \
   attn_temporal_tc_kernel<FMT_, 2, NCH_, false><<<grid, kTcThreads, smem, st>>>(                      \
-      maps.qkv, maps.o_hi, maps.o_second, maps.o_hi, maps.o_second, F, J, n_units, n_mt, NKp, tc_stages(n_mt))
-  if (fmt == FMT_F8C) {
+      maps.qkv, maps.o_hi, maps.o_second, maps.o_hi, maps.o_second, o_sf, F, J, n_units, n_mt, NKp, tc_stages(n_mt))
+  if (fmt == FMT_F4C) {
+    if (!o_sf) return cudaErrorInvalidValue;
+    if (nch == 8) D3D_LAUNCH_TC(FMT_F4C, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_F4C, 3); else D3D_LAUNCH_TC(FMT_F4C, 0);
+  } else if (fmt == FMT_F8C) {
     if (nch == 8) D3D_LAUNCH_TC(FMT_F8C, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_F8C, 3); else D3D_LAUNCH_TC(FMT_F8C, 0);
   } else {
     if (nch == 8) D3D_LAUNCH_TC(FMT_SPLIT16, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_SPLIT16, 3); else D3D_LAUNCH_TC(FMT_SPLIT16, 0);
@@ -647,7 +718,8 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, i
 }
 
 // Spatial mode (J == 17): units of (clip, 7-frame group, head)
-cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int B, int F, int num_sms, cudaStream_t st) {
+cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, uint8_t* o_sf, int fmt, int B, int F, int num_sms,
+                                   cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   const int G = (F + 6) / 7;
   const int64_t units64 = static_cast<int64_t>(B) * G * kHeads;
@@ -655,12 +727,17 @@ cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int B, int F
   const int n_units = static_cast<int>(units64);
   const int grid = n_units < num_sms ? n_units : num_sms;
   const int smem = tc_smem_bytes<2>(1);
-  if (fmt == FMT_F8C)
+  if (fmt == FMT_F4C) {
+    if (!o_sf) return cudaErrorInvalidValue;
+    attn_temporal_tc_kernel<FMT_F4C, 2, 0, true><<<grid, kTcThreads, smem, st>>>(
+        maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, o_sf, F, G, n_units, 1, 128, tc_stages(1));
+  } else if (fmt == FMT_F8C) {
     attn_temporal_tc_kernel<FMT_F8C, 2, 0, true><<<grid, kTcThreads, smem, st>>>(
-        maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, F, G, n_units, 1, 128, tc_stages(1));
-  else
+        maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, o_sf, F, G, n_units, 1, 128, tc_stages(1));
+  } else {
     attn_temporal_tc_kernel<FMT_SPLIT16, 2, 0, true><<<grid, kTcThreads, smem, st>>>(
-        maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, F, G, n_units, 1, 128, tc_stages(1));
+        maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, o_sf, F, G, n_units, 1, 128, tc_stages(1));
+  }
   return cudaGetLastError();
 }
 

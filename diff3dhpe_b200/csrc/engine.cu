@@ -27,9 +27,10 @@ struct Lin {
   int N = 0, K = 0;
   __half* hi = nullptr;
   __half* lo = nullptr;
+  uint8_t* sf = nullptr;        // FMT_F4C: scale factors, behind the c4 bytes inside the `lo` allocation
   float* bias = nullptr;
   bool have_w = false;
-  CUtensorMap m_hi, m_lo;
+  CUtensorMap m_hi, m_lo, m_sf;
   CUtensorMap m_hi64, m_lo64;   // 64-row boxes (pair-cluster multicast slices)
 };
 
@@ -43,7 +44,8 @@ struct Blk {
 struct OperandBuf {   // a GEMM A operand living in the workspace
   __half* hi = nullptr;
   __half* lo = nullptr;
-  CUtensorMap m_hi, m_lo;
+  uint8_t* sf = nullptr;        // FMT_F4C: scale factors, behind the c4 bytes inside the `lo` allocation
+  CUtensorMap m_hi, m_lo, m_sf;
 };
 
 }  // namespace
@@ -165,10 +167,15 @@ int dev_alloc(d3d_handle* h, T** p, int64_t n, bool zero = true) {
   return 0;
 }
 
+#ifndef D3D_ATTN_TC_F4C
+#define D3D_ATTN_TC_F4C 1     // 0: route FMT_F4C attention through the mma.sync kernels + a split pass (bring-up A/B)
+#endif
+
 // fp16 main operand: finite up to 65504; the e5m2 images (w 2^-4, (w - hi) 2^8 <= |w| / 8) stay below e5m2's 57344
 constexpr float kMaxWeightAbs = 65504.0f;
 
 int mode_fmt(int gemm_mode) {
+  if (gemm_mode == D3D_GEMM_TC_F4C || gemm_mode == D3D_GEMM_SIMT_F4C) return FMT_F4C;
   return (gemm_mode == D3D_GEMM_TC_F8C || gemm_mode == D3D_GEMM_SIMT_F8C) ? FMT_F8C : FMT_SPLIT16;
 }
 
@@ -177,14 +184,24 @@ int make_maps(CUtensorMap* m_hi, CUtensorMap* m_second, const __half* hi, const 
               int fmt, int box_rows = 128) {
   if (make_operand_map(m_hi, hi, rows, K, box_rows)) return -1;
   if (fmt == FMT_F8C) return make_operand_map_u8(m_second, second, rows, 2 * static_cast<int64_t>(K), box_rows);
+  if (fmt == FMT_F4C) return make_operand_map_u8(m_second, second, rows, K, box_rows);      // c4: K bytes per row
   return make_operand_map(m_second, second, rows, K, box_rows);
+}
+// FMT_F4C: the scale-factor array sits behind the c4 bytes of the second array (2 K bytes per row were allocated, c4
+// takes K and the scales K / 16); rows must be a multiple of 128 (whole scale-factor atoms)
+int make_sf(uint8_t** sf, CUtensorMap* m_sf, __half* second, int64_t rows, int K, int fmt) {
+  *sf = nullptr;
+  if (fmt != FMT_F4C) return 0;
+  if (rows % 128 != 0 || K % 64 != 0) return -1;
+  *sf = reinterpret_cast<uint8_t*>(second) + op_sf_base(rows, K);
+  return make_sf_map(m_sf, *sf, rows * (K / 16));
 }
 
 int alloc_operand(d3d_handle* h, OperandBuf* o, int64_t rows, int K) {
   int r;
   if ((r = dev_alloc(h, &o->hi, rows * K))) return r;
   if ((r = dev_alloc(h, &o->lo, rows * K))) return r;
-  if (make_maps(&o->m_hi, &o->m_lo, o->hi, o->lo, rows, K, h->fmt))
+  if (make_maps(&o->m_hi, &o->m_lo, o->hi, o->lo, rows, K, h->fmt) || make_sf(&o->sf, &o->m_sf, o->lo, rows, K, h->fmt))
     return fail(h, -20, "cuTensorMapEncodeTiled failed for a workspace operand");
   return 0;
 }
@@ -197,7 +214,7 @@ int alloc_lin(d3d_handle* h, Lin* l, int N, int K) {
   if ((r = dev_alloc(h, &l->lo, static_cast<int64_t>(N) * K))) return r;
   if ((r = dev_alloc(h, &l->bias, N))) return r;
   if (make_maps(&l->m_hi, &l->m_lo, l->hi, l->lo, N, K, h->fmt) ||
-      make_maps(&l->m_hi64, &l->m_lo64, l->hi, l->lo, N, K, h->fmt, 64))
+      make_maps(&l->m_hi64, &l->m_lo64, l->hi, l->lo, N, K, h->fmt, 64) || make_sf(&l->sf, &l->m_sf, l->lo, N, K, h->fmt))
     return fail(h, -20, "cuTensorMapEncodeTiled failed for a weight operand");
   return 0;
 }
@@ -248,8 +265,9 @@ bool fuse_ln_enabled() { return env_int("D3D_GEMM_FUSE_LN", 0) == 1; }
 // out = epilogue(Aop . W^T + bias)
 int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int epi, const float* residual,
              float* out_f32, __half* out_hi, __half* out_lo, __half* out_qkv, int mode, cudaStream_t st,
-             const LnFuse* ln = nullptr) {
+             const LnFuse* ln = nullptr, uint8_t* out_sf = nullptr) {
   GemmParams p{};
+  p.out_sf = out_sf;
   if (ln) {
     epi = EPI_F32_LN;
     p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_eps = ln->eps;
@@ -271,13 +289,14 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   p.stream_out = env_int("D3D_GEMM_STREAM_OUT", 1);
   // measured (profiles/r01q_*): DRAM reads of the qkv GEMM 2.9x -> 1.1x its algorithmic bytes, step time -1.7 %
   p.n_inner = env_int("D3D_GEMM_N_INNER", 1);
-  if (mode == D3D_GEMM_SIMT_FP32 || mode == D3D_GEMM_SIMT_F8C) {
-    KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, w.hi, w.lo, p, epi, mode_fmt(mode), st));
+  if (mode == D3D_GEMM_SIMT_FP32 || mode == D3D_GEMM_SIMT_F8C || mode == D3D_GEMM_SIMT_F4C) {
+    KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, a.sf, w.hi, w.lo, w.sf, p, epi, mode_fmt(mode), st));
   } else {
     GemmMaps m;
     m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
     m.b_hi64 = w.m_hi64; m.b_lo64 = w.m_lo64;
-    const int passes = mode == D3D_GEMM_TC_FP16 ? 1 : (mode == D3D_GEMM_TC_F8C ? 2 : 3);
+    m.a_sf = a.m_sf; m.b_sf = w.m_sf;
+    const int passes = mode == D3D_GEMM_TC_FP16 ? 1 : (mode == D3D_GEMM_TC_F8C ? 2 : (mode == D3D_GEMM_TC_F4C ? 4 : 3));
     // epilogue warps per CTA: 16 pays where the epilogue, not the mainloop, sets the tile time
     const int ew = epi == EPI_GELU_SPLIT ? env_int("D3D_GEMM_EW_GELU", 16)
                  : epi == EPI_QKV16    ? env_int("D3D_GEMM_EW_QKV", 8)
@@ -287,28 +306,45 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   return 0;
 }
 
+bool attn_tc_has_f4c() { return D3D_ATTN_TC_F4C != 0; }
+
 int run_attention(d3d_handle* h, const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int B, bool spatial,
                   int mode, cudaStream_t st) {
+  const int64_t T_all = static_cast<int64_t>(B) * h->F * h->J;
+  const bool tc_path = mode == D3D_ATTN_DEFAULT && qkv == h->QKV &&
+                       (spatial ? (h->have_attn_sp && h->J == 17 && env_int("D3D_ATTN_TC_SPATIAL", 1))
+                                : (h->have_attn_tc && env_int("D3D_ATTN_TC", 1)));
+  if (h->fmt == FMT_F4C && !o_f32 && !(tc_path && attn_tc_has_f4c())) {
+    // the mma.sync / CUDA-core attention kernels do not write the block-scaled operand: fp32 result into the (dead)
+    // H operand's memory, then one split pass into ATT
+    if (o_hi != h->ATT.hi || o_lo != h->ATT.lo) return fail(h, -2, "attention output must be the ATT operand");
+    float* scratch = reinterpret_cast<float*>(h->H.hi);
+    int r = run_attention(h, qkv, nullptr, nullptr, scratch, B, spatial, mode == D3D_ATTN_DEFAULT ? D3D_ATTN_MMA_SYNC : mode, st);
+    if (r) return r;
+    KLP(spatial ? D3D_PROF_ATTN_SPATIAL : D3D_PROF_ATTN_TEMPORAL, st,
+        launch_split(scratch, h->ATT.hi, h->ATT.lo, h->ATT.sf, T_all, kC, FMT_F4C, 0, st));
+    return 0;
+  }
   if (spatial) {
     if (mode == D3D_ATTN_SIMT || h->J != 17) {
       KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_generic_simt(qkv, o_hi, o_lo, o_f32, h->fmt, B * h->F, h->J, h->J, 1, 1, st));
-    } else if (mode == D3D_ATTN_DEFAULT && h->have_attn_sp && qkv == h->QKV && env_int("D3D_ATTN_TC_SPATIAL", 1)) {
+    } else if (tc_path && (h->fmt != FMT_F4C || attn_tc_has_f4c())) {
       if (!o_f32 && (o_hi != h->ATT.hi || o_lo != h->ATT.lo)) return fail(h, -2, "attention output must be the ATT operand");
       const int64_t T = static_cast<int64_t>(B) * h->F * h->J;
-      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial_tc(h->attn_sp, h->fmt, B, h->F, h->num_sms, st));
-      if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, o_f32, T, kC, h->fmt, st));
+      KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial_tc(h->attn_sp, h->ATT.sf, h->fmt, B, h->F, h->num_sms, st));
+      if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, h->ATT.sf, o_f32, T, kC, h->fmt, st));
     } else {
       KLP(D3D_PROF_ATTN_SPATIAL, st, launch_attn_spatial(qkv, o_hi, o_lo, o_f32, h->fmt, static_cast<int64_t>(B) * h->F, h->J, st));
     }
   } else {
     if (mode == D3D_ATTN_SIMT) {
       KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_simt(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));
-    } else if (mode == D3D_ATTN_DEFAULT && h->have_attn_tc && qkv == h->QKV && env_int("D3D_ATTN_TC", 1)) {
+    } else if (tc_path && (h->fmt != FMT_F4C || attn_tc_has_f4c())) {
       // the tcgen05 kernel's tensor maps are bound to QKV -> ATT; an fp32 result (op-level entry point) is merged
       // from the operand pair afterwards
       if (!o_f32 && (o_hi != h->ATT.hi || o_lo != h->ATT.lo)) return fail(h, -2, "attention output must be the ATT operand");
-      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_tc(h->attn_tc, qkv, h->fmt, B, h->F, h->J, h->num_sms, st));
-      if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, o_f32, static_cast<int64_t>(B) * h->F * h->J, kC, h->fmt, st));
+      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_tc(h->attn_tc, qkv, h->ATT.sf, h->fmt, B, h->F, h->J, h->num_sms, st));
+      if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, h->ATT.sf, o_f32, static_cast<int64_t>(B) * h->F * h->J, kC, h->fmt, st));
     } else {
       KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));
     }
@@ -357,7 +393,7 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
   const int gm = h->cfg.gemm_mode, am = h->cfg.attn_mode;
   int r;
   KLP(D3D_PROF_LIFT, st, launch_lift_ln(x2d, y, x5, h->wf_t, h->bf, h->spos, tv, tv_stride,
-                                        LnParams{h->blk[0].n1g, h->blk[0].n1b}, h->X, h->A.hi, h->A.lo, h->fmt, T, h->J,
+                                        LnParams{h->blk[0].n1g, h->blk[0].n1b}, h->X, h->A.hi, h->A.lo, h->A.sf, h->fmt, T, h->J,
                                         h->F * h->J, st));
   for (int b = 0; b < n_blocks; ++b) {
     const Blk& k = h->blk[b];
@@ -369,16 +405,16 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
       if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st, &ln2))) return r;
     } else {
       if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
-      KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, h->fmt, T, st));
+      KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, h->A.sf, h->fmt, T, st));
     }
-    if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, nullptr, gm, st))) return r;
+    if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, nullptr, gm, st, nullptr, h->H.sf))) return r;
     if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
     if (b + 1 < n_blocks) {
       const LnParams post = spatial ? LnParams{h->sn_g, h->sn_b} : LnParams{h->tn_g, h->tn_b};
       const Blk& nx = h->blk[b + 1];
       KLP(D3D_PROF_LN, st,
           launch_postnorm_add_ln(h->X, post, (b + 1 == 1) ? h->tpos : nullptr, tv ? tv + (b + 1) * kC : nullptr,
-                                 tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo, h->fmt, T, h->J, h->F, st));
+                                 tv_stride, LnParams{nx.n1g, nx.n1b}, h->A.hi, h->A.lo, h->A.sf, h->fmt, T, h->J, h->F, st));
     }
   }
   return 0;
@@ -616,7 +652,7 @@ int d3d_load_weights(d3d_handle* h, const d3d_tensor* tensors, int32_t n) {
     int r = copy_to(stage, t, static_cast<int64_t>(l.N) * l.K);
     if (r) return r;
     CK(cudaMemset(h->absmax_dev, 0, 2 * sizeof(float)));
-    CK(launch_split(stage, l.hi, l.lo, l.N, l.K, h->fmt, 1, 0, h->absmax_dev));
+    CK(launch_split(stage, l.hi, l.lo, l.sf, l.N, l.K, h->fmt, 1, 0, h->absmax_dev));
     CK(cudaDeviceSynchronize());
     // range guard: the main operand is fp16 and the correction operands are scaled images of it, so a
     // weight beyond the fp16 range (or a non-finite one) would silently become Inf inside every GEMM.  [0] = max |w|
@@ -1013,7 +1049,13 @@ int d3d_debug_attention_operand(d3d_handle* h, const float* qkv, void* hi_out, v
   int r = run_attention(h, h->QKV, h->ATT.hi, h->ATT.lo, nullptr, B, spatial != 0, attn_mode, st);
   if (r) return r;
   CK(cudaMemcpyAsync(hi_out, h->ATT.hi, static_cast<size_t>(T) * kC * 2, cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpyAsync(second_out, h->ATT.lo, static_cast<size_t>(T) * kC * 2, cudaMemcpyDeviceToDevice, st));
+  if (h->fmt == FMT_F4C) {
+    // second_out: [T][512] c4 bytes (256 B of P nibbles | 256 B of Q nibbles), then [T][32] scale bytes, row-major
+    CK(cudaMemcpyAsync(second_out, h->ATT.lo, static_cast<size_t>(T) * kC, cudaMemcpyDeviceToDevice, st));
+    KL(launch_sf_rows(h->ATT.sf, static_cast<uint8_t*>(second_out) + static_cast<size_t>(T) * kC, T, kC, st));
+  } else {
+    CK(cudaMemcpyAsync(second_out, h->ATT.lo, static_cast<size_t>(T) * kC * 2, cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 
@@ -1037,6 +1079,7 @@ struct OpLinearBufs {
   OperandBuf a;
   Lin w;
   __half *o_hi = nullptr, *o_lo = nullptr;
+  uint8_t* o_sf = nullptr;
   std::vector<void*> mine;
   ~OpLinearBufs() { for (void* p : mine) cudaFree(p); }
 };
@@ -1059,11 +1102,13 @@ int prep_op_linear(d3d_handle* h, OpLinearBufs& b, int64_t M, int N, int K, int 
   b.w.N = N;
   b.w.K = K;
   if (act) {
-    CK(tmp_alloc(b, &b.o_hi, M * N));
-    CK(tmp_alloc(b, &b.o_lo, M * N));
+    CK(tmp_alloc(b, &b.o_hi, Mp * N));
+    CK(tmp_alloc(b, &b.o_lo, Mp * N));
+    if (fmt == FMT_F4C) b.o_sf = reinterpret_cast<uint8_t*>(b.o_lo) + op_sf_base(Mp, N);
   }
   if (make_maps(&b.a.m_hi, &b.a.m_lo, b.a.hi, b.a.lo, Mp, K, fmt) || make_maps(&b.w.m_hi, &b.w.m_lo, b.w.hi, b.w.lo, N, K, fmt) ||
-      make_maps(&b.w.m_hi64, &b.w.m_lo64, b.w.hi, b.w.lo, N, K, fmt, 64))
+      make_maps(&b.w.m_hi64, &b.w.m_lo64, b.w.hi, b.w.lo, N, K, fmt, 64) || make_sf(&b.a.sf, &b.a.m_sf, b.a.lo, Mp, K, fmt) ||
+      make_sf(&b.w.sf, &b.w.m_sf, b.w.lo, N, K, fmt))
     return fail(h, -20, "cuTensorMapEncodeTiled failed");
   return 0;
 }
@@ -1082,11 +1127,12 @@ int d3d_op_linear(d3d_handle* h, const float* a, const float* w, const float* bi
   int r = prep_op_linear(h, b, M, N, K, act, fmt);
   if (r) return r;
   b.w.bias = const_cast<float*>(bias);
-  KL(launch_split(a, b.a.hi, b.a.lo, M, K, fmt, 0, st));
-  KL(launch_split(w, b.w.hi, b.w.lo, N, K, fmt, 1, st));
+  if (fmt == FMT_F4C && (N % 256 != 0 || K % 128 != 0)) return fail(h, -2, "the F4C GEMM needs N%256==0 and K%128==0");
+  KL(launch_split(a, b.a.hi, b.a.lo, b.a.sf, M, K, fmt, 0, st));
+  KL(launch_split(w, b.w.hi, b.w.lo, b.w.sf, N, K, fmt, 1, st));
   if (act) {
-    if ((r = run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st))) return r;
-    KL(launch_merge(b.o_hi, b.o_lo, out, M, N, fmt, st));
+    if ((r = run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st, nullptr, b.o_sf))) return r;
+    KL(launch_merge(b.o_hi, b.o_lo, b.o_sf, out, M, N, fmt, st));
   } else {
     if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, out, nullptr, nullptr, nullptr, gemm_mode, st))) return r;
   }
@@ -1106,14 +1152,14 @@ int d3d_op_linear_ln(d3d_handle* h, const float* a, const float* w, const float*
   int r = prep_op_linear(h, b, M, kC, K, 1 /*allocates o_hi / o_lo [M, 512]*/, FMT_F8C);
   if (r) return r;
   b.w.bias = const_cast<float*>(bias);
-  KL(launch_split(a, b.a.hi, b.a.lo, M, K, FMT_F8C, 0, st));
-  KL(launch_split(w, b.w.hi, b.w.lo, kC, K, FMT_F8C, 1, st));
+  KL(launch_split(a, b.a.hi, b.a.lo, nullptr, M, K, FMT_F8C, 0, st));
+  KL(launch_split(w, b.w.hi, b.w.lo, nullptr, kC, K, FMT_F8C, 1, st));
   OperandBuf dst;
   dst.hi = b.o_hi;
   dst.lo = b.o_lo;
   const LnFuse ln{gamma, beta, eps, &dst};
   if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, x_out, nullptr, nullptr, nullptr, D3D_GEMM_TC_F8C, st, &ln))) return r;
-  KL(launch_merge(b.o_hi, b.o_lo, ln_out, M, kC, FMT_F8C, st));
+  KL(launch_merge(b.o_hi, b.o_lo, nullptr, ln_out, M, kC, FMT_F8C, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1139,13 +1185,13 @@ int d3d_op_linear_bench(d3d_handle* h, int64_t M, int32_t N, int32_t K, int32_t 
   const int64_t na = M * K;
   for (int64_t off = 0; off < na; off += static_cast<int64_t>(host.size()))
     CK(cudaMemcpy(fa + off, host.data(), sizeof(float) * static_cast<size_t>(std::min<int64_t>(host.size(), na - off)), cudaMemcpyHostToDevice));
-  CK(launch_split(fa, b.a.hi, b.a.lo, M, K, fmt, 0, st));
-  CK(launch_split(fa, b.w.hi, b.w.lo, N, K, fmt, 1, st));
+  CK(launch_split(fa, b.a.hi, b.a.lo, b.a.sf, M, K, fmt, 0, st));
+  CK(launch_split(fa, b.w.hi, b.w.lo, b.w.sf, N, K, fmt, 1, st));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   auto once = [&]() -> int {
-    if (act) return run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st);
+    if (act) return run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st, nullptr, b.o_sf);
     return run_gemm(h, b.a, b.w, M, EPI_F32, nullptr, fo, nullptr, nullptr, nullptr, gemm_mode, st);
   };
   for (int i = 0; i < 3; ++i)

@@ -9,7 +9,11 @@
 //     parity bar).  The 1-pass mode issues only A_hi.B_hi.  PASSES == 2 is the FMT_F8C mode of operand.cuh: the
 //     fp16 main product followed by ONE kind::f8f6f4 (e5m2) product over K' = 2K that carries both correction
 //     terms -- 2 tensor-pipe units instead of 3; the second tensor maps then describe the uint8 c8 arrays and
-//     the ring holds 2 * K/64 uniform stages per tile (fp16 stages first, then fp8 stages).
+//     the ring holds 2 * K/64 uniform stages per tile (fp16 stages first, then fp8 stages).  PASSES == 4 is FMT_F4C:
+//     the correction product in block-scaled e2m1 (kind::mxf4.block_scale, 4x the fp16 rate; 1.5 units): K/64 fp16
+//     stages, then K/128 stages of 256 e2m1 each that also carry the stage's ue8m0 scale-factor atoms (3 KB), which the
+//     MMA thread copies into TMEM with tcgen05.cp right before the stage's four MMAs.  The scale columns live in the
+//     first 32 columns of the OTHER accumulator, which the previous tile's epilogue has drained by then (see sf_free).
 //   * TMA (cp.async.bulk.tensor, SWIZZLE_128B) stages {128 rows x 64} fp16 boxes; a ring of mbarrier-guarded
 //     stages feeds one MMA-issuing thread.
 //   * CG = 2 (default): a CTA PAIR (thread-block cluster of 2, tcgen05.mma.cta_group::2) owns a 256 x 256
@@ -56,15 +60,20 @@ struct Cfg {
   static constexpr int kBRows = BN / CG;                  // weight rows staged by one CTA
   static constexpr int kTileBytesB = kBRows * BK * 2;
   static constexpr int kThreads = 128 + 32 * EW;
-  static constexpr int kStageBytes = (PASSES == 3 ? 2 : 1) * (kTileBytesA + kTileBytesB);
+  // FMT_F4C: every ring slot has room for the scale-factor atoms of an e2m1 stage behind the A / B tiles:
+  // A: 128 rows x 8 k-blocks = 1 KB, B: 256 rows (BOTH halves: each CTA's MMA scales all 256 columns) x 8 = 2 KB
+  static constexpr int kSfBytes = PASSES == 4 ? 3072 : 0;
+  static constexpr int kStageBytes = (PASSES == 3 ? 2 : 1) * (kTileBytesA + kTileBytesB) + kSfBytes;
   static constexpr int kStagingBytes = EW * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
-  static constexpr int kRing = (PASSES == 2 ? kSmemBudget : 200 * 1024) + 8 * 4096 - kStagingBytes;
+  static constexpr int kRing = ((PASSES == 2 || PASSES == 4) ? kSmemBudget : 200 * 1024) + 8 * 4096 - kStagingBytes;
   static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;   // 256 or 512 (power of two)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256 x 256 tiles");
   static_assert(EW == 8 || (EW == 16 && BN == 256), "16 epilogue warps split a 256-column tile four ways");
+  static_assert(PASSES != 4 || (CG == 2 && BN == 256), "the F4C kernel is the CTA-pair 256 x 256 kernel");
+  static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned stages");
 };
 
 struct Barriers {
@@ -72,6 +81,7 @@ struct Barriers {
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t sf_free[2];     // F4C: the first 32 columns of accumulator a have been read by the epilogue (both CTAs)
   uint32_t tmem_base;
 };
 
@@ -145,6 +155,7 @@ template <int CG, int BN, int PASSES, int EPI, int CS, int EW = 8>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+               const __grid_constant__ CUtensorMap tm_a_sf, const __grid_constant__ CUtensorMap tm_b_sf,
                const GemmParams p) {
   using C = Cfg<CG, BN, PASSES, EW>;
   extern __shared__ uint8_t smem_raw[];
@@ -155,6 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   static_assert(CS == 1 || (CG == 2 && PASSES == 2), "pair clusters are implemented for the CTA-pair F8C kernel");
+  static_assert(PASSES != 4 || EPI != EPI_F32_LN, "the fused LayerNorm epilogue keeps x in TMEM: no room for scale factors");
   const uint32_t crank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // rank in the cluster (0 .. 2*CS-1)
   const uint32_t rank = crank & 1u;                                 // position in the CTA pair, 0 = leader
   const uint32_t pair = crank >> 1;                                 // pair index inside the cluster (0 .. CS-1)
@@ -166,7 +178,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int n_tiles_m = ((p.M + TM - 1) / TM + CS - 1) / CS;        // super-tiles of CS vertically adjacent tiles
   const int n_tiles = n_tiles_m * n_tiles_n;
   const int n_kb = p.K / BK;
-  const int n_steps = PASSES == 2 ? 2 * n_kb : n_kb;       // ring stages consumed per tile
+  const int n_k4 = p.K / 128;                              // F4C: stages of 256 e2m1 (128 bytes of the K-byte c4 row)
+  const int n_steps = PASSES == 2 ? 2 * n_kb : (PASSES == 4 ? n_kb + n_k4 : n_kb);       // ring stages consumed per tile
   // q-th tile of this unit (linear index m * n_tiles_n + n), -1 when the unit is done.
   //   n_inner: the unit walks ALL n-tiles of one m-tile before moving to its next m-tile, so the A tile is re-read
   //            by the same SMs back to back (L2 hits on the same die) instead of by up to n_tiles_n other CTA pairs;
@@ -187,6 +200,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::prefetch_tensormap(&tm_a_lo);
       ptx::prefetch_tensormap(&tm_b_lo);
     }
+    if (PASSES == 4) {
+      ptx::prefetch_tensormap(&tm_a_lo);
+      ptx::prefetch_tensormap(&tm_b_lo);
+      ptx::prefetch_tensormap(&tm_a_sf);
+      ptx::prefetch_tensormap(&tm_b_sf);
+    }
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -196,6 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bars->tmem_full[a], 1);
       ptx::mbar_init(&bars->tmem_empty[a], EW * CG);            // leader's copy collects both CTAs' warps
+      ptx::mbar_init(&bars->sf_free[a], 4 * CG);                // the four warps (one per lane quadrant) owning columns 0..31
     }
     ptx::fence_barrier_init();
   }
@@ -225,7 +245,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         for (int kb = 0; kb < n_steps; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* s = smem + stage * C::kStageBytes;
-          if (PASSES == 2) {
+          if (PASSES == 4) {
+            // fp16 (hi) stages first, then e2m1 (c4) stages with their scale-factor atoms; all bytes of both CTAs complete
+            // on the leader's full barrier
+            const bool f4 = kb >= n_kb;
+            const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), leader);
+            if (rank == 0)
+              ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * (kTileBytesA + C::kTileBytesB + (f4 ? C::kSfBytes : 0)));
+            const int c0 = f4 ? (kb - n_kb) * 128 : kb * BK;      // element coordinate (bytes for the uint8 c4 maps)
+            ptx::tma_load_2d_cg2_hint(s, f4 ? &tm_a_lo : &tm_a_hi, full_leader, c0, m0, pol_a);
+            ptx::tma_load_2d_cg2_hint(s + kTileBytesA, f4 ? &tm_b_lo : &tm_b_hi, full_leader, c0, n0, pol_b);
+            if (f4) {
+              // sf arrays viewed as [bytes / 256][256]: an atom (128 rows x 4 k-blocks) is 2 rows, a stage needs the two
+              // k-atoms (2 j, 2 j + 1) of a 128-row tile = 4 consecutive rows = 1 KB
+              const int apt = p.K / 64;                           // atoms per 128-row tile
+              const int ka = 2 * (kb - n_kb);
+              uint8_t* sfs = s + kTileBytesA + C::kTileBytesB;
+              ptx::tma_load_2d_cg2(sfs, &tm_a_sf, full_leader, 0, 2 * ((m0 >> 7) * apt + ka));
+              const int nt0 = ((tile % n_tiles_n) * BN) >> 7;     // first of the two weight row tiles of this n-tile
+              ptx::tma_load_2d_cg2(sfs + 1024, &tm_b_sf, full_leader, 0, 2 * (nt0 * apt + ka));
+              ptx::tma_load_2d_cg2(sfs + 2048, &tm_b_sf, full_leader, 0, 2 * ((nt0 + 1) * apt + ka));
+            }
+          } else if (PASSES == 2) {
             // uniform stage: one A tile + one B tile of 128-byte rows; fp16 (hi) stages first, then e5m2 (c8) stages
             const bool f8 = kb >= n_kb;
             const CUtensorMap* ma = f8 ? &tm_a_lo : &tm_a_hi;
@@ -304,6 +345,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           ptx::mbar_wait(&bars->full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t s = ptx::smem_u32(smem + stage * C::kStageBytes);
+          if (PASSES == 4) {
+            if (kb < n_kb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::mma_f16_ss_cg2(d_tmem, ptx::make_desc_k_sw128(s + k * 32), ptx::make_desc_k_sw128(s + kTileBytesA + k * 32),
+                                    idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
+              // scale factors of this stage: smem -> the first 24 columns of the OTHER accumulator (SFA 8 + SFB 16).
+              // The previous tile's epilogue has read those columns long before the fp16 stages of this tile are through;
+              // sf_free makes it a guarantee.  tcgen05.cp and tcgen05.mma of one thread execute in issue order, so the
+              // columns can be rewritten every stage without a wait.
+              const uint32_t sf_tmem = tmem_base + (acc ^ 1) * BN;
+              if (kb == n_kb && q_ > 0) {
+                ptx::mbar_wait(&bars->sf_free[acc ^ 1], ((q_ - 1) >> 1) & 1);
+                ptx::tc_fence_after();
+              }
+              const uint32_t sfs = s + kTileBytesA + C::kTileBytesB;
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                ptx::utccp_32x128b_cg2(sf_tmem + 4 * a, ptx::make_desc_sf(sfs + 512 * a));                  // SFA, k-atom a
+                ptx::utccp_32x128b_cg2(sf_tmem + 8 + 8 * a, ptx::make_desc_sf(sfs + 1024 + 512 * a));       // SFB rows 0..127
+                ptx::utccp_32x128b_cg2(sf_tmem + 8 + 8 * a + 4, ptx::make_desc_sf(sfs + 2048 + 512 * a));   // SFB rows 128..255
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {       // 4 x 32 bytes = 4 x 64 e2m1 of K; k-blocks (2k, 2k+1) = bytes 2(k&1).. of atom k>>1
+                const uint32_t id4 = ptx::make_idesc_mxf4(TM, BN, (k & 1) * 2);
+                ptx::mma_mxf4_ss_cg2(d_tmem, ptx::make_desc_k_sw128(s + k * 32), ptx::make_desc_k_sw128(s + kTileBytesA + k * 32),
+                                     id4, sf_tmem + 4 * (k >> 1), sf_tmem + 8 + 8 * (k >> 1), 1u);
+              }
+            }
+            ptx::mma_commit_cg2(&bars->empty[stage], 3);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (PASSES == 2) {
             constexpr uint32_t idesc8 = ptx::make_idesc_f16(TM, BN, 1 /*e5m2*/);
             const bool f8 = kb >= n_kb;
@@ -396,6 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
       };
       if (has_res) load_res(0);              // in flight while the accumulator is still being computed
+      uint32_t sfp_w = 0, sfq_w = 0;         // F4C GELU output: this row's scale bytes of the tile's k-blocks (P / Q part)
       ptx::mbar_wait(&bars->tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll
@@ -414,6 +490,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
         for (int v = 0; v < 8; ++v) bias4[v] = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + v);
         ptx::tmem_ld_wait();
+        if (PASSES == 4 && ci == 0 && half == 0) {
+          // columns 0..31 of this accumulator are in registers: the NEXT tile's e2m1 stages may put their scale factors there
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->sf_free[acc]), leader));
+        }
         if (EPI == EPI_F32 || EPI == EPI_F32_LN) {
           float csum = 0.f;
 #pragma unroll
@@ -466,6 +548,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               float* dst = p.out_f32 + static_cast<size_t>(rr) * p.N + gcol + gsub * 4;
               if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
             }
+          }
+        } else if (EPI == EPI_GELU_SPLIT && PASSES == 4) {
+          // FMT_F4C operand of fc2: this lane's 32 columns are exactly one scale block of each part.  Pass 1: GELU, hi
+          // halves into the staging row (granules 0..3), block maxima of x and of x - hi; pass 2: both e2m1 images
+          // (granule 4 = 32 nibbles of P = q4(x), granule 5 = Q = q4(x - hi)); the two scale bytes join the lane's words.
+          float ax = 0.f, al = 0.f;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint32_t hw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 b = bias4[2 * v + (e >> 1)];
+              ptx::f32x2 xp = ptx::add2(ptx::pack2(__uint_as_float(r[8 * v + 2 * e + 0]), __uint_as_float(r[8 * v + 2 * e + 1])),
+                                        (e & 1) ? ptx::pack2(b.z, b.w) : ptx::pack2(b.x, b.y));
+              xp = gelu_erf2(xp);
+              float x0, x1;
+              ptx::unpack2(xp, x0, x1);
+              const __half2 h01 = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h01);
+              hw[e] = *reinterpret_cast<const uint32_t*>(&h01);
+              ax = fmaxf(ax, fmaxf(fabsf(x0), fabsf(x1)));
+              al = fmaxf(al, fmaxf(fabsf(x0 - hf.x), fabsf(x1 - hf.y)));
+              r[8 * v + 2 * e + 0] = __float_as_uint(x0);
+              r[8 * v + 2 * e + 1] = __float_as_uint(x1);
+            }
+            *stg_at(stg, lane, v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          }
+          const uint32_t bp = op_ue8m0_of(ax), bq = op_ue8m0_of(al);
+          const ptx::f32x2 ip = ptx::splat2(op_ue8m0_inv(bp)), iq = ptx::splat2(op_ue8m0_inv(bq));
+          uint32_t pw[4], qw[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            uint32_t pa = 0, qa = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = __uint_as_float(r[8 * w + 2 * e + 0]), x1 = __uint_as_float(r[8 * w + 2 * e + 1]);
+              const float2 hf = __half22float2(__floats2half2_rn(x0, x1));
+              float a0, a1, l0, l1;
+              ptx::unpack2(ptx::mul2(ptx::pack2(x0, x1), ip), a0, a1);
+              ptx::unpack2(ptx::mul2(ptx::sub2(ptx::pack2(x0, x1), ptx::pack2(hf.x, hf.y)), iq), l0, l1);
+              pa |= op_e2m1x2(a0, a1) << (8 * e);
+              qa |= op_e2m1x2(l0, l1) << (8 * e);
+            }
+            pw[w] = pa; qw[w] = qa;
+          }
+          *stg_at(stg, lane, 4) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *stg_at(stg, lane, 5) = make_uint4(qw[0], qw[1], qw[2], qw[3]);
+          sfp_w |= bp << (8 * ((gcol >> 5) & 3));
+          sfq_w |= bq << (8 * ((gcol >> 5) & 3));
+          __syncwarp();
+          uint8_t* c4 = reinterpret_cast<uint8_t*>(p.out_lo);
+          uint4 vals[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = row_w + 4 * j + rsub;
+            if (rr >= p.M || gsub >= 6) continue;
+            void* dst = gsub < 4 ? static_cast<void*>(p.out_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8)
+                                 : static_cast<void*>(c4 + static_cast<size_t>(rr) * p.N + (gsub == 4 ? 0 : (p.N >> 1)) + (gcol >> 1));
+            if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
           }
         } else {
           // fp16 outputs: row = hi (granules 0..3, 32 halves) | second part (granules 4..7):
@@ -569,6 +712,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           }
         }
         __syncwarp();          // the buffer is rewritten by the next chunk
+      }
+      if (EPI == EPI_GELU_SPLIT && PASSES == 4) {
+        // scale bytes of row (row_w + lane): k-blocks colbase/32 .. +kChunks-1 of part P, the same + N/32 of part Q; they
+        // are adjacent bytes of one scale-factor atom (operand.cuh), written as one word (4 chunks) or half-word (2)
+        const int rr = row_w + lane;
+        if (rr < p.M) {
+          const int kb0 = colbase >> 5, apt = p.N / 64;
+          uint8_t* dp = p.out_sf + op_sf_offset(rr, kb0, apt);
+          uint8_t* dq = p.out_sf + op_sf_offset(rr, (p.N >> 5) + kb0, apt);
+          if (kChunks == 4) {
+            *reinterpret_cast<uint32_t*>(dp) = sfp_w;
+            *reinterpret_cast<uint32_t*>(dq) = sfq_w;
+          } else {
+            *reinterpret_cast<uint16_t*>(dp) = static_cast<uint16_t>(sfp_w >> (8 * (kb0 & 3)));
+            *reinterpret_cast<uint16_t*>(dq) = static_cast<uint16_t>(sfq_w >> (8 * (kb0 & 3)));
+          }
+        }
       }
       if (EPI == EPI_F32_LN) {
         // The two n-tiles of a row tile land in accumulators 0 and 1 back to back (n-inner order, N == 2 BN).  After
@@ -719,7 +879,8 @@ cudaError_t launch_one(const GemmMaps& m, const GemmParams& p, int num_sms, cuda
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, CS == 2 ? m.b_hi64 : m.b_hi, CS == 2 ? m.b_lo64 : m.b_lo, p);
+  return cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, CS == 2 ? m.b_hi64 : m.b_hi, CS == 2 ? m.b_lo64 : m.b_lo,
+                            PASSES == 4 ? m.a_sf : m.a_hi, PASSES == 4 ? m.b_sf : m.b_hi, p);
 }
 
 template <int CG, int BN, int PASSES, int EPI, int CS = 1, int EW = 8>
@@ -754,12 +915,32 @@ cudaError_t configure_gemm_tc() {
   if ((e = configure_one<2, 256, 2, EPI_QKV16, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 2, EPI_F32_LN>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 2, EPI_F32, 1, 16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_F32>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_GELU_SPLIT>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_QKV16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_F32, 1, 16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_GELU_SPLIT, 1, 16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_QKV16, 1, 16>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
                            int pair_cluster, int epi_warps, int num_sms, cudaStream_t st) {
   if (p.M <= 0) return cudaSuccess;
+  if (passes == 4) {
+    // FMT_F4C: CTA-pair 256 x 256 tiles only; K in whole e2m1 stages (256 nibbles = 128 bytes of the K-byte c4 row)
+    if (p.N % 256 != 0 || p.K % 128 != 0 || epi == EPI_F32_LN) return cudaErrorInvalidValue;
+    if (epi == EPI_QKV16 && p.N != 3 * kC) return cudaErrorInvalidValue;
+    if (epi == EPI_GELU_SPLIT && !p.out_sf) return cudaErrorInvalidValue;
+    if (epi_warps == 16) {
+      if (epi == EPI_F32) return launch_one<2, 256, 4, EPI_F32, 1, 16>(maps, p, num_sms, st);
+      if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 4, EPI_GELU_SPLIT, 1, 16>(maps, p, num_sms, st);
+      return launch_one<2, 256, 4, EPI_QKV16, 1, 16>(maps, p, num_sms, st);
+    }
+    if (epi == EPI_F32) return launch_one<2, 256, 4, EPI_F32>(maps, p, num_sms, st);
+    if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 4, EPI_GELU_SPLIT>(maps, p, num_sms, st);
+    return launch_one<2, 256, 4, EPI_QKV16>(maps, p, num_sms, st);
+  }
   if (cta_group == 2 || passes == 2) bn = 256;
   if (epi == EPI_F32_LN) {
     // needs: both 256-column halves of a row tile on the same CTA pair, back to back, in accumulators 0 and 1
@@ -828,6 +1009,25 @@ int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+// FMT_F4C scale-factor array (operand.cuh) viewed as [total_bytes / 256][256] bytes: {256 x 4} boxes, no swizzle, so a
+// box lands in shared memory as 1 KB of consecutive bytes = two 512-byte atoms (the two k-atoms of one e2m1 stage)
+int make_sf_map(CUtensorMap* out, const void* base, int64_t total_bytes) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return -1;
+  EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (total_bytes % 1024 != 0) return -2;
+  cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(total_bytes / 256)};
+  cuuint64_t strides[1] = {256};
+  cuuint32_t box[2] = {256, 4};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }

@@ -33,6 +33,7 @@ struct GemmParams {
   __half* out_hi;         // EPI_GELU_SPLIT
   __half* out_lo;
   __half* out_qkv;        // EPI_QKV16
+  uint8_t* out_sf;        // EPI_GELU_SPLIT with FMT_F4C: scale-factor array of the output operand (K_out = N)
   // L2 policy knobs (defaults chosen from ncu DRAM-traffic measurements): TMA eviction priority of the
   // activation (A) and weight (B) operand loads (0 normal, 1 evict_last, 2 evict_first) and streaming (evict-first)
   // output stores / residual loads
@@ -49,17 +50,21 @@ struct GemmParams {
 struct GemmMaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   CUtensorMap b_hi64, b_lo64;     // weight maps with 64-row boxes (multicast slices of the pair-cluster kernel)
+  CUtensorMap a_sf, b_sf;         // FMT_F4C: scale-factor arrays (make_sf_map)
 };
 
-// passes: 3 (split fp16), 1 (fp16) or 2 (FMT_F8C: fp16 main + e5m2 corrections; the *_lo maps are the uint8 c8 maps).
+// passes: 3 (split fp16), 1 (fp16), 2 (FMT_F8C: fp16 main + e5m2 corrections; the *_lo maps are the uint8 c8 maps) or
+// 4 (FMT_F4C: fp16 main + block-scaled e2m1 corrections; *_lo = uint8 c4 maps [rows, K bytes], *_sf = scale factors;
+// CTA-pair kernel only, N % 256 == 0, K % 128 == 0).
 // cta_group 1: one CTA per 128 x bn tile (bn 128 or 256, N % bn == 0);
 // cta_group 2: a CTA pair per 256 x 256 tile (tcgen05.mma.cta_group::2, N % 256 == 0, bn ignored).
 // pair_cluster 2 (F8C + cta_group 2 only): clusters of two CTA pairs sharing the weight tile through TMA multicast.
 // epi_warps 16 (F8C CTA-pair kernel, GELU / QKV epilogues): 16 epilogue warps per CTA instead of 8.
 cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, int passes, int bn, int cta_group,
                            int pair_cluster, int epi_warps, int num_sms, cudaStream_t st);
-cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
-                             const GemmParams& p, int epi, int fmt, cudaStream_t st);
+cudaError_t launch_gemm_simt(const __half* a_hi, const __half* a_lo, const uint8_t* a_sf, const __half* b_hi,
+                             const __half* b_lo, const uint8_t* b_sf, const GemmParams& p, int epi, int fmt,
+                             cudaStream_t st);
 // One-time per-device kernel attribute setup (dynamic shared memory opt-in); call outside graph capture.
 cudaError_t configure_gemm_tc();
 cudaError_t configure_attention();
@@ -67,6 +72,7 @@ cudaError_t configure_attention_mma();
 // Build a K-major fp16 operand map for a [rows, K] row-major matrix / a uint8 map for a [rows, row_bytes] c8 array.
 int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t K, int box_rows = 128);
 int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes, int box_rows = 128);
+int make_sf_map(CUtensorMap* out, const void* base, int64_t total_bytes);
 
 // ------------------------------------------------------------------ row-wise (one warp per 512-wide token row)
 struct LnParams {
@@ -78,23 +84,27 @@ struct LnParams {
 // op-level tests) and back (activation operands only).
 // absmax (optional, device float[2], zeroed by the caller): [0] = max |x| over the finite inputs, [1] = 1 if any input
 // was NaN / Inf -- the load-time range guard of d3d_load_weights.
-cudaError_t launch_split(const float* in, __half* hi, __half* second, int64_t rows, int K, int fmt, int is_weight,
-                         cudaStream_t st, float* absmax = nullptr);
-cudaError_t launch_merge(const __half* hi, const __half* second, float* out, int64_t rows, int K, int fmt,
-                         cudaStream_t st);
+// sf: the operand's scale-factor array (FMT_F4C only, else ignored / null).
+cudaError_t launch_split(const float* in, __half* hi, __half* second, uint8_t* sf, int64_t rows, int K, int fmt,
+                         int is_weight, cudaStream_t st, float* absmax = nullptr);
+cudaError_t launch_merge(const __half* hi, const __half* second, const uint8_t* sf, float* out, int64_t rows, int K,
+                         int fmt, cudaStream_t st);
+
+// FMT_F4C scale factors of `rows` rows in atom layout -> row-major [rows][K / 16] bytes (test read-back)
+cudaError_t launch_sf_rows(const uint8_t* sf, uint8_t* out, int64_t rows, int K, cudaStream_t st);
 
 // X = [x2d,y] . Wf^T + bf + spos[j] (+ tvec[sample]);  A = LN(X; ln1)  (MODEL:250, 230-233, 113-116, 127)
 cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, const float* wf_t /*[5][512]*/,
                            const float* bf, const float* spos /*[J][512]*/, const float* tvec, int64_t tvec_stride,
-                           LnParams ln1, float* X, __half* a_hi, __half* a_lo, int fmt, int64_t T, int J,
+                           LnParams ln1, float* X, __half* a_hi, __half* a_lo, uint8_t* a_sf, int fmt, int64_t T, int J,
                            int tokens_per_clip, cudaStream_t st);
 // X = LN(X; post) (+ tpos[f]) (+ tvec[sample]);  A = LN(X; ln1)   (MODEL:236/245, 239-242, 113-116, 127)
 cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos /*[F][512] or null*/,
                                    const float* tvec, int64_t tvec_stride, LnParams ln1, __half* a_hi,
-                                   __half* a_lo, int fmt, int64_t T, int J, int F, cudaStream_t st);
+                                   __half* a_lo, uint8_t* a_sf, int fmt, int64_t T, int J, int F, cudaStream_t st);
 // A = LN(X; ln)  (MODEL:128 norm2)
-cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int fmt, int64_t T,
-                            cudaStream_t st);
+cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, uint8_t* a_sf, int fmt,
+                            int64_t T, cudaStream_t st);
 // out = LN(x) fp32 (stand-alone exhibit / op test)
 cudaError_t launch_ln_f32(const float* x, LnParams ln, float eps, float* out, int64_t T, cudaStream_t st);
 
@@ -143,10 +153,11 @@ int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half*
 // spatial mode of the same kernel (J == 17): units of (clip, 7 frames = 119 consecutive tokens, head), block-diagonal mask
 int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int64_t tokens,
                               int F);
-cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, int fmt, int B, int F, int num_sms, cudaStream_t st);
+// o_sf: scale-factor array of the output operand (FMT_F4C; null otherwise)
+cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, uint8_t* o_sf, int fmt, int B, int F, int num_sms, cudaStream_t st);
 cudaError_t configure_attention_tc();
-cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, int fmt, int B, int F, int J, int num_sms,
-                                    cudaStream_t st);
+cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, uint8_t* o_sf, int fmt, int B, int F, int J,
+                                    int num_sms, cudaStream_t st);
 // CUDA-core validation kernels (fp32 arithmetic on the same packed input)
 cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                       int J, cudaStream_t st);

@@ -14,14 +14,26 @@
 //         into the SAME fp32 TMEM accumulator; they only centre the small factors in e5m2's normal range.
 //         Cost: 2 tensor-pipe units instead of 3.  Parity (tools/precision_probe.py, mode f8c52): sampler
 //         max-abs 5.3e-4 / 9.1e-4 at F = 27 / 81 against the 1e-2 bar.
+//     FMT_F4C     (D3D_GEMM_TC_F4C): the same two correction products in BLOCK-SCALED e2m1 (mxfp4: one ue8m0 power-of-two
+//         scale per 32 consecutive elements of K), which tcgen05.mma kind::mxf4.block_scale multiplies at 4x the fp16
+//         rate: 1 + 2/4 = 1.5 tensor-pipe units and 3.06 instead of 4 operand bytes per element.  The second array holds
+//           c4 [rows][K bytes]   : K nibbles P | K nibbles Q (element 2i in the low nibble of byte i)
+//                                  activations: P = q4(x), Q = q4(x - hi);  weights: P = q4(w - hi), Q = q4(w)
+//           sf [rows/128][K/64][512 bytes] at byte offset rows_alloc * K: the scale bytes of a 128-row tile in the
+//                                  layout tcgen05.cp.32x128b.warpx4 copies into TMEM -- scale of (row r, k-block kb of
+//                                  32 elements of the 2K-long c4 row) at  atom (kb / 4):  16 (r % 32) + 4 (r / 32) + kb % 4
+//         D = A_hi.B_hi (kind::f16) + A_c4.B_c4 over K' = 2K (kind::mxf4).  The hardware applies the scales, so no fixed
+//         power-of-two centring is needed.  Parity (tools/precision_probe.py, mode f4c): sampler max-abs 9.1e-4 / 1.6e-3
+//         at F = 27 / 243 (clip off), 1.4e-3 / 2.9e-3 (clip on) against the 1e-2 bar.
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda_fp4.h>
 #include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace d3d {
 
-enum OperandFmt { FMT_SPLIT16 = 0, FMT_F8C = 1 };
+enum OperandFmt { FMT_SPLIT16 = 0, FMT_F8C = 1, FMT_F4C = 2 };
 
 constexpr float kActHiScale = 1.0f / 256.0f;   // activations: e5m2(x * 2^-8)
 constexpr float kActLoScale = 16.0f;           //              e5m2((x - hi) * 2^4)
@@ -42,6 +54,40 @@ __device__ __forceinline__ float op_e5m2_to_float(uint8_t v) {
   const __half_raw hr = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(v), __NV_E5M2);
   return __half2float(__half(hr));
 }
+
+// ---------------------------------------------------------------- FMT_F4C helpers
+// ue8m0 scale byte (value 2^(byte - 127)) for a block whose largest magnitude is amax: the smallest power of two s with
+// amax / s <= 6 (the e2m1 maximum), so the block maximum lands in (3, 6].  amax = 0 gives byte 0 (and q4 = 0).
+__device__ __forceinline__ uint32_t op_ue8m0_of(float amax) {
+  const uint32_t bits = __float_as_uint(amax * (1.0f / 6.0f));
+  const uint32_t e = (bits + 0x7fffffu) >> 23;          // exponent, +1 unless the mantissa is zero
+  return e > 253u ? 253u : e;                            // 255 is NaN in ue8m0; 254 has no finite inverse below
+}
+// 1 / 2^(byte - 127) as a float (byte in [0, 253])
+__device__ __forceinline__ float op_ue8m0_inv(uint32_t byte) { return __uint_as_float((254u - byte) << 23); }
+__device__ __forceinline__ float op_ue8m0_val(uint32_t byte) { return byte ? __uint_as_float(byte << 23) : 5.877471754111438e-39f; }
+// two floats -> one byte of two e2m1 values (x in the low nibble), round-to-nearest-even, saturating at +-6
+__device__ __forceinline__ uint32_t op_e2m1x2(float x, float y) {
+  return static_cast<uint32_t>(__nv_cvt_float2_to_fp4x2(make_float2(x, y), __NV_E2M1, cudaRoundNearest));
+}
+// eight floats -> 4 bytes
+__device__ __forceinline__ uint32_t op_e2m1x8(const float* v, float inv) {
+  return op_e2m1x2(v[0] * inv, v[1] * inv) | (op_e2m1x2(v[2] * inv, v[3] * inv) << 8) |
+         (op_e2m1x2(v[4] * inv, v[5] * inv) << 16) | (op_e2m1x2(v[6] * inv, v[7] * inv) << 24);
+}
+__device__ __forceinline__ float op_e2m1_to_float(uint32_t nibble) {
+  const float mag[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
+  const float m = mag[nibble & 7u];
+  return (nibble & 8u) ? -m : m;
+}
+// byte offset of the scale of (row, k-block kb) inside an operand's sf array; apt = atoms per 128-row tile = K / 64
+__host__ __device__ __forceinline__ size_t op_sf_offset(int64_t row, int kb, int apt) {
+  const int64_t tile = row >> 7;
+  const int r = static_cast<int>(row & 127);
+  return (static_cast<size_t>(tile) * apt + (kb >> 2)) * 512 + 16 * (r & 31) + 4 * (r >> 5) + (kb & 3);
+}
+// byte offset of an operand's sf array behind its c4 bytes (rows_alloc = allocated rows, a multiple of 128)
+__host__ __device__ __forceinline__ size_t op_sf_base(int64_t rows_alloc, int K) { return static_cast<size_t>(rows_alloc) * K; }
 
 // (x0, x1) -> hi pair and fp16 lo pair
 __device__ __forceinline__ void op_split16(float x0, float x1, uint32_t& hi, uint32_t& lo) {

@@ -401,6 +401,45 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory descriptor of a tcgen05.cp.32x128b source: 32 rows x 16 bytes stored contiguously (row r at 16 r), i.e.
+// four 8-row x 16-byte core matrices 128 bytes apart, K-major, no swizzle: SBO = 128 B, LBO unused (one core matrix
+// along K), version 1, layout type 0.  This is the 512-byte scale-factor atom of operand.cuh.
+__device__ __forceinline__ uint64_t make_desc_sf(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+// smem -> TMEM copy of one scale-factor atom: 32 lanes x 128 bits (4 columns), replicated into the four lane quadrants.
+// Executes in issue order with the tcgen05.mma of the same thread (no wait in between).  cta_group::2: issued by the
+// leader, performed in BOTH CTAs of the pair from the same shared-memory offset to the same TMEM address.
+__device__ __forceinline__ void utccp_32x128b_cg2(uint32_t tmem_dst, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(desc) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B, kind::mxf4 (packed e2m1 operands in shared memory, K = 64 per instruction, 4x the
+// kind::f16 rate) with one ue8m0 scale per 32 elements of K for every row of A and B (scale_vec::2X), read from TMEM:
+// sfa / sfb = TMEM addresses of the 4 (A: 128 rows per CTA) / 8 (B: 256 rows) scale columns; which 2 of the 4 bytes of
+// a column this MMA uses is the SF id in the instruction descriptor.
+__device__ __forceinline__ void mma_mxf4_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t sfa, uint32_t sfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+      : "memory");
+}
+// Block-scaled instruction descriptor, kind::mxf4: A / B format e2m1 (= 1) at bits [7,10) / [10,13), K-major operands,
+// N>>3 at [17,23), scale format ue8m0 (bit 23), M>>4 at [24,29), K = 64 (bit 31 = 0); the per-MMA SF ids go to bits
+// [4,6) (B) and [29,31) (A).  (cute/arch/mma_sm100_desc.hpp InstrDescriptorBlockScaled.)
+__host__ __device__ constexpr uint32_t make_idesc_mxf4(uint32_t M, uint32_t N, uint32_t sf_id) {
+  return (sf_id << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24) | (sf_id << 29);
+}
+
 // Instruction descriptor, kind::f16: fp32 accumulate (bits[4,6)=1), A/B format (bits[7,10),[10,13): 0 fp16,
 // 1 bf16), both operands K-major (bits 15,16 = 0), N>>3 at bits [17,23), M>>4 at bits [24,29).
 // kind::f8f6f4 uses the same layout with A/B format 0 = e4m3, 1 = e5m2.

@@ -9,6 +9,7 @@
 //   tta_merge, mpjpe   G-tta  : RUN:583-588, LOSS:15-27
 #include "kernels.cuh"
 #include "operand.cuh"
+#include "ptx.cuh"
 
 namespace d3d {
 namespace {
@@ -40,34 +41,89 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int lane, const
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(p + 128 * i + 4 * lane) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
-// GEMM A operand of the row (K = 512) in the handle's operand format (operand.cuh)
+// GEMM A operand of token row `row` (K = 512) in the handle's operand format (operand.cuh); `second` / `sf` are the BASE
+// pointers of the operand's second array and (FMT_F4C) its scale-factor array.
 template <int FMT>
-__device__ __forceinline__ void store_operand(__half* __restrict__ hi, __half* __restrict__ second, int lane,
-                                              const float (&v)[16]) {
+__device__ __forceinline__ void store_operand(__half* __restrict__ hi, __half* __restrict__ second,
+                                              uint8_t* __restrict__ sf, int64_t row, int lane, const float (&v)[16]) {
+  if (FMT != FMT_F4C) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float x[4] = {v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
+      op_store4<FMT>(hi + row * kC, second + row * kC, kC, 128 * i + 4 * lane, x);
+    }
+    return;
+  }
+  // FMT_F4C: the lane's 4 columns of chunk i belong to the 32-column block (4 i + lane / 8).  The scale byte is a
+  // monotone function of the block maximum, so the 8 lanes of a block reduce the two BYTES (P: q4(x), k-blocks 0..15;
+  // Q: q4(x - hi), k-blocks 16..31) packed in one register with three shuffles + packed-halfword maxima.
+  uint8_t* c4 = reinterpret_cast<uint8_t*>(second) + row * kC;
+  __half* hrow = hi + row * kC;
+  // scale bytes of (row, k-block 4 i + g) sit at sf_row + 512 i + g (P) and sf_row + 512 (4 + i) + g (Q)
+  uint8_t* sf_row = sf + (static_cast<size_t>(row >> 7) * (kC / 64)) * 512 + 16 * (row & 31) + 4 * ((row & 127) >> 5) + (lane >> 3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float x[4] = {v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
-    op_store4<FMT>(hi, second, kC, 128 * i + 4 * lane, x);
+    float x[4], l[4];
+    const __half2 h01 = __floats2half2_rn(v[4 * i], v[4 * i + 1]), h23 = __floats2half2_rn(v[4 * i + 2], v[4 * i + 3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const ptx::f32x2 x01 = ptx::pack2(v[4 * i], v[4 * i + 1]), x23 = ptx::pack2(v[4 * i + 2], v[4 * i + 3]);
+    const ptx::f32x2 l01 = ptx::sub2(x01, ptx::pack2(f01.x, f01.y)), l23 = ptx::sub2(x23, ptx::pack2(f23.x, f23.y));
+    ptx::unpack2(l01, l[0], l[1]);
+    ptx::unpack2(l23, l[2], l[3]);
+    const float ax = fmaxf(fmaxf(fabsf(v[4 * i]), fabsf(v[4 * i + 1])), fmaxf(fabsf(v[4 * i + 2]), fabsf(v[4 * i + 3])));
+    const float al = fmaxf(fmaxf(fabsf(l[0]), fabsf(l[1])), fmaxf(fabsf(l[2]), fabsf(l[3])));
+    uint32_t bb = op_ue8m0_of(ax) | (op_ue8m0_of(al) << 16);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) bb = __vmaxu2(bb, __shfl_xor_sync(0xffffffffu, bb, o));
+    const uint32_t bp = bb & 0xffu, bq = bb >> 16;
+    const ptx::f32x2 ip = ptx::splat2(op_ue8m0_inv(bp)), iq = ptx::splat2(op_ue8m0_inv(bq));
+    const int col = 128 * i + 4 * lane;
+    *reinterpret_cast<uint2*>(hrow + col) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    ptx::unpack2(ptx::mul2(x01, ip), x[0], x[1]);
+    ptx::unpack2(ptx::mul2(x23, ip), x[2], x[3]);
+    *reinterpret_cast<uint16_t*>(c4 + (col >> 1)) = static_cast<uint16_t>(op_e2m1x2(x[0], x[1]) | (op_e2m1x2(x[2], x[3]) << 8));
+    ptx::unpack2(ptx::mul2(l01, iq), l[0], l[1]);
+    ptx::unpack2(ptx::mul2(l23, iq), l[2], l[3]);
+    *reinterpret_cast<uint16_t*>(c4 + (kC >> 1) + (col >> 1)) =
+        static_cast<uint16_t>(op_e2m1x2(l[0], l[1]) | (op_e2m1x2(l[2], l[3]) << 8));
+    if ((lane & 7) == 0) {       // lanes 0, 8, 16, 24: four adjacent bytes of one scale-factor atom
+      sf_row[512 * i] = static_cast<uint8_t>(bp);
+      sf_row[512 * (4 + i)] = static_cast<uint8_t>(bq);
+    }
   }
 }
 
-// y = (x - mean) * rstd * gamma + beta over 512 columns held by the warp (two-pass variance in registers).
+// y = (x - mean) * rstd * gamma + beta over 512 columns held by the warp (two-pass variance in registers).  The
+// element-wise work runs on packed fp32 pairs (FADD2 / FFMA2 / FMUL2: two IEEE-rn operations per issue slot): with the
+// block-scaled operand format these kernels are bound by instruction issue, not by HBM.
 __device__ __forceinline__ void layernorm_row(const float (&x)[16], const float* __restrict__ gamma,
                                               const float* __restrict__ beta, float eps, int lane, float (&y)[16]) {
-  float s = 0.f;
+  ptx::f32x2 xp[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s += x[i];
-  const float mean = warp_sum(s) * (1.0f / kC);
-  float q = 0.f;
+  for (int i = 0; i < 8; ++i) xp[i] = ptx::pack2(x[2 * i], x[2 * i + 1]);
+  ptx::f32x2 sp = ptx::add2(ptx::add2(ptx::add2(xp[0], xp[1]), ptx::add2(xp[2], xp[3])),
+                            ptx::add2(ptx::add2(xp[4], xp[5]), ptx::add2(xp[6], xp[7])));
+  float s0, s1;
+  ptx::unpack2(sp, s0, s1);
+  const float mean = warp_sum(s0 + s1) * (1.0f / kC);
+  const ptx::f32x2 nm = ptx::splat2(-mean);
+  ptx::f32x2 qp = ptx::splat2(0.f);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
-  const float var = warp_sum(q) * (1.0f / kC);
-  const float rstd = 1.0f / sqrtf(var + eps);
-  float g[16], b[16];
-  load_row_ldg(gamma, lane, g);
-  load_row_ldg(beta, lane, b);
+  for (int i = 0; i < 8; ++i) {
+    xp[i] = ptx::add2(xp[i], nm);
+    qp = ptx::fma2(xp[i], xp[i], qp);
+  }
+  ptx::unpack2(qp, s0, s1);
+  const float var = warp_sum(s0 + s1) * (1.0f / kC);
+  const ptx::f32x2 rstd = ptx::splat2(1.0f / sqrtf(var + eps));
 #pragma unroll
-  for (int i = 0; i < 16; ++i) y[i] = fmaf((x[i] - mean) * rstd, g[i], b[i]);
+  for (int i = 0; i < 4; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + 128 * i + 4 * lane));
+    ptx::unpack2(ptx::fma2(ptx::mul2(xp[2 * i], rstd), ptx::pack2(g.x, g.y), ptx::pack2(b.x, b.y)), y[4 * i], y[4 * i + 1]);
+    ptx::unpack2(ptx::fma2(ptx::mul2(xp[2 * i + 1], rstd), ptx::pack2(g.z, g.w), ptx::pack2(b.z, b.w)), y[4 * i + 2], y[4 * i + 3]);
+  }
 }
 
 template <int FMT>
@@ -75,7 +131,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 lift_ln_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, const float* __restrict__ x5,
                const float* __restrict__ wf_t, const float* __restrict__ bf, const float* __restrict__ spos,
                const float* __restrict__ tvec, int64_t tvec_stride, LnParams ln1, float* __restrict__ X,
-               __half* __restrict__ a_hi, __half* __restrict__ a_lo, int64_t T, int J, int tokens_per_clip) {
+               __half* __restrict__ a_hi, __half* __restrict__ a_lo, uint8_t* __restrict__ a_sf, int64_t T, int J,
+               int tokens_per_clip) {
   const int lane = threadIdx.x & 31;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -111,14 +168,14 @@ lift_ln_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, cons
   store_row(X + t * kC, lane, v);
   float a[16];
   layernorm_row(v, ln1.gamma, ln1.beta, 1e-6f, lane, a);
-  store_operand<FMT>(a_hi + t * kC, a_lo + t * kC, lane, a);
+  store_operand<FMT>(a_hi, a_lo, a_sf, t, lane, a);
 }
 
 template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __restrict__ tpos,
                        const float* __restrict__ tvec, int64_t tvec_stride, LnParams ln1, __half* __restrict__ a_hi,
-                       __half* __restrict__ a_lo, int64_t T, int J, int F) {
+                       __half* __restrict__ a_lo, uint8_t* __restrict__ a_sf, int64_t T, int J, int F) {
   const int lane = threadIdx.x & 31;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -137,20 +194,20 @@ postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __rest
   }
   store_row(X + t * kC, lane, z);
   layernorm_row(z, ln1.gamma, ln1.beta, 1e-6f, lane, x);
-  store_operand<FMT>(a_hi + t * kC, a_lo + t * kC, lane, x);
+  store_operand<FMT>(a_hi, a_lo, a_sf, t, lane, x);
 }
 
 template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 ln_split_kernel(const float* __restrict__ X, LnParams ln, float eps, __half* __restrict__ a_hi,
-                __half* __restrict__ a_lo, int64_t T) {
+                __half* __restrict__ a_lo, uint8_t* __restrict__ a_sf, int64_t T) {
   const int lane = threadIdx.x & 31;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   if (t >= T) return;
   float x[16], y[16];
   load_row(X + t * kC, lane, x);
   layernorm_row(x, ln.gamma, ln.beta, eps, lane, y);
-  store_operand<FMT>(a_hi + t * kC, a_lo + t * kC, lane, y);
+  store_operand<FMT>(a_hi, a_lo, a_sf, t, lane, y);
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -287,6 +344,87 @@ __global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ 
     if (bad) absmax[1] = 1.0f;
   }
 }
+// FMT_F4C split: one thread per 32-element block (row, kb) of the [rows, K] input: hi, both nibble parts and both scale
+// bytes.  Activations: P = q4(x), Q = q4(x - hi); weights: P = q4(w - hi), Q = q4(w)  (operand.cuh).
+__global__ void split_f4c_kernel(const float* __restrict__ in, __half* __restrict__ hi, uint8_t* __restrict__ c4,
+                                 uint8_t* __restrict__ sf, int64_t rows, int K, int is_weight, float* __restrict__ absmax) {
+  const int bpr = K / 32;                       // blocks per row and part
+  const int64_t n_blocks = rows * bpr;
+  float amax_all = 0.f;
+  bool bad = false;
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; b < n_blocks;
+       b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = b / bpr;
+    const int kb = static_cast<int>(b - row * bpr);
+    const float* src = in + row * K + kb * 32;
+    float x[32], l[32];
+    float ax = 0.f, al = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(src + e);
+      x[e] = t.x; x[e + 1] = t.y; x[e + 2] = t.z; x[e + 3] = t.w;
+    }
+    uint32_t hw[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      const __half h0 = __float2half_rn(x[e]), h1 = __float2half_rn(x[e + 1]);
+      hw[e >> 1] = op_pack_h2(h0, h1);
+      l[e] = x[e] - __half2float(h0);
+      l[e + 1] = x[e + 1] - __half2float(h1);
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (!isfinite(x[e])) bad = true;
+      ax = fmaxf(ax, fabsf(x[e]));
+      al = fmaxf(al, fabsf(l[e]));
+    }
+    amax_all = fmaxf(amax_all, ax);
+    uint4* hdst = reinterpret_cast<uint4*>(hi + row * K + kb * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) hdst[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+    const float* pv = is_weight ? l : x;       // part P
+    const float* qv = is_weight ? x : l;       // part Q
+    const uint32_t bp = op_ue8m0_of(is_weight ? al : ax), bq = op_ue8m0_of(is_weight ? ax : al);
+    const float ip = op_ue8m0_inv(bp), iq = op_ue8m0_inv(bq);
+    uint8_t* crow = c4 + row * K;
+    *reinterpret_cast<uint4*>(crow + kb * 16) =
+        make_uint4(op_e2m1x8(pv, ip), op_e2m1x8(pv + 8, ip), op_e2m1x8(pv + 16, ip), op_e2m1x8(pv + 24, ip));
+    *reinterpret_cast<uint4*>(crow + (K >> 1) + kb * 16) =
+        make_uint4(op_e2m1x8(qv, iq), op_e2m1x8(qv + 8, iq), op_e2m1x8(qv + 16, iq), op_e2m1x8(qv + 24, iq));
+    sf[op_sf_offset(row, kb, K / 64)] = static_cast<uint8_t>(bp);
+    sf[op_sf_offset(row, bpr + kb, K / 64)] = static_cast<uint8_t>(bq);
+  }
+  if (absmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax_all = fmaxf(amax_all, __shfl_xor_sync(0xffffffffu, amax_all, o));
+    if ((threadIdx.x & 31) == 0 && isfinite(amax_all)) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(amax_all));
+    if (bad) absmax[1] = 1.0f;
+  }
+}
+// FMT_F4C activation operand -> fp32: hi + q4(Q) * scale
+__global__ void merge_f4c_kernel(const __half* __restrict__ hi, const uint8_t* __restrict__ c4, const uint8_t* __restrict__ sf,
+                                 float* __restrict__ out, int64_t n, int K) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / K;
+    const int col = static_cast<int>(i - row * K);
+    const uint32_t byte = c4[row * K + (K >> 1) + (col >> 1)];
+    const float q = op_e2m1_to_float((col & 1) ? (byte >> 4) : (byte & 15u));
+    const float sc = op_ue8m0_val(sf[op_sf_offset(row, K / 32 + col / 32, K / 64)]);
+    out[i] = __half2float(hi[i]) + q * sc;
+  }
+}
+
+// scale-factor atoms -> row-major [rows][K / 16] bytes (test read-back of a FMT_F4C operand)
+__global__ void sf_rows_kernel(const uint8_t* __restrict__ sf, uint8_t* __restrict__ out, int64_t n, int K) {
+  const int per_row = K / 16;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / per_row;
+    out[i] = sf[op_sf_offset(row, static_cast<int>(i - row * per_row), K / 64)];
+  }
+}
+
 // activation operand -> fp32 (hi + lo); for FMT_F8C the lo term comes back from its e5m2 image
 __global__ void merge_kernel(const __half* __restrict__ hi, const __half* __restrict__ second, float* __restrict__ out,
                              int64_t n, int K, int fmt) {
@@ -312,43 +450,57 @@ inline unsigned flat_grid(int64_t n) {
 
 }  // namespace
 
-cudaError_t launch_split(const float* in, __half* hi, __half* second, int64_t rows, int K, int fmt, int is_weight,
-                         cudaStream_t st, float* absmax) {
+cudaError_t launch_split(const float* in, __half* hi, __half* second, uint8_t* sf, int64_t rows, int K, int fmt,
+                         int is_weight, cudaStream_t st, float* absmax) {
   const int64_t n = rows * K;
   if (n <= 0) return cudaSuccess;
-  split_kernel<<<flat_grid(n), 256, 0, st>>>(in, hi, second, n, K, fmt, is_weight, absmax);
+  if (fmt == FMT_F4C) {
+    if (K % 64 != 0 || !sf || !second) return cudaErrorInvalidValue;
+    split_f4c_kernel<<<flat_grid(n / 32), 128, 0, st>>>(in, hi, reinterpret_cast<uint8_t*>(second), sf, rows, K, is_weight,
+                                                       absmax);
+  } else {
+    split_kernel<<<flat_grid(n), 256, 0, st>>>(in, hi, second, n, K, fmt, is_weight, absmax);
+  }
   return cudaGetLastError();
 }
-cudaError_t launch_merge(const __half* hi, const __half* second, float* out, int64_t rows, int K, int fmt,
-                         cudaStream_t st) {
+cudaError_t launch_merge(const __half* hi, const __half* second, const uint8_t* sf, float* out, int64_t rows, int K,
+                         int fmt, cudaStream_t st) {
   const int64_t n = rows * K;
   if (n <= 0) return cudaSuccess;
-  merge_kernel<<<flat_grid(n), 256, 0, st>>>(hi, second, out, n, K, fmt);
+  if (fmt == FMT_F4C) merge_f4c_kernel<<<flat_grid(n), 256, 0, st>>>(hi, reinterpret_cast<const uint8_t*>(second), sf, out, n, K);
+  else merge_kernel<<<flat_grid(n), 256, 0, st>>>(hi, second, out, n, K, fmt);
+  return cudaGetLastError();
+}
+cudaError_t launch_sf_rows(const uint8_t* sf, uint8_t* out, int64_t rows, int K, cudaStream_t st) {
+  const int64_t n = rows * (K / 16);
+  if (n <= 0) return cudaSuccess;
+  sf_rows_kernel<<<flat_grid(n), 256, 0, st>>>(sf, out, n, K);
   return cudaGetLastError();
 }
 cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, const float* wf_t, const float* bf,
                            const float* spos, const float* tvec, int64_t tvec_stride, LnParams ln1, float* X,
-                           __half* a_hi, __half* a_lo, int fmt, int64_t T, int J, int tokens_per_clip,
+                           __half* a_hi, __half* a_lo, uint8_t* a_sf, int fmt, int64_t T, int J, int tokens_per_clip,
                            cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
-  auto kern = fmt == FMT_F8C ? lift_ln_kernel<FMT_F8C> : lift_ln_kernel<FMT_SPLIT16>;
-  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(x2d, y, x5, wf_t, bf, spos, tvec, tvec_stride, ln1, X, a_hi, a_lo, T,
+  auto kern = fmt == FMT_F4C ? lift_ln_kernel<FMT_F4C> : fmt == FMT_F8C ? lift_ln_kernel<FMT_F8C> : lift_ln_kernel<FMT_SPLIT16>;
+  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(x2d, y, x5, wf_t, bf, spos, tvec, tvec_stride, ln1, X, a_hi, a_lo, a_sf, T,
                                                  J, tokens_per_clip);
   return cudaGetLastError();
 }
 cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos, const float* tvec,
-                                   int64_t tvec_stride, LnParams ln1, __half* a_hi, __half* a_lo, int fmt, int64_t T,
-                                   int J, int F, cudaStream_t st) {
+                                   int64_t tvec_stride, LnParams ln1, __half* a_hi, __half* a_lo, uint8_t* a_sf, int fmt,
+                                   int64_t T, int J, int F, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
-  auto kern = fmt == FMT_F8C ? postnorm_add_ln_kernel<FMT_F8C> : postnorm_add_ln_kernel<FMT_SPLIT16>;
-  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, tpos, tvec, tvec_stride, ln1, a_hi, a_lo, T, J, F);
+  auto kern = fmt == FMT_F4C ? postnorm_add_ln_kernel<FMT_F4C>
+            : fmt == FMT_F8C ? postnorm_add_ln_kernel<FMT_F8C> : postnorm_add_ln_kernel<FMT_SPLIT16>;
+  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, tpos, tvec, tvec_stride, ln1, a_hi, a_lo, a_sf, T, J, F);
   return cudaGetLastError();
 }
-cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, int fmt, int64_t T,
-                            cudaStream_t st) {
+cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, uint8_t* a_sf, int fmt,
+                            int64_t T, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
-  auto kern = fmt == FMT_F8C ? ln_split_kernel<FMT_F8C> : ln_split_kernel<FMT_SPLIT16>;
-  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, ln, eps, a_hi, a_lo, T);
+  auto kern = fmt == FMT_F4C ? ln_split_kernel<FMT_F4C> : fmt == FMT_F8C ? ln_split_kernel<FMT_F8C> : ln_split_kernel<FMT_SPLIT16>;
+  kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, ln, eps, a_hi, a_lo, a_sf, T);
   return cudaGetLastError();
 }
 cudaError_t launch_ln_f32(const float* x, LnParams ln, float eps, float* out, int64_t T, cudaStream_t st) {

@@ -51,7 +51,11 @@ enum {
   D3D_GEMM_SIMT_FP32 = 2, /* CUDA-core fp32 validation kernel (same operands as SPLIT3, no tensor cores) */
   D3D_GEMM_TC_F8C = 3,    /* default of the Python drop-ins: fp16 main product + one e5m2 (kind::f8f6f4) product carrying both correction terms:
                              2 tensor-pipe units instead of 3, within the parity bar */
-  D3D_GEMM_SIMT_F8C = 4   /* CUDA-core validation kernel on the F8C operand format */
+  D3D_GEMM_SIMT_F8C = 4,  /* CUDA-core validation kernel on the F8C operand format */
+  D3D_GEMM_TC_F4C = 5,    /* fp16 main product + one BLOCK-SCALED e2m1 product (kind::mxf4.block_scale, one ue8m0 scale per 32
+                             elements of K, 4x the fp16 rate) carrying both correction terms: 1.5 tensor-pipe units, 3.06 operand
+                             bytes per element */
+  D3D_GEMM_SIMT_F4C = 6   /* CUDA-core validation kernel on the F4C operand format */
 };
 /* Attention kernels. */
 enum {
@@ -218,7 +222,9 @@ D3D_API int d3d_op_linear_ln(d3d_handle* h, const float* a_dev, const float* w_d
 
 /* Runs one attention core like d3d_op_attention but returns the result in the raw GEMM A-operand format the proj
  * GEMM consumes: hi_out_dev [T, C] fp16 and second_out_dev [T, 2*C] bytes (operand format of the handle's gemm_mode:
- * fp16 lo[C], or uint8 e5m2(x * 2^-8)[C] | e5m2((x - hi) * 2^4)[C]). */
+ * fp16 lo[C], or uint8 e5m2(x * 2^-8)[C] | e5m2((x - hi) * 2^4)[C]; for the D3D_GEMM_*_F4C modes the buffer holds
+ * [T][C] bytes = C e2m1 nibbles of q4(x) | C nibbles of q4(x - hi) per row, followed by [T][C/16] ue8m0 scale bytes per
+ * row (k-blocks of 32 elements: 16 of the first part, then 16 of the second), element 2i in the low nibble of byte i). */
 D3D_API int d3d_debug_attention_operand(d3d_handle* h, const float* qkv_dev, void* hi_out_dev, void* second_out_dev,
                                 int32_t B, int32_t spatial, int32_t attn_mode, void* stream);
 

@@ -114,6 +114,53 @@ def test_f8c_epilogue_warp_variants(eng27, monkeypatch, ew, act):
         assert (x - y).abs().max().item() < 1e-4
 
 
+F4C_SHAPES = [(128, 1536, 512), (200, 512, 512), (1000, 1024, 512), (459, 512, 1024), (1, 512, 512), (300, 256, 128),
+              (74 * 256 * 3 + 77, 512, 512)]
+
+
+@pytest.mark.parametrize("mode", [_lib.GEMM_TC_F4C, _lib.GEMM_SIMT_F4C])
+@pytest.mark.parametrize("M,N,K", F4C_SHAPES)
+def test_linear_parity_f4c(eng27, mode, M, N, K):
+    """FMT_F4C (fp16 main product + block-scaled e2m1 correction products, kind::mxf4.block_scale) against fp64: the
+    tensor-core kernel and its CUDA-core twin.  The corrections carry ~2 significant bits of a 2^-11 term, so the bound
+    is looser than F8C's 2e-4 and far below single-pass fp16's 2e-3.  Shapes: one tile, ragged M, K = 1024 (8 e2m1
+    stages), a single row, the minimum K (one e2m1 stage), and more tiles than CTA pairs (persistent loop: the scale
+    factors of tile q live in the accumulator of tile q - 1)."""
+    a, w, b = _rand((M, K), 1), _rand((N, K), 2, 0.05), _rand((N,), 3, 0.1)
+    res = _rand((M, N), 4)
+    ref = (a.double() @ w.double().T + b.double() + res.double())
+    out = eng27.op_linear(a.cuda(), w.cuda(), b.cuda(), residual=res.cuda(), act=0, gemm_mode=mode).cpu()
+    scale = (a.double().abs() @ w.double().abs().T).max().item()
+    err = (out.double() - ref).abs().max().item() / scale
+    assert err < 4e-4, f"relative error {err:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", F4C_SHAPES)
+def test_f4c_tc_matches_simt_elementwise(eng27, M, N, K):
+    """Same hi / e2m1 / scale-factor bytes in: the tcgen05 kernel (TMA-staged scale-factor atoms -> tcgen05.cp -> TMEM,
+    kind::mxf4.block_scale MMAs) and the CUDA-core kernel that decodes nibble x 2^(scale - 127) in fp32 form the same
+    products, so they differ only by fp32 accumulation order.  This is the bit-level check of the scale-factor layout,
+    the SF ids and the TMEM column assignment."""
+    a, w, b = _rand((M, K), 8).cuda(), _rand((N, K), 9, 0.05).cuda(), _rand((N,), 10).cuda()
+    x = eng27.op_linear(a, w, b, gemm_mode=_lib.GEMM_TC_F4C)
+    y = eng27.op_linear(a, w, b, gemm_mode=_lib.GEMM_SIMT_F4C)
+    assert (x - y).abs().max().item() < 3e-5
+
+
+@pytest.mark.parametrize("mode", [_lib.GEMM_TC_F4C, _lib.GEMM_SIMT_F4C])
+@pytest.mark.parametrize("ew", [8, 16])
+def test_linear_gelu_f4c_epilogue(eng27, monkeypatch, mode, ew):
+    """fc1 epilogue in the F4C format: bias + exact-erf GELU written as hi fp16 + block-scaled e2m1 images of x and of
+    x - hi + their ue8m0 scale bytes; the test reads back hi + q4(x - hi) * scale.  8 and 16 epilogue warps (one word /
+    one half-word of scale bytes per row and tile), more row tiles than CTA pairs, ragged last tile."""
+    monkeypatch.setenv("D3D_GEMM_EW_GELU", str(ew))
+    M, N, K = 74 * 256 + 300, 1024, 512
+    a, w, b = _rand((M, K), 5), _rand((N, K), 6, 0.05), _rand((N,), 7, 0.1)
+    ref = torch.nn.functional.gelu(a.double() @ w.double().T + b.double())
+    out = eng27.op_linear(a.cuda(), w.cuda(), b.cuda(), act=1, gemm_mode=mode).cpu()
+    assert (out.double() - ref).abs().max().item() < 2e-3
+
+
 def test_tc_matches_simt_elementwise(eng27):
     """Same split operands in, so tensor-core and CUDA-core results differ only by accumulation order and the
     dropped lo*lo term (2^-22 relative)."""
@@ -182,6 +229,52 @@ def test_attention_tcgen05_operand(F, B, spatial, gemm_mode):
         assert (hi + lo8 - ref).abs().max().item() < 4e-3
         # lo is the residual of THIS kernel's hi: |lo8 - (x - hi)| <= 12.5 % of one fp16 half-ulp of x
         assert (lo8.abs() <= 2 ** -11 * hi.abs() * 1.13 + 1e-7).all()
+
+
+def _decode_f4c(second, T, C):
+    """[T*C] c4 bytes + [T*C/16] row-major scale bytes -> (P, Q) fp32 [T, C]: nibble value x 2^(scale - 127)."""
+    c4 = second.reshape(-1)[:T * C].view(T, C).cpu().to(torch.int32)
+    sf = second.reshape(-1)[T * C:T * C + T * C // 16].view(T, C // 16).cpu().to(torch.int32)
+    lut = torch.tensor([0, .5, 1, 1.5, 2, 3, 4, 6, -0., -.5, -1, -1.5, -2, -3, -4, -6])
+    nib = torch.stack([c4 & 15, c4 >> 4], dim=-1).reshape(T, 2 * C)           # element 2i = low nibble of byte i
+    val = lut[nib]
+    scale = torch.exp2(sf.float() - 127.0).repeat_interleave(32, dim=1)          # [T, 2C]
+    return (val * scale)[:, :C], (val * scale)[:, C:], sf
+
+
+@pytest.mark.parametrize("F,B,spatial", [(243, 5, False), (81, 6, False), (129, 3, False), (65, 4, False), (256, 2, False),
+                                         (243, 5, True), (27, 40, True), (7, 17, True), (1, 1, True), (27, 3, False)])
+def test_attention_operand_f4c(F, B, spatial):
+    """The attention kernels' output in the FMT_F4C operand format (block-scaled e2m1 images of x and x - hi + ue8m0
+    scale bytes written straight into the scale-factor atoms) against the CUDA-core fp32 kernel: hi, hi + Q, and P to
+    the quantisation step of its block scale; every scale byte must be the smallest power of two that keeps the block
+    maximum <= 6.  F <= 64 (temporal) goes through the mma.sync kernel + split pass, everything else through the
+    tcgen05 kernel's own epilogue (ragged last spatial group, rows beyond F clipped)."""
+    J, C = 17, 512
+    eng = Engine(F, max_clips=B, gemm_mode=_lib.GEMM_TC_F4C)
+    qkv = _rand((B * F * J, 3 * C), 70 + F, 1.5)
+    qkv[:, :2 * C] = qkv[:, :2 * C].half().float()
+    T = B * F * J
+    ref = eng.op_attention(qkv.cuda(), B, spatial, _lib.ATTN_SIMT).cpu()
+    hi, second = eng.debug_attention_operand(qkv.cuda(), B, spatial, _lib.ATTN_DEFAULT)
+    eng.close()
+    hi = hi.float().cpu()
+    P, Q, sf = _decode_f4c(second, T, C)
+    assert torch.isfinite(hi).all()
+    assert (hi - ref).abs().max().item() < 4e-3 + 2 ** -10 * ref.abs().max().item()
+    assert (hi + Q - ref).abs().max().item() < 4e-3
+    # scale bytes: block maximum of the kernel's own x ~ ref (4e-3) must land in (3, 6] (or the block is ~0)
+    blk = ref.view(T, C // 32, 32).abs().amax(-1)
+    s_p = torch.exp2(sf[:, :C // 32].float() - 127.0)
+    ratio = blk / s_p
+    ok = (ratio <= 6.0 + 0.02) & ((ratio > 3.0 - 0.02) | (blk < 1e-2))
+    assert ok.all(), f"{(~ok).sum().item()} scale bytes out of range"
+    # P = q4(x): within one quantisation step of the block's grid (<= 1 x scale at the top of the range)
+    step = s_p.repeat_interleave(32, dim=1)
+    assert ((P - ref).abs() <= 1.0 * step * 1.01 + 4e-3).all()
+    assert (P - ref).abs().mean().item() < 0.08 * ref.abs().mean().item() + 1e-3
+    # Q = q4(x - hi): |x - hi| <= half an fp16 ulp of x; rounding onto the e2m1 grid moves a value up by at most 4/3
+    assert (Q.abs() <= 2 ** -11 * hi.abs() * 1.35 + 1e-7).all()
 
 
 def test_window_gather_scatter_golden(golden):
@@ -265,7 +358,8 @@ def test_time_table_golden(golden):
     assert np.abs(tab - g["time_table"]).max() < 2e-5
 
 
-@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3, _lib.GEMM_TC_F8C, _lib.GEMM_SIMT_F8C])
+@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3, _lib.GEMM_TC_F8C, _lib.GEMM_SIMT_F8C,
+                                       _lib.GEMM_TC_F4C, _lib.GEMM_SIMT_F4C])
 def test_residual_stream_after_blocks_golden(golden, gemm_mode):
     """Residual stream after STE block 0 and TTE block 0 (sub-sampled) against the imported reference."""
     g = golden("denoise_f27_b3")

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 
 MAXABS_BAR, MPJPE_BAR = 1e-2, 1e-4
 MARGIN = 4.0
+MARGIN_F4C = 2.0
 
 
 def _diffusion(F, S, eta=0.0, clip=True, with_time_emb=True, gemm_mode=_lib.GEMM_TC_F8C, attn_mode=_lib.ATTN_DEFAULT,
@@ -30,7 +31,7 @@ def _mpjpe_delta(a, b, gt):
 
 
 @pytest.mark.parametrize("name", ["denoise_f27_b3", "denoise_f27_b2_notime"])
-@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3, _lib.GEMM_TC_F8C])
+@pytest.mark.parametrize("gemm_mode", [_lib.GEMM_SIMT_FP32, _lib.GEMM_TC_SPLIT3, _lib.GEMM_TC_F8C, _lib.GEMM_TC_F4C])
 def test_forward_denoise_golden(golden, name, gemm_mode):
     g = golden(name)
     F, B = int(g["F"]), int(g["B"])
@@ -47,7 +48,7 @@ def test_forward_denoise_golden(golden, name, gemm_mode):
                                   # cfg2 (F = 81), cfg3 / cfg5 (F = 243), cfg4 (F = 27, no time embedding)
                                   "sampler_f81_b1_s9_clip", "sampler_f243_b1_s9_clip", "sampler_f27_b2_s9_notime"])
 @pytest.mark.parametrize("use_graph,gemm_mode", [(False, _lib.GEMM_TC_F8C), (True, _lib.GEMM_TC_F8C),
-                                                 (True, _lib.GEMM_TC_SPLIT3)])
+                                                 (True, _lib.GEMM_TC_SPLIT3), (True, _lib.GEMM_TC_F4C)])
 def test_sampler_golden(golden, name, use_graph, gemm_mode):
     g = golden(name)
     F, B, S, eta = int(g["F"]), int(g["B"]), int(g["S"]), float(g["eta"])
@@ -59,16 +60,20 @@ def test_sampler_golden(golden, name, use_graph, gemm_mode):
     trace = "rev" in g
     if trace:
         pred, rev, x0s = diff.ddim_sample_loop_ouput_reverse_diffusion(x2d.cuda(), [B, F, 17, 3], noise=noise)
-        assert np.abs(rev.cpu().numpy() - g["rev"]).max() < MAXABS_BAR / MARGIN
-        assert np.abs(x0s.cpu().numpy() - g["x0s"]).max() < MAXABS_BAR / MARGIN
+        tm = MARGIN_F4C if gemm_mode == _lib.GEMM_TC_F4C else MARGIN
+        assert np.abs(rev.cpu().numpy() - g["rev"]).max() < MAXABS_BAR / tm
+        assert np.abs(x0s.cpu().numpy() - g["x0s"]).max() < MAXABS_BAR / tm
     else:
         pred = diff.ddim_sample_loop(x2d.cuda(), [B, F, 17, 3], noise=noise)
         pred2 = diff.ddim_sample_loop(x2d.cuda(), [B, F, 17, 3], noise=noise)      # graph replay / determinism
         assert torch.equal(pred, pred2)
     pred = pred.cpu()
     ref = torch.from_numpy(g["pred"])
-    assert (pred - ref).abs().max().item() < MAXABS_BAR / MARGIN
-    assert _mpjpe_delta(pred, ref, gt) < MPJPE_BAR / MARGIN
+    # F4C (block-scaled e2m1 corrections): the CPU emulation (tools/precision_probe.py f4c) predicts up to 2.9e-3 /
+    # 2.1e-5 at F = 243, S = 9 -- inside the bar with a 2x margin instead of 4x
+    margin = MARGIN_F4C if gemm_mode == _lib.GEMM_TC_F4C else MARGIN
+    assert (pred - ref).abs().max().item() < MAXABS_BAR / margin
+    assert _mpjpe_delta(pred, ref, gt) < MPJPE_BAR / margin
 
 
 def test_fp16_fast_mode_is_within_maxabs_bar(golden):
