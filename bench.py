@@ -379,18 +379,23 @@ def run_ours(args):
     achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12
     passes = {"split3": 3, "f8c": 2, "fp16": 1, "f4c": 1.5}[args.gemm]
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma cta_group::2 kind::f16 + kind::f8f6f4, TMA, TMEM)",
+        "bound": "tensor",
+        "kernel": {"f4c": "gemm_tc_kernel (tcgen05.mma cta_group::2 kind::f16 + kind::mxf4.block_scale, tcgen05.cp scale factors, TMA, TMEM)",
+                   "f8c": "gemm_tc_kernel (tcgen05.mma cta_group::2 kind::f16 + kind::f8f6f4, TMA, TMEM)"}.get(
+                       args.gemm, "gemm_tc_kernel (tcgen05.mma cta_group::2 kind::f16, TMA, TMEM)"),
         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
         "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
         "executed_tflops": achieved * passes, "executed_frac": achieved * passes / peaks["tflops_sustained"],
-        "mma_passes": passes, "executed_note": "fp16-equivalent tensor-pipe units per algorithmic FLOP (f8c: 1 fp16 pass + "
-                                                "2 e5m2 passes at twice the rate = 2)", "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+        "mma_passes": passes, "executed_note": "fp16-equivalent tensor-pipe units per algorithmic FLOP (f4c: 1 fp16 pass + 2 "
+                                                "block-scaled e2m1 passes at four times the rate = 1.5; f8c: 1 + 2 e5m2 passes "
+                                                "at twice the rate = 2)", "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
         "share_of_step": gemm_ms / total_prof_ms,
         "per_class_ms": {k: round(v[0], 3) for k, v in prof.items()},
         "algorithmic_flops_per_launch": gemm_flops / max(gemm_n, 1),
-        "note": "frac = ALGORITHMIC FLOPs over the measured sustained bf16 peak; the shipped precision mode executes 2 tensor-pipe "
-                "units per algorithmic FLOP (ceiling 0.5) and moves 4 B per operand element, so the qkv / fc2 launches sit at "
-                "the L2->SM cap (ncu lts2xbar ~8.6 TB/s), proj at HBM (DESIGN.md 4.1)",
+        "note": "frac = ALGORITHMIC FLOPs over the measured sustained bf16 peak; the shipped precision mode (f4c) executes 1.5 "
+                "tensor-pipe units per algorithmic FLOP (ceiling 0.667) and moves 3.06 B per operand element: qkv sits at the "
+                "L2->SM operand-feed cap, fc1 on its GELU + quantising epilogue, proj / fc2 at HBM (fp32 residual read + write) "
+                "(DESIGN.md 4.1)",
     }
     total_flops = tokens * flops_per_token_call(F) * S
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), if it matches the mode
@@ -403,12 +408,13 @@ def run_ours(args):
             roofline["algorithmic_hbm_bytes_per_launch"] = t.get("algorithmic_bytes_per_launch_avg")
     # memory-bound kernel classes against the measured HBM copy bandwidth (SURVEY.md 8d byte counts + operand writes)
     depth2 = 16
-    ln_bytes = tokens * S * (depth2 * 4096 + (depth2 - 1) * 6144)          # norm2: r X, w A; post-norm+norm1: r X, w X, w A
-    attn_bytes = tokens * S * depth2 * (4096 + 2048)                       # r q|k|v_hi|v_lo, w A operand
+    opb = {"f4c": 1568}.get(args.gemm, 2048)                               # bytes of one 512-wide A operand row (hi + second part)
+    ln_bytes = tokens * S * (depth2 * (2048 + opb) + (depth2 - 1) * (4096 + opb))   # norm2: r X, w A; post-norm+norm1: r X, w X, w A
+    attn_bytes = tokens * S * depth2 * (4096 + opb)                        # r q|k|v_hi|v_lo, w A operand
     hbm = {}
     for name, ms, nbytes in (("ln", prof["ln"][0], ln_bytes),
                              ("attention", prof["attn_spatial"][0] + prof["attn_temporal"][0], attn_bytes),
-                             ("lift", prof["lift"][0], tokens * S * (20 + 4096)),
+                             ("lift", prof["lift"][0], tokens * S * (20 + 2048 + opb)),
                              ("head_ddim", prof["head_ddim"][0], tokens * S * (2048 + 24))):
         gbs = nbytes / (ms / 1000.0) / 1e9
         hbm[name] = {"achieved_gbs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peaks["hbm_gbs"], 3)}
@@ -478,9 +484,10 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="override: clips per GPU (cfg5: total windows)")
     ap.add_argument("--sampling-timesteps", type=int, default=0, help="override: DDIM steps (cfg4 sweep 1/9/25/50)")
     ap.add_argument("--batch", type=int, default=256, help="cfg5: clips per sampler batch (x2 with the flip copies)")
-    ap.add_argument("--gemm", default="f8c", choices=["split3", "f8c", "fp16", "f4c"],
-                    help="GEMM arithmetic: f8c (default; fp16 main + e5m2 correction products), split3 (3 fp16 passes), "
-                         "fp16 (1 pass, outside the parity bar)")
+    ap.add_argument("--gemm", default="f4c", choices=["split3", "f8c", "fp16", "f4c"],
+                    help="GEMM arithmetic: f4c (default; fp16 main + block-scaled e2m1 correction products, 1.5 tensor-pipe "
+                         "units), f8c (fp16 main + e5m2 correction products, 2 units), split3 (3 fp16 passes), fp16 (1 pass, "
+                         "outside the parity bar)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -13,6 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("D3D_LIB", _PKG / "libdiff3d_b200.so"))
 
 GEMM_TC_SPLIT3, GEMM_TC_FP16, GEMM_SIMT_FP32, GEMM_TC_F8C, GEMM_SIMT_F8C, GEMM_TC_F4C, GEMM_SIMT_F4C = 0, 1, 2, 3, 4, 5, 6
+GEMM_DEFAULT = GEMM_TC_F4C      # shipped precision mode of the drop-in modules
 ATTN_DEFAULT, ATTN_SIMT, ATTN_MMA_SYNC = 0, 1, 2
 PROF_CLASSES = ("gemm", "attn_spatial", "attn_temporal", "ln", "lift", "head_ddim")
 

@@ -271,6 +271,47 @@ __device__ __forceinline__ float softmax_row_spatial(uint32_t taddr, int row_l, 
   return rcp_approx(sum);
 }
 
+// Packed temporal mode (F <= 64; cfg4's F = 27): G = 4 (F <= 32) or 2 sequences -- the same (clip, head) of G consecutive
+// joints -- share one 128-row tile, row r = f G + jj (the {64 channels, G joints, 128 / G frames} TMA box lands exactly so).
+// Query row r attends the keys of its own joint only: columns c with c % G == r % G and c / G < F.  One pass over the
+// 128 columns for the max, one for exp2 / sum; P is zero elsewhere, so the P.V chain is the same as in the other modes.
+__device__ __forceinline__ float softmax_row_packed(uint32_t taddr, int F, int G, int row_l) {
+  const int jj = row_l & (G - 1);
+  const uint32_t vm = (G == 4 ? 0x11111111u : 0x55555555u) << jj;      // own-joint columns of any aligned 32-column chunk
+  const int nk = F * G;                                                // columns >= nk are frames >= F (zero-filled rows)
+  uint32_t sv[4][32];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32(taddr + c * 32, sv[c]);
+  ptx::tmem_ld_wait();
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (((vm >> e) & 1u) && c * 32 + e < nk) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
+  const ptx::f32x2 sc2 = ptx::splat2(kScaleLog2e), nm2 = ptx::splat2(-mx * kScaleLog2e);
+  ptx::f32x2 ls = ptx::splat2(0.f);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float t0, t1;
+      ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(sv[c][2 * e]), __uint_as_float(sv[c][2 * e + 1])), sc2, nm2), t0, t1);
+      const int col = c * 32 + 2 * e;
+      const float e0 = (((vm >> (2 * e)) & 1u) && col < nk) ? ex2_approx(t0) : 0.f;
+      const float e1 = (((vm >> (2 * e + 1)) & 1u) && col + 1 < nk) ? ex2_approx(t1) : 0.f;
+      ls = ptx::add2(ls, ptx::pack2(e0, e1));
+      pk[e] = pack_f16x2(e0, e1);
+    }
+    ptx::tmem_st_32x16(taddr + c * 16, pk);
+  }
+  ptx::tmem_st_wait();
+  float s0, s1;
+  ptx::unpack2(ls, s0, s1);
+  return rcp_approx(s0 + s1);
+}
+
 // Work items of a CTA, in order: w = 0, 1, 2, ... ; unit n = w / n_mt (the CTA's n-th unit), 128-query tile
 // m = w % n_mt; slot = w % NSLOT (i-th item of that slot, i = w / NSLOT); shared-memory stage = n % n_stage (k-th use,
 // k = n / n_stage).  n_stage = 2 when a unit has two tiles (96 KB per unit), 4 when it has one (48 KB): units are
@@ -282,12 +323,14 @@ __device__ __forceinline__ float softmax_row_spatial(uint32_t taddr, int row_l, 
 // only on its index inside the clip: results are bit-identical under any batch split.  The maps are 2-D token-major
 // views encoded with rank 4 (coordinates (channel, token, 0, 0)); n_mt == 1, NKp == 128; the store maps have 119-row
 // boxes, the *_tail maps (F % 7) * 17-row boxes.  J carries the groups per clip.
-template <int FMT, int NSLOT, int NCH, bool SPATIAL>
+// PACKED: G = `pk_g` joints per tile (softmax_row_packed); J then counts the joint GROUPS per clip and `j_tok` the joints.
+template <int FMT, int NSLOT, int NCH, bool SPATIAL, bool PACKED = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
                         const __grid_constant__ CUtensorMap tm_second, const __grid_constant__ CUtensorMap tm_hi_tail,
                         const __grid_constant__ CUtensorMap tm_second_tail, uint8_t* __restrict__ sf_out, int F, int J,
-                        int n_units, int n_mt, int NKp, int n_stage) {
+                        int n_units, int n_mt, int NKp, int n_stage, int pk_g = 1, int j_tok = 0) {
+  static_assert(!PACKED || (!SPATIAL && NCH == 0), "the packed mode is a temporal mode with a runtime chunk count");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = 3 * n_mt * kTile;          // Q tiles | K tiles | V tiles of one unit
@@ -332,6 +375,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         const int seq = unit >> 3, h = unit & 7;
         int b = seq / J, j = seq - b * J;
         if (SPATIAL) { j = (b * F + 7 * j) * 17; b = 0; }        // token coordinate of the group's first row
+        if (PACKED) j *= pk_g;                                   // first joint of the group
         const int stage = n % n_stage, k = n / n_stage;
         uint8_t* Qs = smem + stage * stage_bytes;
         uint8_t* Ks = Qs + n_mt * kTile;
@@ -395,7 +439,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const uint32_t taddr = tmem_base + slot * kSlotCols + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int n_chunks = (NKp + 31) >> 5;
     if (!SPATIAL && NCH > 0 && (n_chunks != NCH || F <= 32 * (NCH - 1))) __trap();    // launcher / instantiation mismatch
-    if (SPATIAL && (n_mt != 1 || NKp != 128)) __trap();
+    if ((SPATIAL || PACKED) && (n_mt != 1 || NKp != 128)) __trap();
     const int sw = (row_l & 7) << 4;                                      // swizzle XOR of this row (bytes)
     const bool issuer = row_l == 0;                                       // issues the slot's TMA stores
     uint8_t* Stg = StgAll + slot * kTile;
@@ -407,6 +451,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       int b = seq / J, j = seq - b * J;
       const bool tail = SPATIAL && j == J - 1 && F % 7 != 0;      // last group of a clip: fewer than 7 frames to store
       if (SPATIAL) { j = (b * F + 7 * j) * 17; b = 0; }
+      if (PACKED) j *= pk_g;
       uint8_t* Qs = smem + stage * stage_bytes;
       const uint8_t* Vs = Qs + 2 * n_mt * kTile;
       const int r = m * 128 + row_l;
@@ -416,7 +461,9 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         ptx::mbar_arrive_expect_tx(&bars->vlo_full[slot], kTile);
         ptx::tma_load_4d(Qs + m * kTile, &tm_qkv, &bars->vlo_full[slot], 3 * kC + h * kHd, j, m * 128, b);
       }
-      const float inv = SPATIAL ? softmax_row_spatial(taddr, row_l, warp & 3) : softmax_row<NCH>(taddr, F, n_chunks);
+      const float inv = SPATIAL ? softmax_row_spatial(taddr, row_l, warp & 3)
+                      : PACKED  ? softmax_row_packed(taddr, F, pk_g, row_l)
+                                : softmax_row<NCH>(taddr, F, n_chunks);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->p_full[slot]);
 
@@ -507,9 +554,11 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
         // the row's four scale bytes: k-blocks (2h, 2h+1) of part P and (16 + 2h, 16 + 2h + 1) of part Q are adjacent
         // bytes of a scale-factor atom.  Rows the TMA stores clip (>= F, or past the unit) must not be written here.
-        const int64_t tok = SPATIAL ? static_cast<int64_t>(j) + row_l
-                                    : (static_cast<int64_t>(b) * F + r) * J + j;
-        const bool live = SPATIAL ? row_l < (tail ? (F % 7) * 17 : kSpatialRows) : r < F;
+        const int pf = PACKED ? row_l / pk_g : 0, pj = PACKED ? j + (row_l & (pk_g - 1)) : 0;   // packed: frame, joint of the row
+        const int64_t tok = SPATIAL  ? static_cast<int64_t>(j) + row_l
+                            : PACKED ? (static_cast<int64_t>(b) * F + pf) * j_tok + pj
+                                     : (static_cast<int64_t>(b) * F + r) * J + j;
+        const bool live = SPATIAL ? row_l < (tail ? (F % 7) * 17 : kSpatialRows) : PACKED ? (pf < F && pj < j_tok) : r < F;
         if (live) {
           *reinterpret_cast<uint16_t*>(sf_out + op_sf_offset(tok, 2 * h, kC / 64)) = static_cast<uint16_t>(bp0 | (bp1 << 8));
           *reinterpret_cast<uint16_t*>(sf_out + op_sf_offset(tok, 16 + 2 * h, kC / 64)) = static_cast<uint16_t>(bq0 | (bq1 << 8));
@@ -600,13 +649,15 @@ int encode_rank4(CUtensorMap* out, void* base, CUtensorMapDataType dt, const cuu
 }
 
 // [B, F, J, row] token-major array viewed as a 4-D tensor (channel, j, f, b); box = {64 channels, 1, 128 frames, 1}
+// box_j > 1 (packed mode, F <= 64): box = {box0 channels, box_j joints, 128 / box_j frames, 1}, rows land as f * box_j + jj
 int encode_tokens_4d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int elem_bytes, int64_t row_elems, int J,
-                     int F, int64_t B, CUtensorMapSwizzle swz, int box0 = 64) {
+                     int F, int64_t B, CUtensorMapSwizzle swz, int box0 = 64, int box_j = 1) {
   const cuuint64_t row_bytes = static_cast<cuuint64_t>(row_elems) * elem_bytes;
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(J), static_cast<cuuint64_t>(F),
                               static_cast<cuuint64_t>(B)};
   const cuuint64_t strides[3] = {row_bytes, row_bytes * J, row_bytes * J * F};
-  const cuuint32_t box[4] = {static_cast<cuuint32_t>(box0), 1, 128, 1};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box_j),
+                             static_cast<cuuint32_t>(128 / box_j), 1};
   return encode_rank4(out, base, dt, dims, strides, box, swz);
 }
 
@@ -629,22 +680,25 @@ int tc_smem_bytes(int n_mt) {
 
 }  // namespace
 
+inline int packed_group(int F) { return F <= 32 ? 4 : (F <= 64 ? 2 : 1); }     // joints per 128-row tile
+
 int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int F, int J,
                       int64_t max_clips) {
-  if (encode_tokens_4d(&maps->qkv, const_cast<__half*>(qkv), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kQkvRow, J, F,
-                       max_clips, CU_TENSOR_MAP_SWIZZLE_128B))
+  const int G = packed_group(F);
+  if (encode_tokens_4d(&maps->qkv, const_cast<__half*>(qkv), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kQkvRow, J, F, max_clips,
+                       CU_TENSOR_MAP_SWIZZLE_128B, 64, G))
     return -1;
   if (encode_tokens_4d(&maps->o_hi, o_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, J, F, max_clips,
-                       CU_TENSOR_MAP_SWIZZLE_128B))
+                       CU_TENSOR_MAP_SWIZZLE_128B, 64, G))
     return -1;
   if (fmt == FMT_F8C)
     return encode_tokens_4d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 2 * kC, J, F, max_clips,
-                            CU_TENSOR_MAP_SWIZZLE_NONE);
+                            CU_TENSOR_MAP_SWIZZLE_NONE, 64, G);
   if (fmt == FMT_F4C)       // c4 rows of K = 512 bytes; {32 B x 128 rows} boxes (one head of one part)
     return encode_tokens_4d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kC, J, F, max_clips,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, 32);
+                            CU_TENSOR_MAP_SWIZZLE_NONE, 32, G);
   return encode_tokens_4d(&maps->o_second, o_second, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, kC, J, F, max_clips,
-                          CU_TENSOR_MAP_SWIZZLE_128B);
+                          CU_TENSOR_MAP_SWIZZLE_128B, 64, G);
 }
 
 int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt,
@@ -688,13 +742,37 @@ cudaError_t configure_attention_tc() {
   D3D_CFG_TC(FMT_SPLIT16, 0, true) D3D_CFG_TC(FMT_F8C, 0, true)
   D3D_CFG_TC(FMT_F4C, 0, false) D3D_CFG_TC(FMT_F4C, 3, false) D3D_CFG_TC(FMT_F4C, 8, false) D3D_CFG_TC(FMT_F4C, 0, true)
 #undef D3D_CFG_TC
+#define D3D_CFG_PK(FMT_)                                                                                                     \
+  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_, 2, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                tc_smem_bytes<2>(1))) != cudaSuccess)                                                        \
+    return e;
+  D3D_CFG_PK(FMT_SPLIT16) D3D_CFG_PK(FMT_F8C) D3D_CFG_PK(FMT_F4C)
+#undef D3D_CFG_PK
   return cudaSuccess;
 }
 
 cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, uint8_t* o_sf, int fmt, int B, int F, int J,
                                     int num_sms, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  if (F <= 64 || F > 256) return cudaErrorInvalidValue;
+  if (F < 1 || F > 256) return cudaErrorInvalidValue;
+  if (fmt == FMT_F4C && !o_sf) return cudaErrorInvalidValue;
+  if (F <= 64) {
+    // packed mode: G joints of one (clip, head) per 128-row tile; the maps were built with {.., G, 128 / G, 1} boxes
+    const int G = packed_group(F), JG = (J + G - 1) / G;
+    const int64_t units64 = static_cast<int64_t>(B) * JG * kHeads;
+    if (units64 > 0x7fffffff) return cudaErrorInvalidValue;
+    const int n_units = static_cast<int>(units64);
+    const int grid = n_units < num_sms ? n_units : num_sms;
+    const int smem = tc_smem_bytes<2>(1);
+#define D3D_LAUNCH_PK(FMT_)                                                                   \
+  attn_temporal_tc_kernel<FMT_, 2, 0, false, true><<<grid, kTcThreads, smem, st>>>(           \
+      maps.qkv, maps.o_hi, maps.o_second, maps.o_hi, maps.o_second, o_sf, F, JG, n_units, 1, 128, tc_stages(1), G, J)
+    if (fmt == FMT_F4C) D3D_LAUNCH_PK(FMT_F4C);
+    else if (fmt == FMT_F8C) D3D_LAUNCH_PK(FMT_F8C);
+    else D3D_LAUNCH_PK(FMT_SPLIT16);
+#undef D3D_LAUNCH_PK
+    return cudaGetLastError();
+  }
   const int n_mt = (F + 127) / 128;
   const int NKp = (F + 15) / 16 * 16;
   const int n_units = B * J * kHeads;

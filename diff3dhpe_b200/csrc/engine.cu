@@ -592,7 +592,7 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
         return fail(h, -20, "cuTensorMapEncodeTiled failed for the spatial-attention maps");
       h->have_attn_sp = true;
     }
-    if (h->F > 64) {
+    {   // every F <= 256 runs on the tcgen05 kernel (F <= 64: 2 or 4 joints packed per 128-row tile)
       if (make_attn_tc_maps(&h->attn_tc, h->QKV, h->ATT.hi, h->ATT.lo, h->fmt, h->F, h->J, cfg->max_clips))
         return fail(h, -20, "cuTensorMapEncodeTiled failed for the temporal-attention maps");
       h->have_attn_tc = true;

@@ -85,6 +85,10 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+#ifndef D3D_GEMM_RES_DEPTH
+#define D3D_GEMM_RES_DEPTH 2     // residual chunks prefetched per epilogue warp (A/B builds: 1 = the round-1 epilogue)
+#endif
+
 // D3D_EPI_PACKED = 0 compiles the scalar epilogue math (the A/B baseline of profiles/r01z_bench_scalar_epilogue.json)
 #ifndef D3D_EPI_PACKED
 #define D3D_EPI_PACKED 1
@@ -460,17 +464,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const int row_w = m0 + q * 32;                    // first row of this warp
       const int colbase = n0 + half * kColsW;
       const bool has_res = (EPI == EPI_F32 || EPI == EPI_F32_LN) && p.residual != nullptr;
-      float4 resv[8];
+      // Residual prefetch, kResDepth chunks deep (registers).  The fp32 + residual epilogue moves 256 KB per CTA and tile
+      // (read + write) and, with the F4C mainloop at ~5 us per tile, sets the tile time of proj / fc2: ncu had them at
+      // 55-58 % of DRAM with ONE 4 KB chunk per warp in flight (32 KB per SM, below bandwidth x latency ~ 44 B/ns x 0.8 us);
+      // two chunks per warp double the bytes in flight (profiles/r02d_full_gemm.md -> r02e).
+      constexpr int kResDepth = (EPI == EPI_F32 && EW == 8) ? D3D_GEMM_RES_DEPTH : 1;      // EW = 16: 104 registers, no room
+      float4 resv[kResDepth][8];
       auto load_res = [&](int ci) {                     // residual chunk ci, coalesced (row 4j + rsub, granule gsub)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = row_w + 4 * j + rsub;
           const float* src = p.residual + static_cast<size_t>(rr) * p.N + colbase + ci * 32 + gsub * 4;
-          resv[j] = rr >= p.M ? make_float4(0.f, 0.f, 0.f, 0.f)
-                              : (p.stream_out ? ptx::ld_global_cs(src) : *reinterpret_cast<const float4*>(src));
+          resv[ci % kResDepth][j] = rr >= p.M ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                              : (p.stream_out ? ptx::ld_global_cs(src) : *reinterpret_cast<const float4*>(src));
         }
       };
-      if (has_res) load_res(0);              // in flight while the accumulator is still being computed
+      if (has_res) {                         // in flight while the accumulator is still being computed
+#pragma unroll
+        for (int c = 0; c < kResDepth; ++c) load_res(c);
+      }
       uint32_t sfp_w = 0, sfq_w = 0;         // F4C GELU output: this row's scale bytes of the tile's k-blocks (P / Q part)
       ptx::mbar_wait(&bars->tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
@@ -481,9 +493,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         ptx::tmem_ld_32x32(tmem_base + acc * BN + col0 + (static_cast<uint32_t>(q * 32) << 16), r);
         if (has_res) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) *stg_at(stg, 4 * j + rsub, gsub) = *reinterpret_cast<uint4*>(&resv[j]);
+          for (int j = 0; j < 8; ++j) *stg_at(stg, 4 * j + rsub, gsub) = *reinterpret_cast<uint4*>(&resv[ci % kResDepth][j]);
           __syncwarp();
-          if (ci + 1 < kChunks) load_res(ci + 1);
+          if (ci + kResDepth < kChunks) load_res(ci + kResDepth);
         }
         const int gcol = n0 + col0;
         float4 bias4[8];                                 // issued before the TMEM wait so their latency is hidden

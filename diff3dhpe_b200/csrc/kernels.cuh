@@ -142,7 +142,7 @@ cudaError_t launch_attn_spatial(const __half* qkv, __half* o_hi, __half* o_lo, f
                                 int J, cudaStream_t st);
 cudaError_t launch_attn_temporal_mma(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                      int J, cudaStream_t st);
-// tcgen05 / TMEM / TMA temporal kernel (attention_tc.cu), 64 < F <= 256.  Its tensor maps are bound to one packed
+// tcgen05 / TMEM / TMA temporal kernel (attention_tc.cu), 1 <= F <= 256 (F <= 64: 2 or 4 joints packed per tile).  Its tensor maps are bound to one packed
 // qkv array and one output operand (hi + second array in format fmt) of up to max_clips clips.
 struct AttnTcMaps {
   CUtensorMap qkv, o_hi, o_second;

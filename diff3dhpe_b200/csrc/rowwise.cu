@@ -41,6 +41,19 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int lane, const
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(p + 128 * i + 4 * lane) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
+// a += b  /  a += s * b  over the lane's 16 columns, as 8 packed pairs
+__device__ __forceinline__ void add16(float (&a)[16], const float (&b)[16]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    ptx::unpack2(ptx::add2(ptx::pack2(a[2 * i], a[2 * i + 1]), ptx::pack2(b[2 * i], b[2 * i + 1])), a[2 * i], a[2 * i + 1]);
+}
+__device__ __forceinline__ void fma16(float (&a)[16], float s, const float (&b)[16]) {
+  const ptx::f32x2 s2 = ptx::splat2(s);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    ptx::unpack2(ptx::fma2(s2, ptx::pack2(b[2 * i], b[2 * i + 1]), ptx::pack2(a[2 * i], a[2 * i + 1])), a[2 * i], a[2 * i + 1]);
+}
+
 // GEMM A operand of token row `row` (K = 512) in the handle's operand format (operand.cuh); `second` / `sf` are the BASE
 // pointers of the operand's second array and (FMT_F4C) its scale-factor array.
 template <int FMT>
@@ -151,19 +164,18 @@ lift_ln_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, cons
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     load_row_ldg(wf_t + k * kC, lane, w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fmaf(in[k], w[i], v[i]);
+    fma16(v, in[k], w);
   }
   load_row_ldg(bf, lane, w);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += w[i];
-  load_row_ldg(spos + static_cast<int64_t>(t % J) * kC, lane, w);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += w[i];
+  add16(v, w);
+  // token indices fit 32 bits (launchers check T < 2^31): 32-bit divisions instead of the 64-bit software routine,
+  // which cost these issue-bound kernels ~100 instructions per row
+  const uint32_t t32 = static_cast<uint32_t>(t);
+  load_row_ldg(spos + static_cast<size_t>(t32 % static_cast<uint32_t>(J)) * kC, lane, w);
+  add16(v, w);
   if (tvec) {
-    load_row_ldg(tvec + (t / tokens_per_clip) * tvec_stride, lane, w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += w[i];
+    load_row_ldg(tvec + static_cast<int64_t>(t32 / static_cast<uint32_t>(tokens_per_clip)) * tvec_stride, lane, w);
+    add16(v, w);
   }
   store_row(X + t * kC, lane, v);
   float a[16];
@@ -183,14 +195,12 @@ postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __rest
   load_row(X + t * kC, lane, x);
   layernorm_row(x, post.gamma, post.beta, 1e-6f, lane, z);
   if (tpos) {
-    load_row_ldg(tpos + ((t / J) % F) * kC, lane, w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) z[i] += w[i];
+    load_row_ldg(tpos + static_cast<size_t>((static_cast<uint32_t>(t) / static_cast<uint32_t>(J)) % static_cast<uint32_t>(F)) * kC, lane, w);
+    add16(z, w);
   }
   if (tvec) {
-    load_row_ldg(tvec + (t / (static_cast<int64_t>(J) * F)) * tvec_stride, lane, w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) z[i] += w[i];
+    load_row_ldg(tvec + static_cast<int64_t>(static_cast<uint32_t>(t) / static_cast<uint32_t>(J * F)) * tvec_stride, lane, w);
+    add16(z, w);
   }
   store_row(X + t * kC, lane, z);
   layernorm_row(z, ln1.gamma, ln1.beta, 1e-6f, lane, x);
@@ -482,6 +492,7 @@ cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, co
                            __half* a_hi, __half* a_lo, uint8_t* a_sf, int fmt, int64_t T, int J, int tokens_per_clip,
                            cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
+  if (T > 0x7fffffffLL) return cudaErrorInvalidValue;
   auto kern = fmt == FMT_F4C ? lift_ln_kernel<FMT_F4C> : fmt == FMT_F8C ? lift_ln_kernel<FMT_F8C> : lift_ln_kernel<FMT_SPLIT16>;
   kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(x2d, y, x5, wf_t, bf, spos, tvec, tvec_stride, ln1, X, a_hi, a_lo, a_sf, T,
                                                  J, tokens_per_clip);
@@ -491,6 +502,7 @@ cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos, c
                                    int64_t tvec_stride, LnParams ln1, __half* a_hi, __half* a_lo, uint8_t* a_sf, int fmt,
                                    int64_t T, int J, int F, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
+  if (T > 0x7fffffffLL) return cudaErrorInvalidValue;
   auto kern = fmt == FMT_F4C ? postnorm_add_ln_kernel<FMT_F4C>
             : fmt == FMT_F8C ? postnorm_add_ln_kernel<FMT_F8C> : postnorm_add_ln_kernel<FMT_SPLIT16>;
   kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, tpos, tvec, tvec_stride, ln1, a_hi, a_lo, a_sf, T, J, F);

@@ -30,7 +30,7 @@ class Engine:
 
     def __init__(self, num_frame: int, num_joints: int = 17, embed_dim: int = 512, depth: int = 8, num_heads: int = 8,
                  mlp_hidden: int = 1024, with_time_emb: bool = True, max_clips: int = 1, device=None,
-                 gemm_mode: int = _lib.GEMM_TC_F8C, attn_mode: int = _lib.ATTN_DEFAULT, use_graph: bool = True):
+                 gemm_mode: int = _lib.GEMM_DEFAULT, attn_mode: int = _lib.ATTN_DEFAULT, use_graph: bool = True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("diff3dhpe_b200 needs a CUDA device (sm_100a); there is no CPU fallback")

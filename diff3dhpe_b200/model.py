@@ -90,7 +90,7 @@ class ConditionalDiffusionMixSTES2SGRANDLinLift(nn.Module):
         self._engine_key = None
         self._weights_key = None
         self._weights_epoch = 0
-        self.gemm_mode = _lib.GEMM_TC_F8C
+        self.gemm_mode = _lib.GEMM_DEFAULT
         self.attn_mode = _lib.ATTN_DEFAULT
         self.use_graph = True
         self.max_clips_hint = 1

@@ -2,9 +2,10 @@
 the golden vectors of the imported reference and the CPU oracle run live on the same seeded inputs.
 
 Tolerances (north star): per-joint max-abs error <= 1e-2 (pose scale 1) and MPJPE delta <= 0.1 mm = 1e-4.  The
-shipped default (GEMM_TC_F8C: fp16 main product + e5m2 correction products in the linears; single-pass fp16 attention
-with an exact "- V" term) and the 3-pass split-fp16 mode are asserted against a 4x tighter bound; the CPU precision
-emulation (tools/precision_probe.py) predicts max-abs 6e-4 / 8e-4 / 1.5e-3 at F = 27 / 81 / 243 with 9 steps."""
+shipped default is GEMM_TC_F4C: fp16 main product + block-scaled e2m1 (mxfp4) correction products in the linears,
+single-pass fp16 attention with an exact "- V" term; it is asserted against a 3x tighter bound (measured worst case over
+the goldens 2.8e-3 / 1.6e-5, profiles/r02d_parity_report.log).  GEMM_TC_F8C (e5m2 corrections; worst case 9.7e-4 / 7.7e-6)
+and the 3-pass split-fp16 mode are asserted against a 4x tighter bound."""
 import numpy as np
 import pytest
 import torch
@@ -16,10 +17,10 @@ pytestmark = pytest.mark.gpu
 
 MAXABS_BAR, MPJPE_BAR = 1e-2, 1e-4
 MARGIN = 4.0
-MARGIN_F4C = 2.0
+MARGIN_F4C = 3.0     # measured worst case over the goldens: 2.8e-3 / 1.6e-5 (tools/parity_report.py, profiles/r02d_parity_report.log)
 
 
-def _diffusion(F, S, eta=0.0, clip=True, with_time_emb=True, gemm_mode=_lib.GEMM_TC_F8C, attn_mode=_lib.ATTN_DEFAULT,
+def _diffusion(F, S, eta=0.0, clip=True, with_time_emb=True, gemm_mode=_lib.GEMM_DEFAULT, attn_mode=_lib.ATTN_DEFAULT,
                use_graph=True, max_clips=1):
     m = synthetic.make_model(F, with_time_emb=with_time_emb).cuda()
     m.gemm_mode, m.attn_mode, m.use_graph, m.max_clips_hint = gemm_mode, attn_mode, use_graph, max_clips
@@ -70,7 +71,7 @@ def test_sampler_golden(golden, name, use_graph, gemm_mode):
     pred = pred.cpu()
     ref = torch.from_numpy(g["pred"])
     # F4C (block-scaled e2m1 corrections): the CPU emulation (tools/precision_probe.py f4c) predicts up to 2.9e-3 /
-    # 2.1e-5 at F = 243, S = 9 -- inside the bar with a 2x margin instead of 4x
+    # 2.1e-5 at F = 243, S = 9; measured 1.7e-3 / 9e-6 there and 2.8e-3 / 1.5e-5 at F = 27 -- a 3x margin instead of 4x
     margin = MARGIN_F4C if gemm_mode == _lib.GEMM_TC_F4C else MARGIN
     assert (pred - ref).abs().max().item() < MAXABS_BAR / margin
     assert _mpjpe_delta(pred, ref, gt) < MPJPE_BAR / margin
@@ -98,8 +99,8 @@ def test_forward_api_flip_tta_against_oracle():
     sd = {k: v.detach().cpu() for k, v in diff.model.state_dict().items()}
     with torch.no_grad():
         ref = oracle.sample_tta(sd, x2d, n1, n2, sampling_timesteps=S)
-    assert (merged - ref).abs().max().item() < MAXABS_BAR / MARGIN
-    assert _mpjpe_delta(merged, ref, gt) < MPJPE_BAR / MARGIN
+    assert (merged - ref).abs().max().item() < MAXABS_BAR / MARGIN_F4C      # default mode = F4C
+    assert _mpjpe_delta(merged, ref, gt) < MPJPE_BAR / MARGIN_F4C
     # forward(): same signature / return convention as DIFF:421-449, and it consumes S normal draws in order
     torch.manual_seed(77)
     loss, pred = diff(clean_3d_pose=gt.cuda(), noisy_2d_pose=x2d.cuda(), output_loss=False)
@@ -149,8 +150,8 @@ def test_forward_output_loss_and_repeat_n_golden(golden, monkeypatch, name):
     loss, pred = loss.cpu(), pred.cpu()
     ref_loss, ref_pred = torch.from_numpy(g["loss"]), torch.from_numpy(g["pred"])
     assert pred.shape == ref_pred.shape == (B, F, 17, 3)
-    assert (pred - ref_pred).abs().max().item() < MAXABS_BAR / MARGIN
-    assert _mpjpe_delta(pred, ref_pred, gt) < MPJPE_BAR / MARGIN
+    assert (pred - ref_pred).abs().max().item() < MAXABS_BAR / MARGIN_F4C   # default mode = F4C
+    assert _mpjpe_delta(pred, ref_pred, gt) < MPJPE_BAR / MARGIN_F4C
     # loss: <= 1e-3 relative on the mean (the quantity evaluate() logs) and element-wise against the loss scale
     assert abs(loss.mean().item() - ref_loss.mean().item()) <= 1e-3 * ref_loss.mean().item()
     assert (loss - ref_loss).abs().max().item() <= 2e-3 * ref_loss.abs().max().item()
