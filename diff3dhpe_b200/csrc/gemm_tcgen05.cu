@@ -40,8 +40,12 @@ namespace {
 
 constexpr int BM = 128;                      // rows per CTA
 constexpr int BK = 64;                       // 64 fp16 = 128 B = one swizzle row
-constexpr int kProducerRegs = 40;          // setmaxnreg targets of the EW = 16 kernels (640 threads launch with 96 each)
-constexpr int kEpilogueRegs = 104;
+#ifndef D3D_GEMM_PRODUCER_REGS
+#define D3D_GEMM_PRODUCER_REGS 40
+#define D3D_GEMM_EPILOGUE_REGS 104
+#endif
+constexpr int kProducerRegs = D3D_GEMM_PRODUCER_REGS;   // setmaxnreg targets of the EW = 16 kernels (640 threads launch with 96 each)
+constexpr int kEpilogueRegs = D3D_GEMM_EPILOGUE_REGS;
 // setmaxnreg.inc draws from the registers the SAME CTA released with setmaxnreg.dec (not from the SM's unallocated
 // remainder): the four epilogue warpgroups may not ask for more than the producer warpgroup gave back, or they block
 // forever (first attempt: 40 / 112 -> deadlock on the GPU)
