@@ -41,8 +41,8 @@ namespace {
 constexpr int BM = 128;                      // rows per CTA
 constexpr int BK = 64;                       // 64 fp16 = 128 B = one swizzle row
 #ifndef D3D_GEMM_PRODUCER_REGS
-#define D3D_GEMM_PRODUCER_REGS 40
-#define D3D_GEMM_EPILOGUE_REGS 104
+#define D3D_GEMM_PRODUCER_REGS 32          // 32 / 112 (round 2): no spills left in the 16-warp fp32 / GELU epilogues
+#define D3D_GEMM_EPILOGUE_REGS 112
 #endif
 constexpr int kProducerRegs = D3D_GEMM_PRODUCER_REGS;   // setmaxnreg targets of the EW = 16 kernels (640 threads launch with 96 each)
 constexpr int kEpilogueRegs = D3D_GEMM_EPILOGUE_REGS;
@@ -69,10 +69,13 @@ struct Cfg {
   static constexpr int kSfBytes = PASSES == 4 ? 3072 : 0;
   static constexpr int kStageBytes = (PASSES == 3 ? 2 : 1) * (kTileBytesA + kTileBytesB) + kSfBytes;
   static constexpr int kStagingBytes = EW * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
-  static constexpr int kRing = ((PASSES == 2 || PASSES == 4) ? kSmemBudget : 200 * 1024) + 8 * 4096 - kStagingBytes;
+  static constexpr int kRing = ((PASSES == 2 || PASSES == 4) ? kSmemBudget : 200 * 1024) + 8 * 4096 - kStagingBytes;   // + 8 KB vectors (F4C)
   static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;   // 256 or 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // FMT_F4C operand-producing epilogues (GELU / deferred LayerNorm) read bias (and the folded weight's column sums) from
+  // shared memory, just in time, instead of holding 32 prefetched registers per lane across the accumulator wait
+  static constexpr int kVecBytes = PASSES == 4 ? 2 * 1024 * 4 : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes;
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256 x 256 tiles");
   static_assert(EW == 8 || (EW == 16 && BN == 256), "16 epilogue warps split a 256-column tile four ways");
@@ -117,13 +120,39 @@ __device__ __forceinline__ float gelu_erf(float v) {
 }
 #endif
 
-// The same function on a PACKED pair (FFMA2 / FMUL2: two IEEE-rn operations per fma-pipe slot).  The scalar form costs
+// The same function on a PACKED pair (FFMA2 / FMUL2: two IEEE-rn operations per fma-pipe slot; D3D_GELU_POLY5 = 0 builds
+// this form, the round-1 epilogue).  The scalar form costs
 // 16 fma-pipe instructions per activation incl. bias and operand split; a 3-register FFMA issues every other cycle per
 // scheduler, so 32 768 activations per CTA tile kept the fma pipe busy for ~8 200 cycles -- longer than the tile's
 // mainloop.  Constants are folded so that no scaling multiply is left: with a = |v|,
 //   t = 1 / (1 + (p / sqrt 2) a),  e = exp2(-(log2 e / 2) a^2),  q(t) = -(a1 + t (a2 + ...)) / 2   (exact scaling),
 //   gelu(v) = max(v, 0) + a (q(t) t e).
-#if D3D_EPI_PACKED
+// D3D_GELU_POLY5 = 1 (default): ONE MUFU per activation.  With a = |v| and Q(a) = erfc(a / sqrt 2) / 2 (the normal tail),
+//   gelu(v) = v / 2 + a (1/2 - Q(a)),   Q(a) = exp2(p(a)),  p = degree-5 minimax fit of log2 Q weighted by the sensitivity
+//   a Q(a) of the result (tools/fit_gelu_tail.py): |error| <= 4.8e-7 absolute for every v (the A-S form: <= |v| 1e-7;
+//   both far below the 6e-5 relative precision of the operand format the result is written in).  p's leading coefficient
+//   is negative, so Q underflows to 0 for large a and gelu(v) -> max(v, 0) without a clamp.  5 + 3 packed fma-pipe
+//   instructions and 1 MUFU per activation instead of 10 + 2 (+ the scalar max): the fc1 epilogue is issue-bound.
+#ifndef D3D_GELU_POLY5
+#define D3D_GELU_POLY5 1
+#endif
+#if D3D_EPI_PACKED && D3D_GELU_POLY5
+__device__ __forceinline__ ptx::f32x2 gelu_erf2(ptx::f32x2 v) {
+  float v0, v1, g0, g1, e0, e1;
+  ptx::unpack2(v, v0, v1);
+  const ptx::f32x2 a = ptx::pack2(fabsf(v0), fabsf(v1));
+  ptx::f32x2 q = ptx::fma2(a, ptx::splat2(-4.732940288e-04f), ptx::splat2(7.084461395e-03f));
+  q = ptx::fma2(q, a, ptx::splat2(-5.182716995e-02f));
+  q = ptx::fma2(q, a, ptx::splat2(-4.599926472e-01f));
+  q = ptx::fma2(q, a, ptx::splat2(-1.150787711e+00f));
+  q = ptx::fma2(q, a, ptx::splat2(-1.000037670e+00f));
+  ptx::unpack2(q, g0, g1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  const ptx::f32x2 h = ptx::sub2(ptx::splat2(0.5f), ptx::pack2(e0, e1));
+  return ptx::fma2(a, h, ptx::mul2(v, ptx::splat2(0.5f)));
+}
+#elif D3D_EPI_PACKED
 __device__ __forceinline__ ptx::f32x2 gelu_erf2(ptx::f32x2 v) {
   float v0, v1;
   ptx::unpack2(v, v0, v1);
@@ -147,12 +176,121 @@ __device__ __forceinline__ ptx::f32x2 gelu_erf2(ptx::f32x2 v) {
 
 // Epilogue transpose buffer: 32 rows x 128 B; the 16-byte granule g of row r lives at r*128 + ((g ^ (r&7)) << 4)
 // (the 128-byte swizzle), so "lane = row" accesses and "8 lanes = one row" accesses are both conflict-free.
-__device__ __forceinline__ uint4* stg_at(uint8_t* stg, int r, int g) {
-  return reinterpret_cast<uint4*>(stg + r * 128 + ((g ^ (r & 7)) << 4));
+// The accessors take the buffer's shared-space (32-bit) address: one ld / st.shared with 32-bit address arithmetic per
+// access (through a generic pointer every access cost a 64-bit add and a generic-space instruction).
+__device__ __forceinline__ uint32_t stg_at(uint32_t stg, int r, int g) { return stg + r * 128 + ((g ^ (r & 7)) << 4); }
+__device__ __forceinline__ void stg_st(uint32_t stg, int r, int g, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_at(stg, r, g)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 stg_ld(uint32_t stg, int r, int g) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg_at(stg, r, g))
+               : "memory");
+  return v;
+}
+// read-only per-column vectors in shared memory (written once before the role split): schedulable like any load
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+
+// Coalesced stores of one FMT_F4C staging buffer (32 rows x 128 B: granules 0..3 = 32 hi halves, 4 = 32 P nibbles,
+// 5 = 32 Q nibbles; 8 lanes = one row).  Which array a lane writes depends only on its granule, so base pointer and row
+// pitch are per-lane constants of the whole kernel: a store costs one 64-bit add, no divergent address code (the first
+// version re-derived the three-way address per store: a quarter of the fc1 epilogue's instructions).
+struct F4cStore {
+  uint8_t* base;     // hi: out_hi + 16 gsub bytes;  P: c4;  Q: c4 + N / 2
+  size_t pitch;      // bytes per row: 2 N (hi) or N (c4)
+  int col_shift;     // byte offset of column c inside the row: c << 1 (hi) or c >> 1 (nibbles)
+  bool on;           // granules 6, 7 carry nothing
+};
+__device__ __forceinline__ F4cStore f4c_store_init(__half* out_hi, uint8_t* c4, int N, int gsub) {
+  F4cStore st;
+  const bool hi = gsub < 4;
+  st.base = hi ? reinterpret_cast<uint8_t*>(out_hi) + gsub * 16 : c4 + (gsub == 5 ? (N >> 1) : 0);
+  st.pitch = hi ? static_cast<size_t>(2 * N) : static_cast<size_t>(N);
+  st.col_shift = hi ? 1 : -1;
+  st.on = gsub < 6;
+  return st;
+}
+__device__ __forceinline__ void f4c_store_chunk(const F4cStore& st, uint32_t stg, int rsub, int gsub, int row_w, int gcol,
+                                                int M, bool stream_out) {
+  uint4 vals[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) vals[j] = stg_ld(stg, 4 * j + rsub, gsub);
+  uint8_t* d = st.base + static_cast<size_t>(row_w + rsub) * st.pitch + (st.col_shift > 0 ? gcol << 1 : gcol >> 1);
+  const size_t step = 4 * st.pitch;
+  if (M - row_w >= 32) {                           // warp-uniform: whole chunk inside the matrix, no per-store predicate
+    if (st.on) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (stream_out) ptx::st_global_cs(d, vals[j]); else *reinterpret_cast<uint4*>(d) = vals[j];
+        d += step;
+      }
+    }
+    return;
+  }
+  const int rows_left = M - row_w - rsub;          // ragged last tile: row 4 j + rsub is stored while 4 j < rows_left
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (st.on && 4 * j < rows_left) {
+      if (stream_out) ptx::st_global_cs(d, vals[j]); else *reinterpret_cast<uint4*>(d) = vals[j];
+    }
+    d += step;
+  }
+}
+
+// FMT_F4C image of one 32 x 32 chunk of fp32 values (lane = row, r = the bits of its 32 consecutive columns = exactly one
+// scale block of each part): hi halves into the staging row (granules 0..3) with the block maxima of x and of x - hi, then
+// both e2m1 images (granule 4 = 32 nibbles of P = q4(x), granule 5 = Q = q4(x - hi)), then the coalesced stores.  The two
+// ue8m0 scale bytes join the lane's words (byte (gcol / 32) % 4); the caller writes them once per tile.
+__device__ __forceinline__ void f4c_emit_chunk(const uint32_t (&r)[32], uint32_t stg, int lane, int row_w, int gcol, int M,
+                                               const F4cStore& st, bool stream_out, uint32_t& sfp_w, uint32_t& sfq_w) {
+  float ax = 0.f, al = 0.f;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    uint32_t hw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = __uint_as_float(r[8 * v + 2 * e + 0]), x1 = __uint_as_float(r[8 * v + 2 * e + 1]);
+      const __half2 h01 = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h01);
+      hw[e] = *reinterpret_cast<const uint32_t*>(&h01);
+      ax = fmaxf(ax, fmaxf(fabsf(x0), fabsf(x1)));
+      al = fmaxf(al, fmaxf(fabsf(x0 - hf.x), fabsf(x1 - hf.y)));
+    }
+    stg_st(stg, lane, v, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+  }
+  const uint32_t bp = op_ue8m0_of(ax), bq = op_ue8m0_of(al);
+  const ptx::f32x2 ip = ptx::splat2(op_ue8m0_inv(bp)), iq = ptx::splat2(op_ue8m0_inv(bq));
+  uint32_t pw[4], qw[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    uint32_t pa = 0, qa = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = __uint_as_float(r[8 * w + 2 * e + 0]), x1 = __uint_as_float(r[8 * w + 2 * e + 1]);
+      const float2 hf = __half22float2(__floats2half2_rn(x0, x1));
+      float a0, a1, l0, l1;
+      ptx::unpack2(ptx::mul2(ptx::pack2(x0, x1), ip), a0, a1);
+      ptx::unpack2(ptx::mul2(ptx::sub2(ptx::pack2(x0, x1), ptx::pack2(hf.x, hf.y)), iq), l0, l1);
+      pa |= op_e2m1x2(a0, a1) << (8 * e);
+      qa |= op_e2m1x2(l0, l1) << (8 * e);
+    }
+    pw[w] = pa; qw[w] = qa;
+  }
+  stg_st(stg, lane, 4, make_uint4(pw[0], pw[1], pw[2], pw[3]));
+  stg_st(stg, lane, 5, make_uint4(qw[0], qw[1], qw[2], qw[3]));
+  sfp_w |= bp << (8 * ((gcol >> 5) & 3));
+  sfq_w |= bq << (8 * ((gcol >> 5) & 3));
+  __syncwarp();
+  f4c_store_chunk(st, stg, lane >> 3, lane & 7, row_w, gcol, M, stream_out);
 }
 
 // CS = CTA pairs per cluster (CG == 2 only).  CS == 2: a cluster of 4 CTAs owns two vertically adjacent 256 x 256
@@ -170,11 +308,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + C::kStages * C::kStageBytes;
   Barriers* bars = reinterpret_cast<Barriers*>(staging + C::kStagingBytes);
+  float* sm_bias = reinterpret_cast<float*>(staging + C::kStagingBytes + 256);      // [1024] bias, [1024] column sums
+  float* sm_colsum = sm_bias + 1024;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   static_assert(CS == 1 || (CG == 2 && PASSES == 2), "pair clusters are implemented for the CTA-pair F8C kernel");
   static_assert(PASSES != 4 || EPI != EPI_F32_LN, "the fused LayerNorm epilogue keeps x in TMEM: no room for scale factors");
+  static_assert(PASSES == 4 || (EPI != EPI_F32_EMIT && EPI != EPI_GELU_DLN), "deferred LayerNorm: FMT_F4C kernel only");
+  constexpr bool kF32 = EPI == EPI_F32 || EPI == EPI_F32_LN || EPI == EPI_F32_EMIT;          // fp32 output (+ residual)
+  constexpr bool kGelu4 = (EPI == EPI_GELU_SPLIT || EPI == EPI_GELU_DLN) && PASSES == 4;      // GELU -> FMT_F4C operand
   const uint32_t crank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // rank in the cluster (0 .. 2*CS-1)
   const uint32_t rank = crank & 1u;                                 // position in the CTA pair, 0 = leader
   const uint32_t pair = crank >> 1;                                 // pair index inside the cluster (0 .. CS-1)
@@ -230,6 +373,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (warp == 2) {
     if (CG == 2) ptx::tmem_alloc_cg2<C::kTmemCols>(&bars->tmem_base);
     else ptx::tmem_alloc<C::kTmemCols>(&bars->tmem_base);
+  }
+  if (kGelu4 || EPI == EPI_F32_EMIT) {           // N <= 1024 (checked by the launcher)
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      sm_bias[i] = p.bias[i];
+      if (EPI == EPI_GELU_DLN) sm_colsum[i] = p.ln_colsum[i];
+    }
   }
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();
@@ -456,23 +605,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int half = (warp - 4) >> 2;       // which slice of the BN columns (BN / kColsW columns each)
     constexpr int kColsW = BN / (EW / 4);   // columns per warp
     constexpr int kChunks = kColsW / 32;    // 32-column chunks per warp
-    uint8_t* stg = staging + (warp - 4) * 4096;
+    const uint32_t stg = ptx::smem_u32(staging) + (warp - 4) * 4096;
     const int rsub = lane >> 3, gsub = lane & 7;      // coalesced mapping: instruction j covers rows 4j + rsub
     int acc = 0;
     uint32_t acc_phase = 0;
     // EPI_F32_LN: running (mean, M2) of this lane's row over the 128 columns this warp owns in each accumulator
     float ln_mean[2] = {0.f, 0.f}, ln_m2[2] = {0.f, 0.f};
+    constexpr bool kSmemVec = kGelu4 || EPI == EPI_F32_EMIT;     // bias / column sums come from shared memory
+    const F4cStore f4st = EPI == EPI_F32_EMIT ? f4c_store_init(p.emit_hi, p.emit_c4, p.N, gsub)
+                                              : f4c_store_init(p.out_hi, reinterpret_cast<uint8_t*>(p.out_lo), p.N, gsub);
+    // PASSES == 4 (the shipped kernel): streaming stores are compiled in (D3D_GEMM_STREAM_OUT=0 at BUILD time for the A/B);
+    // a run-time choice cost two predicated stores and four R2UR per store instruction (distinct memory descriptors)
+#ifndef D3D_GEMM_STREAM_OUT
+#define D3D_GEMM_STREAM_OUT 1
+#endif
+    const bool stream_out = PASSES == 4 ? (D3D_GEMM_STREAM_OUT != 0) : (p.stream_out != 0);
+    // EPI_GELU_DLN: (rstd, -rstd mean) of this lane's row, valid for all n-tiles of the current m-tile; the partial sums
+    // of the NEXT m-tile's row are fetched a few per tile while this m-tile is processed (their latency would otherwise
+    // sit on the epilogue's critical path, which sets the tile time of fc1)
+    ptx::f32x2 dln_a = ptx::splat2(1.0f), dln_b = ptx::splat2(0.0f);
+    int dln_mt = -1;                         // m-tile the pair (dln_a, dln_b) belongs to
+    float dln_s1 = 0.f, dln_s2 = 0.f;        // sums gathered so far for m-tile dln_next_mt
+    int dln_next_mt = -1, dln_parts_done = 0;
+    auto dln_row_of = [&](int mt) { return ((mt * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM) + q * 32 + lane; };
     for (int q_ = 0, tile; (tile = tile_of(q_)) >= 0; ++q_) {
       const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
       const int n0 = (tile % n_tiles_n) * BN;
       const int row_w = m0 + q * 32;                    // first row of this warp
       const int colbase = n0 + half * kColsW;
-      const bool has_res = (EPI == EPI_F32 || EPI == EPI_F32_LN) && p.residual != nullptr;
+      const bool has_res = kF32 && p.residual != nullptr;
       // Residual prefetch, kResDepth chunks deep (registers).  The fp32 + residual epilogue moves 256 KB per CTA and tile
       // (read + write) and, with the F4C mainloop at ~5 us per tile, sets the tile time of proj / fc2: ncu had them at
       // 55-58 % of DRAM with ONE 4 KB chunk per warp in flight (32 KB per SM, below bandwidth x latency ~ 44 B/ns x 0.8 us);
       // two chunks per warp double the bytes in flight (profiles/r02d_full_gemm.md -> r02e).
-      constexpr int kResDepth = (EPI == EPI_F32 && EW == 8) ? D3D_GEMM_RES_DEPTH : 1;      // EW = 16: 104 registers, no room
+      constexpr int kResDepth = (EPI == EPI_F32 && EW == 8) ? D3D_GEMM_RES_DEPTH : 1;      // EMIT keeps x in registers too      // EW = 16: 104 registers, no room
+      // 16 warps at 104 registers: x (32 registers) stays live through the operand emission, so the next residual chunk is
+      // requested only after it (four warps per scheduler cover the exposed latency)
+      constexpr bool kLateRes = EPI == EPI_F32_EMIT && EW == 16;
       float4 resv[kResDepth][8];
       auto load_res = [&](int ci) {                     // residual chunk ci, coalesced (row 4j + rsub, granule gsub)
 #pragma unroll
@@ -480,14 +649,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           const int rr = row_w + 4 * j + rsub;
           const float* src = p.residual + static_cast<size_t>(rr) * p.N + colbase + ci * 32 + gsub * 4;
           resv[ci % kResDepth][j] = rr >= p.M ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                              : (p.stream_out ? ptx::ld_global_cs(src) : *reinterpret_cast<const float4*>(src));
+                                              : (stream_out ? ptx::ld_global_cs(src) : *reinterpret_cast<const float4*>(src));
         }
       };
       if (has_res) {                         // in flight while the accumulator is still being computed
 #pragma unroll
         for (int c = 0; c < kResDepth; ++c) load_res(c);
       }
-      uint32_t sfp_w = 0, sfq_w = 0;         // F4C GELU output: this row's scale bytes of the tile's k-blocks (P / Q part)
+      uint32_t sfp_w = 0, sfq_w = 0;         // F4C output operand: this row's scale bytes of the tile's k-blocks (P / Q part)
+      ptx::f32x2 ln_s1p = ptx::splat2(0.f), ln_s2p = ptx::splat2(0.f);   // EPI_F32_EMIT: (sum, sum of squares) of this lane's row, 64 columns
+      float2 dln_pf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // partial sums in flight during this tile
+      int dln_pf_n = 0;
+      if (EPI == EPI_GELU_DLN) {
+        const int parts = p.K >> 6;
+        const int mt = tile / n_tiles_n;
+        if (mt != dln_mt) {
+          // statistics of this m-tile: whatever was not prefetched is loaded now (all of it for the first m-tile)
+          const int rr = dln_row_of(mt);
+          if (dln_next_mt != mt) { dln_s1 = 0.f; dln_s2 = 0.f; dln_parts_done = 0; }
+          if (rr < p.M)           // same order of additions as the prefetched path: results must not depend on which
+            for (int pt = dln_parts_done; pt < parts; pt += 2) {      // tiles of a CTA a row falls into (batch-split invariance)
+              const float2 v0 = p.ln_stats[static_cast<size_t>(pt) * p.M + rr];
+              const float2 v1 = p.ln_stats[static_cast<size_t>(pt + 1) * p.M + rr];
+              dln_s1 += v0.x + v1.x; dln_s2 += v0.y + v1.y;
+            }
+          const float inv_k = 1.0f / static_cast<float>(p.K);
+          const float mean = dln_s1 * inv_k;
+          const float var = fmaxf(fmaf(-mean, mean, dln_s2 * inv_k), 0.0f);
+          const float rstd = 1.0f / sqrtf(var + p.ln_eps);
+          dln_a = ptx::splat2(rstd);
+          dln_b = ptx::splat2(-rstd * mean);
+          dln_mt = mt;
+          dln_s1 = 0.f; dln_s2 = 0.f; dln_parts_done = 0;
+          const int nt = tile_of(q_ + n_tiles_n - tile % n_tiles_n);       // first tile of this unit's next m-tile
+          dln_next_mt = nt >= 0 ? nt / n_tiles_n : -1;
+        }
+        if (dln_next_mt >= 0 && dln_parts_done < parts) {                   // two more parts of the next m-tile's row
+          const int rr = dln_row_of(dln_next_mt);
+          dln_pf_n = 2;                                                     // K % 128 == 0: an even number of parts
+          if (rr < p.M) {
+            dln_pf[0] = p.ln_stats[static_cast<size_t>(dln_parts_done) * p.M + rr];
+            dln_pf[1] = p.ln_stats[static_cast<size_t>(dln_parts_done + 1) * p.M + rr];
+          }
+        }
+      }
       ptx::mbar_wait(&bars->tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll
@@ -497,14 +702,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         ptx::tmem_ld_32x32(tmem_base + acc * BN + col0 + (static_cast<uint32_t>(q * 32) << 16), r);
         if (has_res) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) *stg_at(stg, 4 * j + rsub, gsub) = *reinterpret_cast<uint4*>(&resv[ci % kResDepth][j]);
+          for (int j = 0; j < 8; ++j) stg_st(stg, 4 * j + rsub, gsub, *reinterpret_cast<uint4*>(&resv[ci % kResDepth][j]));
           __syncwarp();
-          if (ci + kResDepth < kChunks) load_res(ci + kResDepth);
+          if (!kLateRes && ci + kResDepth < kChunks) load_res(ci + kResDepth);
         }
         const int gcol = n0 + col0;
         float4 bias4[8];                                 // issued before the TMEM wait so their latency is hidden
+        if (!kSmemVec) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) bias4[v] = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + v);
+          for (int v = 0; v < 8; ++v) bias4[v] = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + v);
+        }
+        const uint32_t sb4 = ptx::smem_u32(sm_bias + gcol), sc4 = ptx::smem_u32(sm_colsum + gcol);   // kSmemVec: read just in time
         ptx::tmem_ld_wait();
         if (PASSES == 4 && ci == 0 && half == 0) {
           // columns 0..31 of this accumulator are in registers: the NEXT tile's e2m1 stages may put their scale factors there
@@ -512,22 +720,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->sf_free[acc]), leader));
         }
-        if (EPI == EPI_F32 || EPI == EPI_F32_LN) {
+        if (EPI == EPI_F32_EMIT) {
+          // x = acc + bias + residual on packed pairs; x stays in r for the operand image; (sum, sum of squares) per lane
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const float4 b = lds_f4(sb4 + 16 * v);
+            const uint4 ru = stg_ld(stg, lane, v);
+            const ptx::f32x2 o01 = ptx::add2(ptx::add2(ptx::pack2(__uint_as_float(r[4 * v + 0]), __uint_as_float(r[4 * v + 1])), ptx::pack2(b.x, b.y)),
+                                             ptx::pack2(__uint_as_float(ru.x), __uint_as_float(ru.y)));
+            const ptx::f32x2 o23 = ptx::add2(ptx::add2(ptx::pack2(__uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3])), ptx::pack2(b.z, b.w)),
+                                             ptx::pack2(__uint_as_float(ru.z), __uint_as_float(ru.w)));
+            float o0, o1, o2, o3;
+            ptx::unpack2(o01, o0, o1);
+            ptx::unpack2(o23, o2, o3);
+            r[4 * v + 0] = __float_as_uint(o0); r[4 * v + 1] = __float_as_uint(o1);
+            r[4 * v + 2] = __float_as_uint(o2); r[4 * v + 3] = __float_as_uint(o3);
+            stg_st(stg, lane, v, make_uint4(r[4 * v + 0], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]));
+            ln_s1p = ptx::add2(ln_s1p, ptx::add2(o01, o23));
+            ln_s2p = ptx::fma2(o01, o01, ptx::fma2(o23, o23, ln_s2p));
+          }
+          __syncwarp();
+          uint4 vals[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vals[j] = stg_ld(stg, 4 * j + rsub, gsub);
+          {
+            float* d = p.out_f32 + static_cast<size_t>(row_w + rsub) * p.N + gcol + gsub * 4;
+            const size_t step = static_cast<size_t>(4) * p.N;
+            if (p.M - row_w >= 32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { ptx::st_global_cs(d, vals[j]); d += step; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { if (row_w + 4 * j + rsub < p.M) ptx::st_global_cs(d, vals[j]); d += step; }
+            }
+          }
+          __syncwarp();                        // every lane has read the fp32 rows out of the staging buffer
+          f4c_emit_chunk(r, stg, lane, row_w, gcol, p.M, f4st, stream_out, sfp_w, sfq_w);
+          if (kLateRes && ci + 1 < kChunks) load_res(ci + 1);
+          if (ci & 1) {                        // two chunks = 64 columns = one statistics part
+            const int rr = row_w + lane;
+            float a0, a1, q0, q1;
+            ptx::unpack2(ln_s1p, a0, a1);
+            ptx::unpack2(ln_s2p, q0, q1);
+            if (rr < p.M) p.ln_stats[static_cast<size_t>(gcol >> 6) * p.M + rr] = make_float2(a0 + a1, q0 + q1);
+            ln_s1p = ptx::splat2(0.f); ln_s2p = ptx::splat2(0.f);
+          }
+        } else if (kF32) {
           float csum = 0.f;
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
-            const float4 b = bias4[v];
+            const float4 b = kSmemVec ? lds_f4(sb4 + 16 * v) : bias4[v];
             float4 o;
             o.x = __uint_as_float(r[4 * v + 0]) + b.x;
             o.y = __uint_as_float(r[4 * v + 1]) + b.y;
             o.z = __uint_as_float(r[4 * v + 2]) + b.z;
             o.w = __uint_as_float(r[4 * v + 3]) + b.w;
-            uint4* cell = stg_at(stg, lane, v);
             if (has_res) {
-              const float4 rr = *reinterpret_cast<const float4*>(cell);
-              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              const uint4 ru = stg_ld(stg, lane, v);
+              o.x += __uint_as_float(ru.x); o.y += __uint_as_float(ru.y); o.z += __uint_as_float(ru.z); o.w += __uint_as_float(ru.w);
             }
-            *reinterpret_cast<float4*>(cell) = o;
+            stg_st(stg, lane, v, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
             if (EPI == EPI_F32_LN) {           // keep x for the statistics and the TMEM write-back
               r[4 * v + 0] = __float_as_uint(o.x); r[4 * v + 1] = __float_as_uint(o.y);
               r[4 * v + 2] = __float_as_uint(o.z); r[4 * v + 3] = __float_as_uint(o.w);
@@ -556,16 +808,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           __syncwarp();
           uint4 vals[8];                       // all shared loads first, then all global stores (distinct registers)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
+          for (int j = 0; j < 8; ++j) vals[j] = stg_ld(stg, 4 * j + rsub, gsub);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int rr = row_w + 4 * j + rsub;
             if (rr < p.M) {
               float* dst = p.out_f32 + static_cast<size_t>(rr) * p.N + gcol + gsub * 4;
-              if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
+              if (stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
             }
           }
-        } else if (EPI == EPI_GELU_SPLIT && PASSES == 4) {
+        } else if (kGelu4) {
           // FMT_F4C operand of fc2: this lane's 32 columns are exactly one scale block of each part.  Pass 1: GELU, hi
           // halves into the staging row (granules 0..3), block maxima of x and of x - hi; pass 2: both e2m1 images
           // (granule 4 = 32 nibbles of P = q4(x), granule 5 = Q = q4(x - hi)); the two scale bytes join the lane's words.
@@ -575,9 +827,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             uint32_t hw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float4 b = bias4[2 * v + (e >> 1)];
-              ptx::f32x2 xp = ptx::add2(ptx::pack2(__uint_as_float(r[8 * v + 2 * e + 0]), __uint_as_float(r[8 * v + 2 * e + 1])),
-                                        (e & 1) ? ptx::pack2(b.z, b.w) : ptx::pack2(b.x, b.y));
+              const float4 b = lds_f4(sb4 + 16 * (2 * v + (e >> 1)));
+              const ptx::f32x2 accp = ptx::pack2(__uint_as_float(r[8 * v + 2 * e + 0]), __uint_as_float(r[8 * v + 2 * e + 1]));
+              ptx::f32x2 bp2 = (e & 1) ? ptx::pack2(b.z, b.w) : ptx::pack2(b.x, b.y);
+              ptx::f32x2 xp;
+              if (EPI == EPI_GELU_DLN) {        // rstd acc + (c_n - rstd mean s_n)
+                const float4 cs = lds_f4(sc4 + 16 * (2 * v + (e >> 1)));
+                bp2 = ptx::fma2(dln_b, (e & 1) ? ptx::pack2(cs.z, cs.w) : ptx::pack2(cs.x, cs.y), bp2);
+                xp = ptx::fma2(dln_a, accp, bp2);
+              } else {
+                xp = ptx::add2(accp, bp2);
+              }
               xp = gelu_erf2(xp);
               float x0, x1;
               ptx::unpack2(xp, x0, x1);
@@ -589,7 +849,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               r[8 * v + 2 * e + 0] = __float_as_uint(x0);
               r[8 * v + 2 * e + 1] = __float_as_uint(x1);
             }
-            *stg_at(stg, lane, v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            stg_st(stg, lane, v, make_uint4(hw[0], hw[1], hw[2], hw[3]));
           }
           const uint32_t bp = op_ue8m0_of(ax), bq = op_ue8m0_of(al);
           const ptx::f32x2 ip = ptx::splat2(op_ue8m0_inv(bp)), iq = ptx::splat2(op_ue8m0_inv(bq));
@@ -609,23 +869,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
             pw[w] = pa; qw[w] = qa;
           }
-          *stg_at(stg, lane, 4) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-          *stg_at(stg, lane, 5) = make_uint4(qw[0], qw[1], qw[2], qw[3]);
+          stg_st(stg, lane, 4, make_uint4(pw[0], pw[1], pw[2], pw[3]));
+          stg_st(stg, lane, 5, make_uint4(qw[0], qw[1], qw[2], qw[3]));
           sfp_w |= bp << (8 * ((gcol >> 5) & 3));
           sfq_w |= bq << (8 * ((gcol >> 5) & 3));
           __syncwarp();
-          uint8_t* c4 = reinterpret_cast<uint8_t*>(p.out_lo);
-          uint4 vals[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = row_w + 4 * j + rsub;
-            if (rr >= p.M || gsub >= 6) continue;
-            void* dst = gsub < 4 ? static_cast<void*>(p.out_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8)
-                                 : static_cast<void*>(c4 + static_cast<size_t>(rr) * p.N + (gsub == 4 ? 0 : (p.N >> 1)) + (gcol >> 1));
-            if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
-          }
+          f4c_store_chunk(f4st, stg, rsub, gsub, row_w, gcol, p.M, stream_out);
         } else {
           // fp16 outputs: row = hi (granules 0..3, 32 halves) | second part (granules 4..7):
           //   fp16 lo (FMT_SPLIT16, and always for q|k|v), or for the FMT_F8C fc2 operand
@@ -674,19 +923,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               }
 #endif
             }
-            *stg_at(stg, lane, v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            stg_st(stg, lane, v, make_uint4(hw[0], hw[1], hw[2], hw[3]));
             if (f8out) {
               a8w[2 * v] = a16[0] | (a16[1] << 16); a8w[2 * v + 1] = a16[2] | (a16[3] << 16);
               l8w[2 * v] = l16[0] | (l16[1] << 16); l8w[2 * v + 1] = l16[2] | (l16[3] << 16);
             } else {
-              *stg_at(stg, lane, 4 + v) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              stg_st(stg, lane, 4 + v, make_uint4(lw[0], lw[1], lw[2], lw[3]));
             }
           }
           if (f8out) {
-            *stg_at(stg, lane, 4) = make_uint4(a8w[0], a8w[1], a8w[2], a8w[3]);
-            *stg_at(stg, lane, 5) = make_uint4(a8w[4], a8w[5], a8w[6], a8w[7]);
-            *stg_at(stg, lane, 6) = make_uint4(l8w[0], l8w[1], l8w[2], l8w[3]);
-            *stg_at(stg, lane, 7) = make_uint4(l8w[4], l8w[5], l8w[6], l8w[7]);
+            stg_st(stg, lane, 4, make_uint4(a8w[0], a8w[1], a8w[2], a8w[3]));
+            stg_st(stg, lane, 5, make_uint4(a8w[4], a8w[5], a8w[6], a8w[7]));
+            stg_st(stg, lane, 6, make_uint4(l8w[0], l8w[1], l8w[2], l8w[3]));
+            stg_st(stg, lane, 7, make_uint4(l8w[4], l8w[5], l8w[6], l8w[7]));
           }
           __syncwarp();
           __half* hi_base;
@@ -702,7 +951,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             uint8_t* c8 = reinterpret_cast<uint8_t*>(p.out_lo);
             uint4 vals[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
+            for (int j = 0; j < 8; ++j) vals[j] = stg_ld(stg, 4 * j + rsub, gsub);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int rr = row_w + 4 * j + rsub;
@@ -710,33 +959,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               void* dst = gsub < 4 ? static_cast<void*>(p.out_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8)
                                    : static_cast<void*>(c8 + static_cast<size_t>(rr) * (2 * p.N) + (gsub < 6 ? 0 : p.N) +
                                                         gcol + (gsub & 1) * 16);
-              if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
+              if (stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
             }
           } else {
             __half* dst_base = gsub < 4 ? hi_base : lo_base;
             uint4 vals[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
+            for (int j = 0; j < 8; ++j) vals[j] = stg_ld(stg, 4 * j + rsub, gsub);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int rr = row_w + 4 * j + rsub;
               if (rr < p.M && dst_base) {
                 __half* dst = dst_base + static_cast<size_t>(rr) * ld + (gsub & 3) * 8;
-                if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
+                if (stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
               }
             }
           }
         }
         __syncwarp();          // the buffer is rewritten by the next chunk
       }
-      if (EPI == EPI_GELU_SPLIT && PASSES == 4) {
+      if (kGelu4 || EPI == EPI_F32_EMIT) {
         // scale bytes of row (row_w + lane): k-blocks colbase/32 .. +kChunks-1 of part P, the same + N/32 of part Q; they
         // are adjacent bytes of one scale-factor atom (operand.cuh), written as one word (4 chunks) or half-word (2)
         const int rr = row_w + lane;
         if (rr < p.M) {
           const int kb0 = colbase >> 5, apt = p.N / 64;
-          uint8_t* dp = p.out_sf + op_sf_offset(rr, kb0, apt);
-          uint8_t* dq = p.out_sf + op_sf_offset(rr, (p.N >> 5) + kb0, apt);
+          uint8_t* sf_out = EPI == EPI_F32_EMIT ? p.emit_sf : p.out_sf;
+          uint8_t* dp = sf_out + op_sf_offset(rr, kb0, apt);
+          uint8_t* dq = sf_out + op_sf_offset(rr, (p.N >> 5) + kb0, apt);
           if (kChunks == 4) {
             *reinterpret_cast<uint32_t*>(dp) = sfp_w;
             *reinterpret_cast<uint32_t*>(dq) = sfq_w;
@@ -753,7 +1003,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         // GEMM's A operand.  Accumulator 0 is released only here (x lives in it between the passes).
         if (acc == 1) {
           ptx::tmem_st_wait();
-          *reinterpret_cast<float4*>(stg + lane * 16) = make_float4(ln_mean[0], ln_m2[0], ln_mean[1], ln_m2[1]);
+          *reinterpret_cast<float4*>(staging + (warp - 4) * 4096 + lane * 16) = make_float4(ln_mean[0], ln_m2[0], ln_mean[1], ln_m2[1]);
           ptx::bar_sync(1, EW * 32);
           const float4 oth = *reinterpret_cast<const float4*>(staging + ((warp - 4) ^ 4) * 4096 + lane * 16);
           ptx::bar_sync(1, EW * 32);                       // every partner row is read: the buffers may be reused
@@ -794,18 +1044,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                   a16[e] = op_e5m2x2(x0 * kActHiScale, x1 * kActHiScale);
                   l16[e] = op_e5m2x2((x0 - __half2float(h0)) * kActLoScale, (x1 - __half2float(h1)) * kActLoScale);
                 }
-                *stg_at(stg, lane, v) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                stg_st(stg, lane, v, make_uint4(hw[0], hw[1], hw[2], hw[3]));
                 a8w[2 * v] = a16[0] | (a16[1] << 16); a8w[2 * v + 1] = a16[2] | (a16[3] << 16);
                 l8w[2 * v] = l16[0] | (l16[1] << 16); l8w[2 * v + 1] = l16[2] | (l16[3] << 16);
               }
-              *stg_at(stg, lane, 4) = make_uint4(a8w[0], a8w[1], a8w[2], a8w[3]);
-              *stg_at(stg, lane, 5) = make_uint4(a8w[4], a8w[5], a8w[6], a8w[7]);
-              *stg_at(stg, lane, 6) = make_uint4(l8w[0], l8w[1], l8w[2], l8w[3]);
-              *stg_at(stg, lane, 7) = make_uint4(l8w[4], l8w[5], l8w[6], l8w[7]);
+              stg_st(stg, lane, 4, make_uint4(a8w[0], a8w[1], a8w[2], a8w[3]));
+              stg_st(stg, lane, 5, make_uint4(a8w[4], a8w[5], a8w[6], a8w[7]));
+              stg_st(stg, lane, 6, make_uint4(l8w[0], l8w[1], l8w[2], l8w[3]));
+              stg_st(stg, lane, 7, make_uint4(l8w[4], l8w[5], l8w[6], l8w[7]));
               __syncwarp();
               uint4 vals[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) vals[j] = *stg_at(stg, 4 * j + rsub, gsub);
+              for (int j = 0; j < 8; ++j) vals[j] = stg_ld(stg, 4 * j + rsub, gsub);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const int rr = row_w + 4 * j + rsub;
@@ -813,7 +1063,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 void* dst = gsub < 4 ? static_cast<void*>(p.ln_hi + static_cast<size_t>(rr) * p.N + gcol + gsub * 8)
                                      : static_cast<void*>(c8 + static_cast<size_t>(rr) * (2 * p.N) + (gsub < 6 ? 0 : p.N) +
                                                           gcol + (gsub & 1) * 16);
-                if (p.stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
+                if (stream_out) ptx::st_global_cs(dst, vals[j]); else *reinterpret_cast<uint4*>(dst) = vals[j];
               }
               __syncwarp();
             }
@@ -832,6 +1082,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[acc]), leader));
           else ptx::mbar_arrive(&bars->tmem_empty[acc]);
         }
+      }
+      if (EPI == EPI_GELU_DLN && dln_pf_n > 0) {       // the prefetched partial sums have long arrived
+        dln_s1 += dln_pf[0].x + dln_pf[1].x;
+        dln_s2 += dln_pf[0].y + dln_pf[1].y;
+        dln_parts_done += dln_pf_n;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -937,6 +1192,10 @@ cudaError_t configure_gemm_tc() {
   if ((e = configure_one<2, 256, 4, EPI_F32, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 4, EPI_GELU_SPLIT, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 4, EPI_QKV16, 1, 16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_F32_EMIT>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_F32_EMIT, 1, 16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_GELU_DLN>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_GELU_DLN, 1, 16>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -947,16 +1206,25 @@ cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, i
     // FMT_F4C: CTA-pair 256 x 256 tiles only; K in whole e2m1 stages (256 nibbles = 128 bytes of the K-byte c4 row)
     if (p.N % 256 != 0 || p.K % 128 != 0 || epi == EPI_F32_LN) return cudaErrorInvalidValue;
     if (epi == EPI_QKV16 && p.N != 3 * kC) return cudaErrorInvalidValue;
-    if (epi == EPI_GELU_SPLIT && !p.out_sf) return cudaErrorInvalidValue;
+    if ((epi == EPI_GELU_SPLIT || epi == EPI_GELU_DLN) && (!p.out_sf || p.N > 1024)) return cudaErrorInvalidValue;
+    // deferred LayerNorm: statistics parts of 64 columns, eight per 512-wide row
+    if (epi == EPI_F32_EMIT && (p.N != kC || !p.residual || !p.emit_hi || !p.emit_c4 || !p.emit_sf || !p.ln_stats))
+      return cudaErrorInvalidValue;
+    if (epi == EPI_GELU_DLN && (p.K != kC || !p.ln_stats || !p.ln_colsum)) return cudaErrorInvalidValue;
     if (epi_warps == 16) {
       if (epi == EPI_F32) return launch_one<2, 256, 4, EPI_F32, 1, 16>(maps, p, num_sms, st);
       if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 4, EPI_GELU_SPLIT, 1, 16>(maps, p, num_sms, st);
+      if (epi == EPI_F32_EMIT) return launch_one<2, 256, 4, EPI_F32_EMIT, 1, 16>(maps, p, num_sms, st);
+      if (epi == EPI_GELU_DLN) return launch_one<2, 256, 4, EPI_GELU_DLN, 1, 16>(maps, p, num_sms, st);
       return launch_one<2, 256, 4, EPI_QKV16, 1, 16>(maps, p, num_sms, st);
     }
     if (epi == EPI_F32) return launch_one<2, 256, 4, EPI_F32>(maps, p, num_sms, st);
     if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 4, EPI_GELU_SPLIT>(maps, p, num_sms, st);
+    if (epi == EPI_F32_EMIT) return launch_one<2, 256, 4, EPI_F32_EMIT>(maps, p, num_sms, st);
+    if (epi == EPI_GELU_DLN) return launch_one<2, 256, 4, EPI_GELU_DLN>(maps, p, num_sms, st);
     return launch_one<2, 256, 4, EPI_QKV16>(maps, p, num_sms, st);
   }
+  if (epi == EPI_F32_EMIT || epi == EPI_GELU_DLN) return cudaErrorInvalidValue;     // FMT_F4C kernel only
   if (cta_group == 2 || passes == 2) bn = 256;
   if (epi == EPI_F32_LN) {
     // needs: both 256-column halves of a row tile on the same CTA pair, back to back, in accumulators 0 and 1

@@ -21,7 +21,14 @@ constexpr int kHidden = 1024;  // mlp hidden
 //                out_f32 = x = acc + bias + residual;  ln_hi/ln_second[M,512] = operand(LN(x; ln_gamma, ln_beta, ln_eps)).
 //                CTA-pair F8C tcgen05 kernel only (both 256-column halves of a row tile finish back to back on the
 //                same CTA pair with the n-inner tile order, so the full rows sit in the two TMEM accumulators).
-enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_QKV16 = 2, EPI_F32_LN = 3 };
+// EPI_F32_EMIT   EPI_F32 with a residual, N == 512, FMT_F4C CTA-pair kernel: out_f32 = x = acc + bias + residual AND
+//                the SAME x leaves as a block-scaled GEMM operand (emit_hi / emit_c4 / emit_sf, K_out = N) together with
+//                per-row partial statistics ln_stats[part][M] = (sum, sum of squares) over columns 64 part .. 64 part + 63.
+//                This is proj + the DEFERRED norm2 (MODEL:127-128): the LayerNorm itself is applied by the consumer,
+// EPI_GELU_DLN   EPI_GELU_SPLIT whose A operand is that un-normalised x and whose weights were folded at load time
+//                (W' = gamma (.) W):  LN(x) . W^T + b = rstd_r (acc - mean_r s_n) + c_n  with  s_n = sum_k W'[n,k]
+//                (ln_colsum), c_n = b_n + sum_k W[n,k] beta_k (passed as `bias`), (mean_r, rstd_r) from ln_stats.
+enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_QKV16 = 2, EPI_F32_LN = 3, EPI_F32_EMIT = 4, EPI_GELU_DLN = 5 };
 
 constexpr int kQkvRow = 4 * kC;   // halves per token row of the packed q|k|v_hi|v_lo tensor
 
@@ -44,6 +51,11 @@ struct GemmParams {
   __half* ln_hi;          // A operand of the next GEMM (FMT_F8C: hi fp16 [M,512] + c8 bytes [M,1024])
   __half* ln_second;
   int n_inner;            // tile order of the persistent tcgen05 kernel: 1 = all n-tiles of an m-tile on the same CTA pair
+  __half* emit_hi;        // EPI_F32_EMIT: x as a FMT_F4C operand [M,N] (hi fp16, c4 bytes, scale-factor atoms)
+  uint8_t* emit_c4;
+  uint8_t* emit_sf;
+  float2* ln_stats;       // EPI_F32_EMIT (written) / EPI_GELU_DLN (read): [8][M] (sum, sum of squares) per 64 columns
+  const float* ln_colsum; // EPI_GELU_DLN: s_n = sum_k W'[n,k]  [N]
 };
 
 // A: [M,K] fp16 (hi, lo), W: [N,K] fp16 (hi, lo); K-major.  Tensor maps use a {64, 128} box, SWIZZLE_128B.
@@ -89,6 +101,11 @@ cudaError_t launch_split(const float* in, __half* hi, __half* second, uint8_t* s
                          int is_weight, cudaStream_t st, float* absmax = nullptr);
 cudaError_t launch_merge(const __half* hi, const __half* second, const uint8_t* sf, float* out, int64_t rows, int K,
                          int fmt, cudaStream_t st);
+
+// Deferred LayerNorm (EPI_GELU_DLN): w_out = w (.) gamma (fp32, to be split), colsum[n] = sum_k w_out[n,k],
+// cbias[n] = bias[n] + sum_k w[n,k] beta[k]   (fold.cu; fp64 sums)
+cudaError_t launch_fold_ln_linear(const float* w, const float* gamma, const float* beta, const float* bias, float* w_out,
+                                  float* colsum, float* cbias, int N, int K, cudaStream_t st);
 
 // FMT_F4C scale factors of `rows` rows in atom layout -> row-major [rows][K / 16] bytes (test read-back)
 cudaError_t launch_sf_rows(const uint8_t* sf, uint8_t* out, int64_t rows, int K, cudaStream_t st);

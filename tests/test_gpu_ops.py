@@ -161,6 +161,33 @@ def test_linear_gelu_f4c_epilogue(eng27, monkeypatch, mode, ew):
     assert (out.double() - ref).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("ew_emit,ew_gelu", [(8, 16), (16, 8)])
+@pytest.mark.parametrize("M", [128, 1377, 74 * 256 + 300])
+def test_deferred_norm2_pair(eng27, monkeypatch, M, ew_emit, ew_gelu):
+    """proj + residual + norm2 + fc1 + GELU (MODEL:127-128, 51-52) as the shipped F4C path runs them: the proj epilogue
+    writes x and emits the SAME x as fc1's block-scaled operand plus per-row partial sums (EPI_F32_EMIT); fc1 runs on the
+    un-normalised rows with norm2.weight folded into its weight and applies (mean, rstd) in its epilogue (EPI_GELU_DLN).
+    Against fp64 torch: x, and gelu(layer_norm(x) w2^T + b2).  Rows carry a mean of ~ 0.6 sigma (more than the sampler's
+    0.2) so that the acc - mean * colsum cancellation is exercised; gains / biases are non-trivial; sizes: one CTA, ragged
+    tiles, more row tiles than CTA pairs."""
+    monkeypatch.setenv("D3D_GEMM_EW_EMIT", str(ew_emit))
+    monkeypatch.setenv("D3D_GEMM_EW_GELU", str(ew_gelu))
+    K = 512
+    a, w, b = _rand((M, K), 51), _rand((512, K), 52, 0.05), _rand((512,), 53, 0.1)
+    res = _rand((M, 512), 54, 1.5) + 1.0
+    gam, bet = _rand((512,), 55) * 0.3 + 1.0, _rand((512,), 56, 0.2)
+    w2, b2 = _rand((1024, 512), 57, 0.05), _rand((1024,), 58, 0.1)
+    x_ref = a.double() @ w.double().T + b.double() + res.double()
+    ln_ref = torch.nn.functional.layer_norm(x_ref, (512,), gam.double(), bet.double(), 1e-6)
+    h_ref = torch.nn.functional.gelu(ln_ref @ w2.double().T + b2.double())
+    x, hid = eng27.op_linear_dln_linear(a.cuda(), w.cuda(), b.cuda(), res.cuda(), gam.cuda(), bet.cuda(), 1e-6, w2.cuda(),
+                                        b2.cuda())
+    scale = (a.double().abs() @ w.double().abs().T).max().item()
+    assert (x.cpu().double() - x_ref).abs().max().item() / scale < 4e-4
+    # same bound as test_linear_gelu_f4c_epilogue (the operand read-back keeps ~13 bits; pre-activations are O(1))
+    assert (hid.cpu().double() - h_ref).abs().max().item() < 2e-3
+
+
 def test_tc_matches_simt_elementwise(eng27):
     """Same split operands in, so tensor-core and CUDA-core results differ only by accumulation order and the
     dropped lo*lo term (2^-22 relative)."""
