@@ -78,6 +78,8 @@ struct d3d_handle {
   // (EPI_F32_EMIT), the fc1 epilogue applies the LayerNorm (EPI_GELU_DLN); no ln_split pass
   bool defer_ln2 = false;
   float2* ln_stats = nullptr;   // [8][tok_cap] (sum, sum of squares) per 64 columns
+  CUtensorMap m_x;              // fp32 [tok_cap, 512] view of X in {32 x 32} boxes: destination of the EPI_F32_RED epilogue
+  bool have_m_x = false;
   AttnTcMaps attn_tc;        // tcgen05 temporal attention: maps bound to QKV -> ATT
   bool have_attn_tc = false;
   AttnTcMaps attn_sp;        // spatial mode of the same kernel (J == 17)
@@ -281,8 +283,14 @@ struct DeferLn {          // deferred LayerNorm (EPI_F32_EMIT producer / EPI_GEL
 // out = epilogue(Aop . W^T + bias)
 int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int epi, const float* residual,
              float* out_f32, __half* out_hi, __half* out_lo, __half* out_qkv, int mode, cudaStream_t st,
-             const LnFuse* ln = nullptr, uint8_t* out_sf = nullptr, const DeferLn* dl = nullptr) {
+             const LnFuse* ln = nullptr, uint8_t* out_sf = nullptr, const DeferLn* dl = nullptr,
+             const CUtensorMap* out_map = nullptr) {
   GemmParams p{};
+  // in-place residual update on the F4C tcgen05 kernel: let the L2 do the add (TMA reduction) instead of pulling the
+  // residual rows into the SM (D3D_GEMM_RED=0: the load-add-store epilogue)
+  if (epi == EPI_F32 && !ln && out_map && residual && residual == out_f32 && mode == D3D_GEMM_TC_F4C && pick_cg(w.N) == 2 &&
+      env_int("D3D_GEMM_RED", 1) == 1)
+    epi = EPI_F32_RED;
   p.out_sf = out_sf;
   if (dl) {
     if (mode != D3D_GEMM_TC_F4C) return fail(h, -3, "the deferred-LayerNorm epilogues need the F4C tcgen05 GEMM");
@@ -322,11 +330,13 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
     m.a_hi = a.m_hi; m.a_lo = a.m_lo; m.b_hi = w.m_hi; m.b_lo = w.m_lo;
     m.b_hi64 = w.m_hi64; m.b_lo64 = w.m_lo64;
     m.a_sf = a.m_sf; m.b_sf = w.m_sf;
+    if (epi == EPI_F32_RED) m.out = *out_map;
     const int passes = mode == D3D_GEMM_TC_FP16 ? 1 : (mode == D3D_GEMM_TC_F8C ? 2 : (mode == D3D_GEMM_TC_F4C ? 4 : 3));
     // epilogue warps per CTA: 16 pays where the epilogue, not the mainloop, sets the tile time
     const int ew = (epi == EPI_GELU_SPLIT || epi == EPI_GELU_DLN) ? env_int("D3D_GEMM_EW_GELU", 16)
                  : epi == EPI_QKV16    ? env_int("D3D_GEMM_EW_QKV", 8)
                  : epi == EPI_F32_EMIT ? env_int("D3D_GEMM_EW_EMIT", 8)
+                 : epi == EPI_F32_RED  ? 8
                                         : env_int("D3D_GEMM_EW_F32", 8);
     KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), pick_cs(M), ew, h->num_sms, st));
   }
@@ -437,12 +447,14 @@ int run_blocks(d3d_handle* h, const float* x2d, const float* y, const float* x5,
       if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32_EMIT, h->X, h->X, nullptr, nullptr, nullptr, gm, st, nullptr, nullptr, &dl))) return r;
       if ((r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_DLN, nullptr, nullptr, h->H.hi, h->H.lo, nullptr, gm, st, nullptr, h->H.sf, &dl))) return r;
     } else {
-      if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
+      if ((r = run_gemm(h, h->ATT, k.proj, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st, nullptr, nullptr, nullptr,
+                        h->have_m_x ? &h->m_x : nullptr))) return r;
       KLP(D3D_PROF_LN, st, launch_ln_split(h->X, LnParams{k.n2g, k.n2b}, 1e-6f, h->A.hi, h->A.lo, h->A.sf, h->fmt, T, st));
     }
     if (!h->defer_ln2 &&
         (r = run_gemm(h, h->A, k.fc1, T, EPI_GELU_SPLIT, nullptr, nullptr, h->H.hi, h->H.lo, nullptr, gm, st, nullptr, h->H.sf))) return r;
-    if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st))) return r;
+    if ((r = run_gemm(h, h->H, k.fc2, T, EPI_F32, h->X, h->X, nullptr, nullptr, nullptr, gm, st, nullptr, nullptr, nullptr,
+                      h->have_m_x ? &h->m_x : nullptr))) return r;
     if (b + 1 < n_blocks) {
       const LnParams post = spatial ? LnParams{h->sn_g, h->sn_b} : LnParams{h->tn_g, h->tn_b};
       const Blk& nx = h->blk[b + 1];
@@ -576,7 +588,10 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
   d3d_handle* h = new d3d_handle();
   h->cfg = *cfg;
   h->fmt = mode_fmt(cfg->gemm_mode);
-  h->defer_ln2 = cfg->gemm_mode == D3D_GEMM_TC_F4C && env_int("D3D_DEFER_LN2", 1) == 1 && pick_cg(kC) == 2;
+  // OFF by default (D3D_DEFER_LN2=1 enables it): measured on B200 at cfg3 (profiles/r02j_*): with the residual update of
+  // proj done by the L2 (EPI_F32_RED) the separate norm2 pass is cheaper than the emitting epilogue, which has to pull
+  // the residual rows into the SM -- 3183 ms per step (RED + norm2 kernel) against 3217 ms (EMIT + DLN)
+  h->defer_ln2 = cfg->gemm_mode == D3D_GEMM_TC_F4C && env_int("D3D_DEFER_LN2", 0) == 1 && pick_cg(kC) == 2;
   h->F = cfg->num_frame;
   h->J = cfg->num_joints;
   h->nblk = 2 * cfg->depth;
@@ -623,6 +638,8 @@ int d3d_create(const d3d_config* cfg, d3d_handle** out) {
     if ((r = dev_alloc(h, &h->perm_dev, 64))) return r;
 
     if ((r = dev_alloc(h, &h->X, h->tok_cap * kC))) return r;
+    if (make_f32_tile_map(&h->m_x, h->X, h->tok_cap, kC)) return fail(h, -20, "cuTensorMapEncodeTiled failed for X");
+    h->have_m_x = true;
     if ((r = dev_alloc(h, &h->QKV, h->tok_cap * kQkvRow))) return r;
     if ((r = alloc_operand(h, &h->A, h->tok_cap, kC))) return r;
     if ((r = alloc_operand(h, &h->ATT, h->tok_cap, kC))) return r;
@@ -1193,6 +1210,12 @@ int d3d_op_linear(d3d_handle* h, const float* a, const float* w, const float* bi
   if (act) {
     if ((r = run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st, nullptr, b.o_sf))) return r;
     KL(launch_merge(b.o_hi, b.o_lo, b.o_sf, out, M, N, fmt, st));
+  } else if (residual && gemm_mode == D3D_GEMM_TC_F4C && N % 256 == 0 && env_int("D3D_GEMM_RED", 1) == 1) {
+    // as the sampler runs proj / fc2: the residual already sits in `out`, the epilogue reduce-adds into it
+    CUtensorMap om;
+    if (make_f32_tile_map(&om, out, M, N)) return fail(h, -20, "cuTensorMapEncodeTiled failed");
+    CK(cudaMemcpyAsync(out, residual, static_cast<size_t>(M) * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, out, out, nullptr, nullptr, nullptr, gemm_mode, st, nullptr, nullptr, nullptr, &om))) return r;
   } else {
     if ((r = run_gemm(h, b.a, b.w, M, EPI_F32, residual, out, nullptr, nullptr, nullptr, gemm_mode, st))) return r;
   }
@@ -1300,9 +1323,11 @@ int d3d_op_linear_bench(d3d_handle* h, int64_t M, int32_t N, int32_t K, int32_t 
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   const DeferLn dl{&emit, stats, colsum, fb, 1e-6f};
+  CUtensorMap fo_map;
+  if (make_f32_tile_map(&fo_map, fo, M, N)) return fail(h, -20, "cuTensorMapEncodeTiled failed");
   auto once = [&]() -> int {
     if (act == 1) return run_gemm(h, b.a, b.w, M, EPI_GELU_SPLIT, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st, nullptr, b.o_sf);
-    if (act == 2) return run_gemm(h, b.a, b.w, M, EPI_F32, fo, fo, nullptr, nullptr, nullptr, gemm_mode, st);
+    if (act == 2) return run_gemm(h, b.a, b.w, M, EPI_F32, fo, fo, nullptr, nullptr, nullptr, gemm_mode, st, nullptr, nullptr, nullptr, &fo_map);
     if (act == 3) return run_gemm(h, b.a, b.w, M, EPI_F32_EMIT, fo, fo, nullptr, nullptr, nullptr, gemm_mode, st, nullptr, nullptr, &dl);
     if (act == 4) return run_gemm(h, b.a, b.w, M, EPI_GELU_DLN, nullptr, nullptr, b.o_hi, b.o_lo, nullptr, gemm_mode, st, nullptr, b.o_sf, &dl);
     return run_gemm(h, b.a, b.w, M, EPI_F32, nullptr, fo, nullptr, nullptr, nullptr, gemm_mode, st);

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const __grid_constant__ CUtensorMap tm_a_sf, const __grid_constant__ CUtensorMap tm_b_sf,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   using C = Cfg<CG, BN, PASSES, EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -317,6 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   static_assert(PASSES != 4 || EPI != EPI_F32_LN, "the fused LayerNorm epilogue keeps x in TMEM: no room for scale factors");
   static_assert(PASSES == 4 || (EPI != EPI_F32_EMIT && EPI != EPI_GELU_DLN), "deferred LayerNorm: FMT_F4C kernel only");
   constexpr bool kF32 = EPI == EPI_F32 || EPI == EPI_F32_LN || EPI == EPI_F32_EMIT;          // fp32 output (+ residual)
+  static_assert(EPI != EPI_F32_RED || PASSES == 4, "the reduction epilogue is built for the FMT_F4C kernel");
   constexpr bool kGelu4 = (EPI == EPI_GELU_SPLIT || EPI == EPI_GELU_DLN) && PASSES == 4;      // GELU -> FMT_F4C operand
   const uint32_t crank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // rank in the cluster (0 .. 2*CS-1)
   const uint32_t rank = crank & 1u;                                 // position in the CTA pair, 0 = leader
@@ -357,6 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::prefetch_tensormap(&tm_a_sf);
       ptx::prefetch_tensormap(&tm_b_sf);
     }
+    if (EPI == EPI_F32_RED) ptx::prefetch_tensormap(&tm_out);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -720,7 +722,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->sf_free[acc]), leader));
         }
-        if (EPI == EPI_F32_EMIT) {
+        if (EPI == EPI_F32_RED) {
+          // X += acc + bias: the chunk goes into the staging buffer (lane = row; the buffer's swizzle is the tensor map's
+          // SWIZZLE_128B) and one lane hands it to the TMA unit as an fp32 add-reduction into X.  The buffer is reused once
+          // the previous reduction has READ it (bulk async-group).
+          if (lane == 0) ptx::bulk_wait_read_all();
+          __syncwarp();
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const float4 b = bias4[v];
+            stg_st(stg, lane, v, make_uint4(__float_as_uint(__uint_as_float(r[4 * v + 0]) + b.x), __float_as_uint(__uint_as_float(r[4 * v + 1]) + b.y),
+                                            __float_as_uint(__uint_as_float(r[4 * v + 2]) + b.z), __float_as_uint(__uint_as_float(r[4 * v + 3]) + b.w)));
+          }
+          ptx::fence_proxy_async();            // generic-proxy writes -> visible to the async proxy (TMA)
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_reduce_add_2d(&tm_out, stg, gcol, row_w);
+            ptx::bulk_commit();
+          }
+        } else if (EPI == EPI_F32_EMIT) {
           // x = acc + bias + residual on packed pairs; x stays in r for the operand image; (sum, sum of squares) per lane
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
@@ -1090,6 +1110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI == EPI_F32_RED && lane == 0) ptx::bulk_wait_all();     // the staging buffer must outlive the last reduction
   }
 #undef D3D_PRODUCER_REGS
   __syncwarp();
@@ -1151,7 +1172,7 @@ cudaError_t launch_one(const GemmMaps& m, const GemmParams& p, int num_sms, cuda
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, CS == 2 ? m.b_hi64 : m.b_hi, CS == 2 ? m.b_lo64 : m.b_lo,
-                            PASSES == 4 ? m.a_sf : m.a_hi, PASSES == 4 ? m.b_sf : m.b_hi, p);
+                            PASSES == 4 ? m.a_sf : m.a_hi, PASSES == 4 ? m.b_sf : m.b_hi, EPI == EPI_F32_RED ? m.out : m.a_hi, p);
 }
 
 template <int CG, int BN, int PASSES, int EPI, int CS = 1, int EW = 8>
@@ -1192,6 +1213,7 @@ cudaError_t configure_gemm_tc() {
   if ((e = configure_one<2, 256, 4, EPI_F32, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 4, EPI_GELU_SPLIT, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 4, EPI_QKV16, 1, 16>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 256, 4, EPI_F32_RED>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 4, EPI_F32_EMIT>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 4, EPI_F32_EMIT, 1, 16>()) != cudaSuccess) return e;
   if ((e = configure_one<2, 256, 4, EPI_GELU_DLN>()) != cudaSuccess) return e;
@@ -1211,6 +1233,7 @@ cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, i
     if (epi == EPI_F32_EMIT && (p.N != kC || !p.residual || !p.emit_hi || !p.emit_c4 || !p.emit_sf || !p.ln_stats))
       return cudaErrorInvalidValue;
     if (epi == EPI_GELU_DLN && (p.K != kC || !p.ln_stats || !p.ln_colsum)) return cudaErrorInvalidValue;
+    if (epi == EPI_F32_RED && (!p.out_f32 || epi_warps == 16)) return cudaErrorInvalidValue;
     if (epi_warps == 16) {
       if (epi == EPI_F32) return launch_one<2, 256, 4, EPI_F32, 1, 16>(maps, p, num_sms, st);
       if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 4, EPI_GELU_SPLIT, 1, 16>(maps, p, num_sms, st);
@@ -1219,12 +1242,13 @@ cudaError_t launch_gemm_tc(const GemmMaps& maps, const GemmParams& p, int epi, i
       return launch_one<2, 256, 4, EPI_QKV16, 1, 16>(maps, p, num_sms, st);
     }
     if (epi == EPI_F32) return launch_one<2, 256, 4, EPI_F32>(maps, p, num_sms, st);
+    if (epi == EPI_F32_RED) return launch_one<2, 256, 4, EPI_F32_RED>(maps, p, num_sms, st);
     if (epi == EPI_GELU_SPLIT) return launch_one<2, 256, 4, EPI_GELU_SPLIT>(maps, p, num_sms, st);
     if (epi == EPI_F32_EMIT) return launch_one<2, 256, 4, EPI_F32_EMIT>(maps, p, num_sms, st);
     if (epi == EPI_GELU_DLN) return launch_one<2, 256, 4, EPI_GELU_DLN>(maps, p, num_sms, st);
     return launch_one<2, 256, 4, EPI_QKV16>(maps, p, num_sms, st);
   }
-  if (epi == EPI_F32_EMIT || epi == EPI_GELU_DLN) return cudaErrorInvalidValue;     // FMT_F4C kernel only
+  if (epi == EPI_F32_EMIT || epi == EPI_GELU_DLN || epi == EPI_F32_RED) return cudaErrorInvalidValue;     // FMT_F4C kernel only
   if (cta_group == 2 || passes == 2) bn = 256;
   if (epi == EPI_F32_LN) {
     // needs: both 256-column halves of a row tile on the same CTA pair, back to back, in accumulators 0 and 1
@@ -1292,6 +1316,22 @@ int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_
   cuuint32_t box[2] = {128, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+int make_f32_tile_map(CUtensorMap* out, const float* base, int64_t rows, int N) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return -1;
+  EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(N) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;

@@ -28,7 +28,12 @@ constexpr int kHidden = 1024;  // mlp hidden
 // EPI_GELU_DLN   EPI_GELU_SPLIT whose A operand is that un-normalised x and whose weights were folded at load time
 //                (W' = gamma (.) W):  LN(x) . W^T + b = rstd_r (acc - mean_r s_n) + c_n  with  s_n = sum_k W'[n,k]
 //                (ln_colsum), c_n = b_n + sum_k W[n,k] beta_k (passed as `bias`), (mean_r, rstd_r) from ln_stats.
-enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_QKV16 = 2, EPI_F32_LN = 3, EPI_F32_EMIT = 4, EPI_GELU_DLN = 5 };
+// EPI_F32_RED    out_f32[M,N] += acc + bias: the in-place residual update of proj / fc2 (MODEL:127-128) as a TMA REDUCTION
+//                (cp.reduce.async.bulk.tensor .add.f32): the L2 adds the staged fp32 chunk to X, so the residual rows
+//                never travel L2 -> SM -- the link that bounds all four GEMMs.  Needs the `out` tensor map of GemmMaps
+//                ({32 floats x 32 rows} boxes over out_f32); same single fp32 rounding as (acc + bias) + x.
+enum GemmEpi { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_QKV16 = 2, EPI_F32_LN = 3, EPI_F32_EMIT = 4, EPI_GELU_DLN = 5,
+               EPI_F32_RED = 6 };
 
 constexpr int kQkvRow = 4 * kC;   // halves per token row of the packed q|k|v_hi|v_lo tensor
 
@@ -63,6 +68,7 @@ struct GemmMaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   CUtensorMap b_hi64, b_lo64;     // weight maps with 64-row boxes (multicast slices of the pair-cluster kernel)
   CUtensorMap a_sf, b_sf;         // FMT_F4C: scale-factor arrays (make_sf_map)
+  CUtensorMap out;                // EPI_F32_RED: fp32 [M, N] destination, {32 x 32} boxes, SWIZZLE_128B (make_f32_tile_map)
 };
 
 // passes: 3 (split fp16), 1 (fp16), 2 (FMT_F8C: fp16 main + e5m2 corrections; the *_lo maps are the uint8 c8 maps) or
@@ -85,6 +91,8 @@ cudaError_t configure_attention_mma();
 int make_operand_map(CUtensorMap* out, const __half* base, int64_t rows, int64_t K, int box_rows = 128);
 int make_operand_map_u8(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes, int box_rows = 128);
 int make_sf_map(CUtensorMap* out, const void* base, int64_t total_bytes);
+// fp32 [rows, N] row-major matrix, {32 floats x 32 rows} boxes, SWIZZLE_128B (the epilogue's staging-buffer layout)
+int make_f32_tile_map(CUtensorMap* out, const float* base, int64_t rows, int N);
 
 // ------------------------------------------------------------------ row-wise (one warp per 512-wide token row)
 struct LnParams {

@@ -118,14 +118,17 @@ F4C_SHAPES = [(128, 1536, 512), (200, 512, 512), (1000, 1024, 512), (459, 512, 1
               (74 * 256 * 3 + 77, 512, 512)]
 
 
-@pytest.mark.parametrize("mode", [_lib.GEMM_TC_F4C, _lib.GEMM_SIMT_F4C])
+@pytest.mark.parametrize("mode,red", [(_lib.GEMM_TC_F4C, 1), (_lib.GEMM_TC_F4C, 0), (_lib.GEMM_SIMT_F4C, 0)])
 @pytest.mark.parametrize("M,N,K", F4C_SHAPES)
-def test_linear_parity_f4c(eng27, mode, M, N, K):
-    """FMT_F4C (fp16 main product + block-scaled e2m1 correction products, kind::mxf4.block_scale) against fp64: the
+def test_linear_parity_f4c(eng27, monkeypatch, mode, red, M, N, K):
+    """red = 1 (shipped): the residual sits in the output and the epilogue reduce-adds acc + bias into it through the TMA
+    unit (EPI_F32_RED, cp.reduce.async.bulk.tensor .add.f32: the L2 performs the add); red = 0: the load-add-store epilogue.
+    FMT_F4C (fp16 main product + block-scaled e2m1 correction products, kind::mxf4.block_scale) against fp64: the
     tensor-core kernel and its CUDA-core twin.  The corrections carry ~2 significant bits of a 2^-11 term, so the bound
     is looser than F8C's 2e-4 and far below single-pass fp16's 2e-3.  Shapes: one tile, ragged M, K = 1024 (8 e2m1
     stages), a single row, the minimum K (one e2m1 stage), and more tiles than CTA pairs (persistent loop: the scale
     factors of tile q live in the accumulator of tile q - 1)."""
+    monkeypatch.setenv("D3D_GEMM_RED", str(red))
     a, w, b = _rand((M, K), 1), _rand((N, K), 2, 0.05), _rand((N,), 3, 0.1)
     res = _rand((M, N), 4)
     ref = (a.double() @ w.double().T + b.double() + res.double())
@@ -133,6 +136,19 @@ def test_linear_parity_f4c(eng27, mode, M, N, K):
     scale = (a.double().abs() @ w.double().abs().T).max().item()
     err = (out.double() - ref).abs().max().item() / scale
     assert err < 4e-4, f"relative error {err:.3e}"
+
+
+def test_reduction_epilogue_is_bit_equal_to_load_add_store(eng27, monkeypatch):
+    """(acc + bias) + x rounded once in fp32, whether the SM adds the residual it loaded or the L2 adds the chunk the TMA
+    unit hands it: the two epilogues must agree bit for bit (more row tiles than CTA pairs, ragged last tile)."""
+    M, N, K = 74 * 256 + 300, 512, 512
+    a, w, b = _rand((M, K), 61).cuda(), _rand((N, K), 62, 0.05).cuda(), _rand((N,), 63, 0.1).cuda()
+    res = _rand((M, N), 64, 2.0).cuda()
+    outs = []
+    for red in (1, 0):
+        monkeypatch.setenv("D3D_GEMM_RED", str(red))
+        outs.append(eng27.op_linear(a, w, b, residual=res, act=0, gemm_mode=_lib.GEMM_TC_F4C))
+    assert torch.equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize("M,N,K", F4C_SHAPES)
