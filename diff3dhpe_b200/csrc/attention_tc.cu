@@ -471,15 +471,15 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       // landed in the dead Q tile long ago; ncu had 15 % of the softmax warps' samples idle on o_full and another 10 % on
       // the shared-memory loads below when they sat inside the epilogue loop, profiles/r01p_full_attn_tc.md)
       ptx::mbar_wait(&bars->vlo_full[slot], i & 1);
-      uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // v_lo row in, hi row out (same thread, same 16 bytes)
-      const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
+      const uint32_t hi_row = ptx::smem_u32(Qs + m * kTile + row_l * 128);   // v_lo row in, hi row out (same thread, same 16 bytes)
+      const uint32_t v_row = ptx::smem_u32(Vs) + static_cast<uint32_t>(r) * 128;
       ptx::f32x2 nv[32];
       {
         uint4 vh[8], vl[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          vh[g] = *reinterpret_cast<const uint4*>(v_row + ((g << 4) ^ sw));
-          vl[g] = *reinterpret_cast<const uint4*>(hi_row + ((g << 4) ^ sw));
+          vh[g] = ptx::lds128(v_row + ((g << 4) ^ sw));
+          vl[g] = ptx::lds128(hi_row + ((g << 4) ^ sw));
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -531,9 +531,10 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             ra = __float_as_uint(x0);
             rb = __float_as_uint(x1);
           }
-          *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          ptx::sts128(hi_row + ((g << 4) ^ sw), make_uint4(hw[0], hw[1], hw[2], hw[3]));
         }
         const uint32_t bp0 = op_ue8m0_of(ax[0]), bp1 = op_ue8m0_of(ax[1]), bq0 = op_ue8m0_of(al[0]), bq1 = op_ue8m0_of(al[1]);
+        uint32_t pw[8], qw[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const ptx::f32x2 ip = ptx::splat2(op_ue8m0_inv(g < 4 ? bp0 : bp1)), iq = ptx::splat2(op_ue8m0_inv(g < 4 ? bq0 : bq1));
@@ -549,8 +550,14 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             pa |= op_e2m1x2(a0, a1) << (8 * e);
             qa |= op_e2m1x2(l0, l1) << (8 * e);
           }
-          *reinterpret_cast<uint32_t*>(Stg + row_l * 32 + g * 4) = pa;
-          *reinterpret_cast<uint32_t*>(Stg + 4096 + row_l * 32 + g * 4) = qa;
+          pw[g] = pa; qw[g] = qa;
+        }
+        {
+          const uint32_t st = ptx::smem_u32(Stg) + row_l * 32;         // [128 rows][32 B] P tile, then the Q tile
+          ptx::sts128(st, make_uint4(pw[0], pw[1], pw[2], pw[3]));
+          ptx::sts128(st + 16, make_uint4(pw[4], pw[5], pw[6], pw[7]));
+          ptx::sts128(st + 4096, make_uint4(qw[0], qw[1], qw[2], qw[3]));
+          ptx::sts128(st + 4096 + 16, make_uint4(qw[4], qw[5], qw[6], qw[7]));
         }
         // the row's four scale bytes: k-blocks (2h, 2h+1) of part P and (16 + 2h, 16 + 2h + 1) of part Q are adjacent
         // bytes of a scale-factor atom.  Rows the TMA stores clip (>= F, or past the unit) must not be written here.
@@ -590,7 +597,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             l8[e] = op_e5m2x2(l0, l1);
           }
         }
-        *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        ptx::sts128(hi_row + ((g << 4) ^ sw), make_uint4(hw[0], hw[1], hw[2], hw[3]));
         if (FMT == FMT_SPLIT16) {            // lo rows: 128 B, swizzled like hi
           *reinterpret_cast<uint4*>(Stg + row_l * 128 + ((g << 4) ^ sw)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         } else {                             // c8: [128 rows][64 B] e5m2(x 2^-8), then [128 rows][64 B] e5m2(lo 2^4)

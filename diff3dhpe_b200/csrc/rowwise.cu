@@ -129,7 +129,12 @@ __device__ __forceinline__ void layernorm_row(const float (&x)[16], const float*
   }
   ptx::unpack2(qp, s0, s1);
   const float var = warp_sum(s0 + s1) * (1.0f / kC);
-  const ptx::f32x2 rstd = ptx::splat2(1.0f / sqrtf(var + eps));
+  // 1 / sqrt(var + eps): MUFU.RSQ + one Newton step (< 1 ulp) -- the IEEE sqrt + division pair cost ~25 instructions with
+  // its slow-path calls in kernels whose issue slots set the in-step time
+  const float ve = var + eps;
+  float r0;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(ve));
+  const ptx::f32x2 rstd = ptx::splat2(r0 * fmaf(-0.5f * ve, r0 * r0, 1.5f));
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane));
@@ -174,7 +179,9 @@ lift_ln_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, cons
   load_row_ldg(spos + static_cast<size_t>(t32 % static_cast<uint32_t>(J)) * kC, lane, w);
   add16(v, w);
   if (tvec) {
-    load_row_ldg(tvec + static_cast<int64_t>(t32 / static_cast<uint32_t>(tokens_per_clip)) * tvec_stride, lane, w);
+    const float* tv = tvec;
+    if (tvec_stride != 0) tv += static_cast<int64_t>(t32 / static_cast<uint32_t>(tokens_per_clip)) * tvec_stride;
+    load_row_ldg(tv, lane, w);
     add16(v, w);
   }
   store_row(X + t * kC, lane, v);
@@ -198,8 +205,10 @@ postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __rest
     load_row_ldg(tpos + static_cast<size_t>((static_cast<uint32_t>(t) / static_cast<uint32_t>(J)) % static_cast<uint32_t>(F)) * kC, lane, w);
     add16(z, w);
   }
-  if (tvec) {
-    load_row_ldg(tvec + static_cast<int64_t>(static_cast<uint32_t>(t) / static_cast<uint32_t>(J * F)) * tvec_stride, lane, w);
+  if (tvec) {          // eval: every clip shares t (tvec_stride == 0), no clip index needed
+    const float* tv = tvec;
+    if (tvec_stride != 0) tv += static_cast<int64_t>(static_cast<uint32_t>(t) / static_cast<uint32_t>(J * F)) * tvec_stride;
+    load_row_ldg(tv, lane, w);
     add16(z, w);
   }
   store_row(X + t * kC, lane, z);
