@@ -471,15 +471,15 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       // landed in the dead Q tile long ago; ncu had 15 % of the softmax warps' samples idle on o_full and another 10 % on
       // the shared-memory loads below when they sat inside the epilogue loop, profiles/r01p_full_attn_tc.md)
       ptx::mbar_wait(&bars->vlo_full[slot], i & 1);
-      const uint32_t hi_row = ptx::smem_u32(Qs + m * kTile + row_l * 128);   // v_lo row in, hi row out (same thread, same 16 bytes)
-      const uint32_t v_row = ptx::smem_u32(Vs) + static_cast<uint32_t>(r) * 128;
+      uint8_t* hi_row = Qs + m * kTile + row_l * 128;        // v_lo row in, hi row out (same thread, same 16 bytes)
+      const uint8_t* v_row = Vs + static_cast<size_t>(r) * 128;
       ptx::f32x2 nv[32];
       {
         uint4 vh[8], vl[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          vh[g] = ptx::lds128(v_row + ((g << 4) ^ sw));
-          vl[g] = ptx::lds128(hi_row + ((g << 4) ^ sw));
+          vh[g] = *reinterpret_cast<const uint4*>(v_row + ((g << 4) ^ sw));
+          vl[g] = *reinterpret_cast<const uint4*>(hi_row + ((g << 4) ^ sw));
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -531,7 +531,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             ra = __float_as_uint(x0);
             rb = __float_as_uint(x1);
           }
-          ptx::sts128(hi_row + ((g << 4) ^ sw), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         }
         const uint32_t bp0 = op_ue8m0_of(ax[0]), bp1 = op_ue8m0_of(ax[1]), bq0 = op_ue8m0_of(al[0]), bq1 = op_ue8m0_of(al[1]);
         uint32_t pw[8], qw[8];
@@ -552,12 +552,12 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
           }
           pw[g] = pa; qw[g] = qa;
         }
-        {
-          const uint32_t st = ptx::smem_u32(Stg) + row_l * 32;         // [128 rows][32 B] P tile, then the Q tile
-          ptx::sts128(st, make_uint4(pw[0], pw[1], pw[2], pw[3]));
-          ptx::sts128(st + 16, make_uint4(pw[4], pw[5], pw[6], pw[7]));
-          ptx::sts128(st + 4096, make_uint4(qw[0], qw[1], qw[2], qw[3]));
-          ptx::sts128(st + 4096 + 16, make_uint4(qw[4], qw[5], qw[6], qw[7]));
+        {                                                              // [128 rows][32 B] P tile, then the Q tile
+          uint4* stp = reinterpret_cast<uint4*>(Stg + row_l * 32);
+          stp[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          stp[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+          stp[256] = make_uint4(qw[0], qw[1], qw[2], qw[3]);
+          stp[257] = make_uint4(qw[4], qw[5], qw[6], qw[7]);
         }
         // the row's four scale bytes: k-blocks (2h, 2h+1) of part P and (16 + 2h, 16 + 2h + 1) of part Q are adjacent
         // bytes of a scale-factor atom.  Rows the TMA stores clip (>= F, or past the unit) must not be written here.
@@ -597,7 +597,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             l8[e] = op_e5m2x2(l0, l1);
           }
         }
-        ptx::sts128(hi_row + ((g << 4) ^ sw), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        *reinterpret_cast<uint4*>(hi_row + ((g << 4) ^ sw)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         if (FMT == FMT_SPLIT16) {            // lo rows: 128 B, swizzled like hi
           *reinterpret_cast<uint4*>(Stg + row_l * 128 + ((g << 4) ^ sw)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         } else {                             // c8: [128 rows][64 B] e5m2(x 2^-8), then [128 rows][64 B] e5m2(lo 2^4)
@@ -621,6 +621,358 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
         ptx::bulk_commit();
         ptx::bulk_wait_read_all();           // Stg / Q_m have been read: the tile has left shared memory
+        ptx::mbar_arrive(&bars->stage_free[stage]);
+      }
+    }
+    if (issuer) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kSlotCols * NSLOT>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Temporal mode with TWO softmax warpgroups per slot (FMT_F4C, 64 < F <= 256; round 2).
+//
+// ncu on the kernel above at F = 243 (profiles/r02f_full_attn_temporal.md + source page): 11 000 warp-instructions per
+// 128 x 256 tile executed by FOUR warps (2750 each, strictly serial: max pass, exp2 pass, "- V", epilogue), 1.9 issued
+// instructions per cycle and SM with two warps per scheduler, MUFU 35 % busy, DRAM 49 %: the tile time is the length of
+// one thread's instruction stream, not a throughput limit.  Here a slot's 128 rows are owned by two warpgroups:
+//   half h (0 / 1) takes the 32-column chunks [c0_h, c1_h) of S (c_split = ceil(n / 2)) and, in the epilogue, the 32
+//   channels [32 h, 32 h + 32) of the row -- exactly one scale block of each part;
+//   * row maximum: partial maxima meet in shared memory (one named barrier of the slot's 256 threads);
+//   * P of chunk c is written at TMEM column  32 c0_h + 16 (c - c0_h): the start of the half's OWN S columns, so no half
+//     overwrites S columns the other one still reads (the single-warpgroup layout, P contiguous from column 0, would);
+//     the P.V chain takes its A operand from the two ranges;
+//   * O = P.V accumulates into columns [192, 256) (NKp > 128; S chunks 6, 7 are dead once both halves arrived on p_full)
+//     or [128, 192);
+//   * row sums meet in shared memory behind the barrier that already guards the staging buffer.
+// 640 threads: warps 0..15 softmax (warpgroup = slot * 2 + half, TMEM lane quadrant = warp & 3), 16 = TMA producer,
+// 17 = MMA issuer / TMEM allocator, 18..19 idle.  96 registers at launch; control warpgroup 40, softmax warpgroups 104.
+//
+// MEASURED (profiles/r02o_*, r02p_*): correct (the whole GPU suite passes on it) and 23 % SLOWER than the one-warpgroup
+// kernel at cfg3 (357 vs 290 ms of temporal attention per step), so it ships OFF (D3D_ATTN_WG2=1 selects it).  The two
+// halves of a row share the TMEM lane quadrant and with it the SM sub-partition's MUFU unit: the exp2 pass of a tile costs
+// 256 MUFU per row and sub-partition either way (2048 cycles), both halves reach it together behind the exchange barrier,
+// and what the split saves in the max pass and the epilogue is less than the third 256-thread barrier per tile, the TMEM
+// loads no longer issued a batch ahead (104 instead of 216 registers) and the spills cost.  What would help is MUFU
+// capacity, not threads: part of the exp2 on the FMA pipes.
+constexpr int kTc2Threads = 640;
+constexpr int kCtrlRegs2 = 40, kSoftmaxRegs2 = 104;
+static_assert(4 * 128 * (kSoftmaxRegs2 - 96) <= 128 * (96 - kCtrlRegs2), "setmaxnreg pool overdrawn");
+
+// P column (offset inside the slot) of chunk c
+__device__ __forceinline__ int p_col2(int c, int c_split) { return c < c_split ? c * 16 : 32 * c_split + (c - c_split) * 16; }
+
+template <int NCH>
+__global__ void __launch_bounds__(kTc2Threads, 1)
+attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
+                         const __grid_constant__ CUtensorMap tm_second, uint8_t* __restrict__ sf_out, int F, int J,
+                         int n_units, int n_mt, int NKp, int n_stage) {
+  constexpr int NSLOT = 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = 3 * n_mt * kTile;
+  uint8_t* StgAll = smem + n_stage * stage_bytes;    // per slot 16 KB: [0, 4 KB) P tile, [4, 8 KB) Q tile, [8 KB, ..) exchange
+  TcBars<NSLOT>* bars = reinterpret_cast<TcBars<NSLOT>*>(StgAll + NSLOT * kTile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kTmaWarp = 16, kMmaWarp = 17;
+  const int n_local = blockIdx.x < n_units ? (n_units - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+  const int W = n_local * n_mt;
+  const int n_chunks = (NKp + 31) >> 5;
+  const int c_split = (n_chunks + 1) >> 1;
+  const uint32_t o_col = NKp > 128 ? 192u : 128u;
+
+  if (warp == kTmaWarp && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tm_qkv);
+    ptx::prefetch_tensormap(&tm_hi);
+    ptx::prefetch_tensormap(&tm_second);
+    for (int s = 0; s < n_stage; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->stage_free[s], n_mt);
+    }
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      ptx::mbar_init(&bars->s_full[s], 1);
+      ptx::mbar_init(&bars->p_full[s], 256);
+      ptx::mbar_init(&bars->o_full[s], 1);
+      ptx::mbar_init(&bars->tmem_free[s], 256);
+      ptx::mbar_init(&bars->vlo_full[s], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == kMmaWarp) ptx::tmem_alloc<kSlotCols * NSLOT>(&bars->tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs2));
+    if (ptx::elect_one()) {
+      for (int n = 0; n < n_local; ++n) {
+        const int unit = blockIdx.x + n * gridDim.x;
+        const int seq = unit >> 3, h = unit & 7;
+        const int b = seq / J, j = seq - b * J;
+        const int stage = n % n_stage, k = n / n_stage;
+        uint8_t* Qs = smem + stage * stage_bytes;
+        uint8_t* Ks = Qs + n_mt * kTile;
+        uint8_t* Vs = Ks + n_mt * kTile;
+        ptx::mbar_wait(&bars->stage_free[stage], (k & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars->full[stage], 3 * n_mt * kTile);
+        for (int t = 0; t < n_mt; ++t) {
+          ptx::tma_load_4d(Ks + t * kTile, &tm_qkv, &bars->full[stage], kC + h * kHd, j, t * 128, b);
+          ptx::tma_load_4d(Qs + t * kTile, &tm_qkv, &bars->full[stage], h * kHd, j, t * 128, b);
+          ptx::tma_load_4d(Vs + t * kTile, &tm_qkv, &bars->full[stage], 2 * kC + h * kHd, j, t * 128, b);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs2));
+    if (ptx::elect_one()) {
+      const uint32_t idesc_qk = ptx::make_idesc_f16(128, static_cast<uint32_t>(NKp), 0);
+      const uint32_t idesc_pv = ptx::make_idesc_f16(128, kHd, 0) | (1u << 16);      // B (= V) is MN-major
+      const uint32_t s0 = ptx::smem_u32(smem);
+      const int n_ks = NKp >> 4;
+      auto issue_pv = [&](int w) {           // O[128, 64] = P[128, NKp] (TMEM, two column ranges) . V[NKp, 64], 16 keys per MMA
+        const int slot = w % NSLOT, i = w / NSLOT, stage = (w / n_mt) % n_stage;
+        const uint32_t sV = s0 + stage * stage_bytes + 2 * n_mt * kTile;
+        const uint32_t tcol = tmem_base + slot * kSlotCols;
+        ptx::mbar_wait(&bars->p_full[slot], i & 1);
+        ptx::tc_fence_after();
+        for (int ks = 0; ks < n_ks; ++ks)
+          ptx::mma_f16_ts(tcol + o_col, tcol + p_col2(ks >> 1, c_split) + (ks & 1) * 8, make_desc_mn_sw128(sV + ks * 2048),
+                          idesc_pv, ks != 0 ? 1u : 0u);
+        ptx::mma_commit(&bars->o_full[slot]);
+      };
+      for (int w = 0; w < W; ++w) {
+        const int n = w / n_mt, m = w - n * n_mt;
+        const int slot = w % NSLOT, i = w / NSLOT, stage = n % n_stage;
+        const uint32_t sQ = s0 + stage * stage_bytes, sK = sQ + n_mt * kTile;
+        if (m == 0) {
+          ptx::mbar_wait(&bars->full[stage], (n / n_stage) & 1);
+          ptx::tc_fence_after();
+        }
+        ptx::mbar_wait(&bars->tmem_free[slot], (i & 1) ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::mma_f16_ss(tmem_base + slot * kSlotCols, ptx::make_desc_k_sw128(sQ + m * kTile + k * 32),
+                          ptx::make_desc_k_sw128(sK + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+        ptx::mma_commit(&bars->s_full[slot]);
+        if (w >= NSLOT - 1) issue_pv(w - (NSLOT - 1));
+      }
+      for (int w = W - (NSLOT - 1); w < W; ++w)
+        if (w >= 0) issue_pv(w);
+    }
+  } else if (warp > kMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs2));
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue: thread = (query row, half)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSoftmaxRegs2));
+    const int wg = warp >> 2, slot = wg >> 1, half = wg & 1;
+    const int row_l = (warp & 3) * 32 + lane;
+    const uint32_t taddr = tmem_base + slot * kSlotCols + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    if (NCH > 0 && (n_chunks != NCH || F <= 32 * (NCH - 1))) __trap();
+    const int c0 = half ? c_split : 0, c1 = half ? n_chunks : c_split;       // this half's chunks of S
+    constexpr int kMaxHalf = NCH > 0 ? (NCH + 1) / 2 : 4;
+    const int sw = (row_l & 7) << 4;
+    const bool issuer = half == 0 && row_l == 0;
+    uint8_t* Stg = StgAll + slot * kTile;
+    float* xmax = reinterpret_cast<float*>(Stg + 8192);      // [2 halves][128 rows]
+    float* xsum = xmax + 256;
+    auto full = [&](int c) { return (c + 1) * 32 <= F; };
+    for (int w = slot; w < W; w += NSLOT) {
+      const int n = w / n_mt, m = w - n * n_mt;
+      const int i = w / NSLOT, stage = n % n_stage;
+      const int unit = blockIdx.x + n * gridDim.x;
+      const int seq = unit >> 3, h = unit & 7;
+      const int b = seq / J, j = seq - b * J;
+      uint8_t* Qs = smem + stage * stage_bytes;
+      const uint8_t* Vs = Qs + 2 * n_mt * kTile;
+      const int r = m * 128 + row_l;
+      ptx::mbar_wait(&bars->s_full[slot], i & 1);
+      ptx::tc_fence_after();
+      if (issuer) {      // Q_m is dead once S is complete: it receives the v_lo rows of the tile (exact "- V" term)
+        ptx::mbar_arrive_expect_tx(&bars->vlo_full[slot], kTile);
+        ptx::tma_load_4d(Qs + m * kTile, &tm_qkv, &bars->vlo_full[slot], 3 * kC + h * kHd, j, m * 128, b);
+      }
+      // ---- pass 1: maximum over this half's columns, then over the row
+      uint32_t a0[32], a1[32];
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      auto max_chunk = [&](const uint32_t (&rr)[32], int c) {
+        if (full(c)) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rr[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e < F) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rr[e]));
+        }
+      };
+#pragma unroll
+      for (int q = 0; q < kMaxHalf; q += 2) {
+        const int c = c0 + q;
+        if (c < c1) {
+          ptx::tmem_ld_32x32(taddr + c * 32, a0);
+          if (c + 1 < c1) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, a1);
+          ptx::tmem_ld_wait();
+          max_chunk(a0, c);
+          if (c + 1 < c1) max_chunk(a1, c + 1);
+        }
+      }
+      const float m_own = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      xmax[half * 128 + row_l] = m_own;
+      ptx::tmem_ld_32x32(taddr + c0 * 32, a0);                   // pass 2 streams in behind the exchange barrier
+      if (c0 + 1 < c1) ptx::tmem_ld_32x32(taddr + (c0 + 1) * 32, a1);
+      ptx::bar_sync(1 + slot, 256);
+      const float nmxs = -fmaxf(m_own, xmax[(half ^ 1) * 128 + row_l]) * kScaleLog2e;
+      // ---- pass 2: P = exp2(S c - m c) as packed fp16 at the start of this half's own S columns, partial row sum
+      ptx::f32x2 ls[2] = {ptx::splat2(0.f), ptx::splat2(0.f)};
+      const ptx::f32x2 sc2 = ptx::splat2(kScaleLog2e), nm2 = ptx::splat2(nmxs);
+      auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
+        uint32_t pk[16];
+        if (full(c)) {                         // warp-uniform: every chunk but the row's last one takes the unmasked form
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float t0, t1;
+            ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(rr[2 * e]), __uint_as_float(rr[2 * e + 1])), sc2, nm2), t0, t1);
+            const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+            ls[e & 1] = ptx::add2(ls[e & 1], ptx::pack2(e0, e1));
+            pk[e] = pack_f16x2(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float t0, t1;
+            ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(rr[2 * e]), __uint_as_float(rr[2 * e + 1])), sc2, nm2), t0, t1);
+            const int col = c * 32 + 2 * e;
+            const float e0 = col < F ? ex2_approx(t0) : 0.f;
+            const float e1 = col + 1 < F ? ex2_approx(t1) : 0.f;
+            ls[e & 1] = ptx::add2(ls[e & 1], ptx::pack2(e0, e1));
+            pk[e] = pack_f16x2(e0, e1);
+          }
+        }
+        ptx::tmem_st_32x16(taddr + 32 * c0 + (c - c0) * 16, pk);
+      };
+#pragma unroll
+      for (int q = 0; q < kMaxHalf; q += 2) {
+        const int c = c0 + q;
+        if (c < c1) {
+          if (q > 0) {
+            ptx::tmem_ld_32x32(taddr + c * 32, a0);
+            if (c + 1 < c1) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, a1);
+          }
+          ptx::tmem_ld_wait();
+          exp_chunk(a0, c);
+          if (c + 1 < c1) exp_chunk(a1, c + 1);
+        }
+      }
+      ptx::tmem_st_wait();
+      xsum[half * 128 + row_l] = row_sum(ls);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars->p_full[slot]);
+
+      // ---- while the P.V chain runs: this half's 32 channels of the exact "- V" term
+      ptx::mbar_wait(&bars->vlo_full[slot], i & 1);
+      const uint32_t hi_row = ptx::smem_u32(Qs + m * kTile + row_l * 128);   // v_lo row in, hi row out
+      const uint32_t v_row = ptx::smem_u32(Vs) + static_cast<uint32_t>(r) * 128;
+      ptx::f32x2 nv[16];
+      {
+        uint4 vh[4], vl[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          vh[g] = ptx::lds128(v_row + (((half * 4 + g) << 4) ^ sw));
+          vl[g] = ptx::lds128(hi_row + (((half * 4 + g) << 4) ^ sw));
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t vhw[4] = {vh[g].x, vh[g].y, vh[g].z, vh[g].w};
+          const uint32_t vlw[4] = {vl[g].x, vl[g].y, vl[g].z, vl[g].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vhw[e]));
+            const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&vlw[e]));
+            float s0, s1;
+            ptx::unpack2(ptx::add2(ptx::pack2(a.x, a.y), ptx::pack2(c.x, c.y)), s0, s1);
+            nv[4 * g + e] = ptx::pack2(-s0, -s1);
+          }
+        }
+      }
+      // ---- this half's 32 columns of O out of TMEM, then the slot is free for the next S
+      ptx::mbar_wait(&bars->o_full[slot], i & 1);
+      ptx::tc_fence_after();
+      uint32_t o0[32];
+      ptx::tmem_ld_32x32(taddr + o_col + half * 32, o0);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars->tmem_free[slot]);
+
+      // ---- epilogue: out = O / l - (v_hi + v_lo): one scale block of each part per half
+      ptx::bar_sync(1 + slot, 256);          // the previous tile's stores have read Stg; both partial row sums are visible
+      const ptx::f32x2 inv2 = ptx::splat2(rcp_approx(xsum[row_l] + xsum[128 + row_l]));
+      float ax = 0.f, al = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float x0, x1;
+          ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(o0[8 * g + 2 * e]), __uint_as_float(o0[8 * g + 2 * e + 1])), inv2,
+                                 nv[4 * g + e]), x0, x1);
+          const __half2 h01 = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h01);
+          hw[e] = *reinterpret_cast<const uint32_t*>(&h01);
+          ax = fmaxf(ax, fmaxf(fabsf(x0), fabsf(x1)));
+          al = fmaxf(al, fmaxf(fabsf(x0 - hf.x), fabsf(x1 - hf.y)));
+          o0[8 * g + 2 * e] = __float_as_uint(x0);
+          o0[8 * g + 2 * e + 1] = __float_as_uint(x1);
+        }
+        ptx::sts128(hi_row + (((half * 4 + g) << 4) ^ sw), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+      }
+      const uint32_t bp = op_ue8m0_of(ax), bq = op_ue8m0_of(al);
+      const ptx::f32x2 ip = ptx::splat2(op_ue8m0_inv(bp)), iq = ptx::splat2(op_ue8m0_inv(bq));
+      uint32_t pw[4], qw[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pa = 0, qa = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = __uint_as_float(o0[8 * g + 2 * e]), x1 = __uint_as_float(o0[8 * g + 2 * e + 1]);
+          const float2 hf = __half22float2(__floats2half2_rn(x0, x1));
+          float q0, q1, l0, l1;
+          ptx::unpack2(ptx::mul2(ptx::pack2(x0, x1), ip), q0, q1);
+          ptx::unpack2(ptx::mul2(ptx::sub2(ptx::pack2(x0, x1), ptx::pack2(hf.x, hf.y)), iq), l0, l1);
+          pa |= op_e2m1x2(q0, q1) << (8 * e);
+          qa |= op_e2m1x2(l0, l1) << (8 * e);
+        }
+        pw[g] = pa; qw[g] = qa;
+      }
+      {
+        const uint32_t st = ptx::smem_u32(Stg) + row_l * 32 + half * 16;     // [128 rows][32 B] P tile, then the Q tile
+        ptx::sts128(st, make_uint4(pw[0], pw[1], pw[2], pw[3]));
+        ptx::sts128(st + 4096, make_uint4(qw[0], qw[1], qw[2], qw[3]));
+      }
+      if (r < F) {       // rows the TMA stores clip must not leave scale bytes either
+        const int64_t tok = (static_cast<int64_t>(b) * F + r) * J + j;
+        sf_out[op_sf_offset(tok, 2 * h + half, kC / 64)] = static_cast<uint8_t>(bp);
+        sf_out[op_sf_offset(tok, 16 + 2 * h + half, kC / 64)] = static_cast<uint8_t>(bq);
+      }
+      ptx::fence_proxy_async();
+      ptx::bar_sync(1 + slot, 256);          // every row is staged, and nobody still reads v_hi rows of this tile
+      if (issuer) {
+        ptx::tma_store_4d(&tm_hi, Qs + m * kTile, h * kHd, j, m * 128, b);
+        ptx::tma_store_4d(&tm_second, Stg, h * 32, j, m * 128, b);
+        ptx::tma_store_4d(&tm_second, Stg + 4096, (kC >> 1) + h * 32, j, m * 128, b);
+        ptx::bulk_commit();
+        ptx::bulk_wait_read_all();
         ptx::mbar_arrive(&bars->stage_free[stage]);
       }
     }
@@ -749,6 +1101,8 @@ cudaError_t configure_attention_tc() {
   D3D_CFG_TC(FMT_SPLIT16, 0, true) D3D_CFG_TC(FMT_F8C, 0, true)
   D3D_CFG_TC(FMT_F4C, 0, false) D3D_CFG_TC(FMT_F4C, 3, false) D3D_CFG_TC(FMT_F4C, 8, false) D3D_CFG_TC(FMT_F4C, 0, true)
 #undef D3D_CFG_TC
+  for (auto kern : {attn_temporal_tc2_kernel<8>, attn_temporal_tc2_kernel<3>, attn_temporal_tc2_kernel<0>})
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<2>(2))) != cudaSuccess) return e;
 #define D3D_CFG_PK(FMT_)                                                                                                     \
   if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_, 2, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 tc_smem_bytes<2>(1))) != cudaSuccess)                                                        \
@@ -759,7 +1113,7 @@ cudaError_t configure_attention_tc() {
 }
 
 cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, uint8_t* o_sf, int fmt, int B, int F, int J,
-                                    int num_sms, cudaStream_t st) {
+                                    int num_sms, cudaStream_t st, int wg2) {
   if (B <= 0) return cudaSuccess;
   if (F < 1 || F > 256) return cudaErrorInvalidValue;
   if (fmt == FMT_F4C && !o_sf) return cudaErrorInvalidValue;
@@ -790,7 +1144,15 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, u
 #define D3D_LAUNCH_TC(FMT_, NCH_)                                                                               \
   attn_temporal_tc_kernel<FMT_, 2, NCH_, false><<<grid, kTcThreads, smem, st>>>(                      \
       maps.qkv, maps.o_hi, maps.o_second, maps.o_hi, maps.o_second, o_sf, F, J, n_units, n_mt, NKp, tc_stages(n_mt))
-  if (fmt == FMT_F4C) {
+  if (fmt == FMT_F4C && wg2) {
+    // two softmax warpgroups per slot (D3D_ATTN_WG2=0: the one-warpgroup kernel)
+    if (!o_sf) return cudaErrorInvalidValue;
+#define D3D_LAUNCH_TC2(NCH_)                                                       \
+  attn_temporal_tc2_kernel<NCH_><<<grid, kTc2Threads, smem, st>>>(maps.qkv, maps.o_hi, maps.o_second, o_sf, F, J, n_units, \
+                                                                   n_mt, NKp, tc_stages(n_mt))
+    if (nch == 8) D3D_LAUNCH_TC2(8); else if (nch == 3) D3D_LAUNCH_TC2(3); else D3D_LAUNCH_TC2(0);
+#undef D3D_LAUNCH_TC2
+  } else if (fmt == FMT_F4C) {
     if (!o_sf) return cudaErrorInvalidValue;
     if (nch == 8) D3D_LAUNCH_TC(FMT_F4C, 8); else if (nch == 3) D3D_LAUNCH_TC(FMT_F4C, 3); else D3D_LAUNCH_TC(FMT_F4C, 0);
   } else if (fmt == FMT_F8C) {

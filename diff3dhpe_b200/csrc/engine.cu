@@ -380,7 +380,8 @@ int run_attention(d3d_handle* h, const __half* qkv, __half* o_hi, __half* o_lo, 
       // the tcgen05 kernel's tensor maps are bound to QKV -> ATT; an fp32 result (op-level entry point) is merged
       // from the operand pair afterwards
       if (!o_f32 && (o_hi != h->ATT.hi || o_lo != h->ATT.lo)) return fail(h, -2, "attention output must be the ATT operand");
-      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_tc(h->attn_tc, qkv, h->ATT.sf, h->fmt, B, h->F, h->J, h->num_sms, st));
+      KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_tc(h->attn_tc, qkv, h->ATT.sf, h->fmt, B, h->F, h->J, h->num_sms, st,
+                                                              env_int("D3D_ATTN_WG2", 0)));
       if (o_f32) KL(launch_merge(h->ATT.hi, h->ATT.lo, h->ATT.sf, o_f32, static_cast<int64_t>(B) * h->F * h->J, kC, h->fmt, st));
     } else {
       KLP(D3D_PROF_ATTN_TEMPORAL, st, launch_attn_temporal_mma(qkv, o_hi, o_lo, o_f32, h->fmt, B, h->F, h->J, st));

@@ -181,8 +181,9 @@ int make_attn_tc_maps_spatial(AttnTcMaps* maps, const __half* qkv, __half* o_hi,
 // o_sf: scale-factor array of the output operand (FMT_F4C; null otherwise)
 cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, uint8_t* o_sf, int fmt, int B, int F, int num_sms, cudaStream_t st);
 cudaError_t configure_attention_tc();
+// wg2 != 0 (FMT_F4C, F > 64): two softmax warpgroups per 128-query slot (attn_temporal_tc2_kernel)
 cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, uint8_t* o_sf, int fmt, int B, int F, int J,
-                                    int num_sms, cudaStream_t st);
+                                    int num_sms, cudaStream_t st, int wg2 = 0);
 // CUDA-core validation kernels (fp32 arithmetic on the same packed input)
 cudaError_t launch_attn_temporal_simt(const __half* qkv, __half* o_hi, __half* o_lo, float* o_f32, int fmt, int B, int F,
                                       int J, cudaStream_t st);

@@ -7,6 +7,7 @@
 //   head_ddim          G-head+ddim : Temporal_norm + head LayerNorm(1e-5) + Linear(512->3) + clamp + DDIM update
 //                                                                                  (MODEL:245,255; DIFF:256,283-297)
 //   tta_merge, mpjpe   G-tta  : RUN:583-588, LOSS:15-27
+#include <cstdlib>
 #include "kernels.cuh"
 #include "operand.cuh"
 #include "ptx.cuh"
@@ -110,9 +111,29 @@ __device__ __forceinline__ void store_operand(__half* __restrict__ hi, __half* _
 // y = (x - mean) * rstd * gamma + beta over 512 columns held by the warp (two-pass variance in registers).  The
 // element-wise work runs on packed fp32 pairs (FADD2 / FFMA2 / FMUL2: two IEEE-rn operations per issue slot): with the
 // block-scaled operand format these kernels are bound by instruction issue, not by HBM.
+__device__ __forceinline__ float ln_center(const float (&x)[16], ptx::f32x2 (&xp)[8]);
+__device__ __forceinline__ ptx::f32x2 ln_rstd(float var, float eps);
 __device__ __forceinline__ void layernorm_row(const float (&x)[16], const float* __restrict__ gamma,
                                               const float* __restrict__ beta, float eps, int lane, float (&y)[16]) {
   ptx::f32x2 xp[8];
+  const float var = ln_center(x, xp);
+  // 1 / sqrt(var + eps): MUFU.RSQ + one Newton step (< 1 ulp) -- the IEEE sqrt + division pair cost ~25 instructions with
+  // its slow-path calls (ln_rstd)
+  const ptx::f32x2 rstd = ln_rstd(var, eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + 128 * i + 4 * lane));
+    ptx::unpack2(ptx::fma2(ptx::mul2(xp[2 * i], rstd), ptx::pack2(g.x, g.y), ptx::pack2(b.x, b.y)), y[4 * i], y[4 * i + 1]);
+    ptx::unpack2(ptx::fma2(ptx::mul2(xp[2 * i + 1], rstd), ptx::pack2(g.z, g.w), ptx::pack2(b.z, b.w)), y[4 * i + 2], y[4 * i + 3]);
+  }
+}
+
+// The same LayerNorm on TWO rows of one warp (rows t, t + 1), every parameter vector loaded ONCE for both.  ncu on the
+// one-row kernels (profiles/r02n_full_*.md, r02f_full_postnorm_add_ln.md): l1tex throughput 77-95 % -- each row re-read
+// 2 KB per parameter vector through L1 (24 of postnorm's 36 memory instructions), and at the step's power-capped clock
+// that, not HBM, set their time.  Per-row arithmetic is identical to layernorm_row (results do not depend on the partner).
+__device__ __forceinline__ float ln_center(const float (&x)[16], ptx::f32x2 (&xp)[8]) {      // xp = x - mean; returns var
 #pragma unroll
   for (int i = 0; i < 8; ++i) xp[i] = ptx::pack2(x[2 * i], x[2 * i + 1]);
   ptx::f32x2 sp = ptx::add2(ptx::add2(ptx::add2(xp[0], xp[1]), ptx::add2(xp[2], xp[3])),
@@ -128,19 +149,38 @@ __device__ __forceinline__ void layernorm_row(const float (&x)[16], const float*
     qp = ptx::fma2(xp[i], xp[i], qp);
   }
   ptx::unpack2(qp, s0, s1);
-  const float var = warp_sum(s0 + s1) * (1.0f / kC);
-  // 1 / sqrt(var + eps): MUFU.RSQ + one Newton step (< 1 ulp) -- the IEEE sqrt + division pair cost ~25 instructions with
-  // its slow-path calls in kernels whose issue slots set the in-step time
+  return warp_sum(s0 + s1) * (1.0f / kC);
+}
+__device__ __forceinline__ ptx::f32x2 ln_rstd(float var, float eps) {
   const float ve = var + eps;
   float r0;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(ve));
-  const ptx::f32x2 rstd = ptx::splat2(r0 * fmaf(-0.5f * ve, r0 * r0, 1.5f));
+  return ptx::splat2(r0 * fmaf(-0.5f * ve, r0 * r0, 1.5f));
+}
+// y_r = LN(x_r) (+ add) for r = 0, 1; `add` (optional, a 512-vector common to both rows) is added after beta
+__device__ __forceinline__ void layernorm_2rows(const float (&x0)[16], const float (&x1)[16], const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, const float* __restrict__ add, float eps,
+                                                int lane, float (&y0)[16], float (&y1)[16]) {
+  ptx::f32x2 p0[8], p1[8];
+  const float v0 = ln_center(x0, p0), v1 = ln_center(x1, p1);
+  const ptx::f32x2 r0 = ln_rstd(v0, eps), r1 = ln_rstd(v1, eps);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane));
     const float4 b = __ldg(reinterpret_cast<const float4*>(beta + 128 * i + 4 * lane));
-    ptx::unpack2(ptx::fma2(ptx::mul2(xp[2 * i], rstd), ptx::pack2(g.x, g.y), ptx::pack2(b.x, b.y)), y[4 * i], y[4 * i + 1]);
-    ptx::unpack2(ptx::fma2(ptx::mul2(xp[2 * i + 1], rstd), ptx::pack2(g.z, g.w), ptx::pack2(b.z, b.w)), y[4 * i + 2], y[4 * i + 3]);
+    const ptx::f32x2 g01 = ptx::pack2(g.x, g.y), g23 = ptx::pack2(g.z, g.w), b01 = ptx::pack2(b.x, b.y), b23 = ptx::pack2(b.z, b.w);
+    ptx::f32x2 a0 = ptx::fma2(ptx::mul2(p0[2 * i], r0), g01, b01), a1 = ptx::fma2(ptx::mul2(p0[2 * i + 1], r0), g23, b23);
+    ptx::f32x2 c0 = ptx::fma2(ptx::mul2(p1[2 * i], r1), g01, b01), c1 = ptx::fma2(ptx::mul2(p1[2 * i + 1], r1), g23, b23);
+    if (add) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(add + 128 * i + 4 * lane));
+      const ptx::f32x2 w01 = ptx::pack2(w.x, w.y), w23 = ptx::pack2(w.z, w.w);
+      a0 = ptx::add2(a0, w01); a1 = ptx::add2(a1, w23);
+      c0 = ptx::add2(c0, w01); c1 = ptx::add2(c1, w23);
+    }
+    ptx::unpack2(a0, y0[4 * i], y0[4 * i + 1]);
+    ptx::unpack2(a1, y0[4 * i + 2], y0[4 * i + 3]);
+    ptx::unpack2(c0, y1[4 * i], y1[4 * i + 1]);
+    ptx::unpack2(c1, y1[4 * i + 2], y1[4 * i + 3]);
   }
 }
 
@@ -190,6 +230,60 @@ lift_ln_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, cons
   store_operand<FMT>(a_hi, a_lo, a_sf, t, lane, a);
 }
 
+// lift_ln on two rows per warp: the five fusion_layer weight rows, its bias, the time vector and the norm1 parameters are
+// loaded once for both tokens (only the Spatial_pos_embed row differs); eval only (one time vector for every clip).
+template <int FMT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+lift_ln2_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, const float* __restrict__ x5,
+                const float* __restrict__ wf_t, const float* __restrict__ bf, const float* __restrict__ spos,
+                const float* __restrict__ tvec, LnParams ln1, float* __restrict__ X, __half* __restrict__ a_hi,
+                __half* __restrict__ a_lo, uint8_t* __restrict__ a_sf, int64_t T, int J) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5)) * 2;
+  if (t >= T) return;
+  const bool two = t + 1 < T;
+  const int64_t t1 = two ? t + 1 : t;
+  float in0[5], in1[5];
+  if (x5) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { in0[k] = __ldg(x5 + t * 5 + k); in1[k] = __ldg(x5 + t1 * 5 + k); }
+  } else {
+    in0[0] = __ldg(x2d + t * 2); in0[1] = __ldg(x2d + t * 2 + 1);
+    in0[2] = __ldg(y3 + t * 3); in0[3] = __ldg(y3 + t * 3 + 1); in0[4] = __ldg(y3 + t * 3 + 2);
+    in1[0] = __ldg(x2d + t1 * 2); in1[1] = __ldg(x2d + t1 * 2 + 1);
+    in1[2] = __ldg(y3 + t1 * 3); in1[3] = __ldg(y3 + t1 * 3 + 1); in1[4] = __ldg(y3 + t1 * 3 + 2);
+  }
+  float v0[16], v1[16], w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    load_row_ldg(wf_t + k * kC, lane, w);
+    fma16(v0, in0[k], w);
+    fma16(v1, in1[k], w);
+  }
+  load_row_ldg(bf, lane, w);
+  add16(v0, w);
+  add16(v1, w);
+  const uint32_t j0 = static_cast<uint32_t>(t) % static_cast<uint32_t>(J);
+  const uint32_t j1 = j0 + 1 == static_cast<uint32_t>(J) ? 0u : j0 + 1;
+  load_row_ldg(spos + static_cast<size_t>(j0) * kC, lane, w);
+  add16(v0, w);
+  load_row_ldg(spos + static_cast<size_t>(j1) * kC, lane, w);
+  add16(v1, w);
+  if (tvec) {
+    load_row_ldg(tvec, lane, w);
+    add16(v0, w);
+    add16(v1, w);
+  }
+  store_row(X + t * kC, lane, v0);
+  if (two) store_row(X + (t + 1) * kC, lane, v1);
+  float a0[16], a1[16];
+  layernorm_2rows(v0, v1, ln1.gamma, ln1.beta, nullptr, 1e-6f, lane, a0, a1);
+  store_operand<FMT>(a_hi, a_lo, a_sf, t, lane, a0);
+  if (two) store_operand<FMT>(a_hi, a_lo, a_sf, t + 1, lane, a1);
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 postnorm_add_ln_kernel(float* __restrict__ X, LnParams post, const float* __restrict__ tpos,
@@ -227,6 +321,43 @@ ln_split_kernel(const float* __restrict__ X, LnParams ln, float eps, __half* __r
   load_row(X + t * kC, lane, x);
   layernorm_row(x, ln.gamma, ln.beta, eps, lane, y);
   store_operand<FMT>(a_hi, a_lo, a_sf, t, lane, y);
+}
+
+// Two rows per warp (rows 2 w, 2 w + 1 of the launch): the production forms of ln_split / postnorm_add_ln when no
+// per-row additive term is needed (eval: one time vector for every clip; Temporal_pos_embed only after block 0).
+template <int FMT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ln_split2_kernel(const float* __restrict__ X, LnParams ln, float eps, __half* __restrict__ a_hi, __half* __restrict__ a_lo,
+                 uint8_t* __restrict__ a_sf, int64_t T) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5)) * 2;
+  if (t >= T) return;
+  const bool two = t + 1 < T;
+  float x0[16], x1[16], y0[16], y1[16];
+  load_row(X + t * kC, lane, x0);
+  load_row(X + (two ? t + 1 : t) * kC, lane, x1);
+  layernorm_2rows(x0, x1, ln.gamma, ln.beta, nullptr, eps, lane, y0, y1);
+  store_operand<FMT>(a_hi, a_lo, a_sf, t, lane, y0);
+  if (two) store_operand<FMT>(a_hi, a_lo, a_sf, t + 1, lane, y1);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+postnorm_add_ln2_kernel(float* __restrict__ X, LnParams post, const float* __restrict__ tvec, LnParams ln1,
+                        __half* __restrict__ a_hi, __half* __restrict__ a_lo, uint8_t* __restrict__ a_sf, int64_t T) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5)) * 2;
+  if (t >= T) return;
+  const bool two = t + 1 < T;
+  float x0[16], x1[16], z0[16], z1[16];
+  load_row(X + t * kC, lane, x0);
+  load_row(X + (two ? t + 1 : t) * kC, lane, x1);
+  layernorm_2rows(x0, x1, post.gamma, post.beta, tvec, 1e-6f, lane, z0, z1);
+  store_row(X + t * kC, lane, z0);
+  if (two) store_row(X + (t + 1) * kC, lane, z1);
+  layernorm_2rows(z0, z1, ln1.gamma, ln1.beta, nullptr, 1e-6f, lane, x0, x1);
+  store_operand<FMT>(a_hi, a_lo, a_sf, t, lane, x0);
+  if (two) store_operand<FMT>(a_hi, a_lo, a_sf, t + 1, lane, x1);
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -283,6 +414,64 @@ head_ddim_kernel(const float* __restrict__ X, LnParams post, LnParams head_ln, c
     if (trace_y) trace_y[e * trace_stride + trace_idx] = yn;
     if (trace_x0) trace_x0[e * trace_stride + trace_idx] = x0;
   }
+}
+
+// head_ddim on two rows per warp (the two LayerNorms' parameters and the three head weight rows loaded once for both)
+__device__ __forceinline__ void head_finish(float o0, float o1, float o2, int lane, int64_t t, const DdimStep& s,
+                                            float* __restrict__ y, const float* __restrict__ noise, float* __restrict__ out3,
+                                            float* __restrict__ trace_y, float* __restrict__ trace_x0, int trace_stride,
+                                            int trace_idx) {
+  if (lane < 3) {
+    float x0 = lane == 0 ? o0 : (lane == 1 ? o1 : o2);
+    const int64_t e = t * 3 + lane;
+    if (out3) {                     // forward_denoise: raw head output (MODEL:255-257)
+      out3[e] = x0;
+      return;
+    }
+    if (s.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);          // DIFF:252,256
+    float yn;
+    if (s.last) {
+      yn = x0;                                               // DIFF:283-285
+    } else {
+      // literal DIFF:295-297, one rounding per torch op (no FMA contraction)
+      const float t1 = __fmul_rn(x0, s.sqrt_alpha_next);
+      const float t2 = __fdiv_rn(__fsub_rn(y[e], __fmul_rn(s.alpha, x0)), s.sqrt_one_minus);
+      yn = __fadd_rn(t1, __fmul_rn(s.c, t2));
+      if (noise) yn = __fadd_rn(yn, __fmul_rn(s.sigma, noise[e]));
+    }
+    y[e] = yn;
+    if (trace_y) trace_y[e * trace_stride + trace_idx] = yn;
+    if (trace_x0) trace_x0[e * trace_stride + trace_idx] = x0;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+head_ddim2_kernel(const float* __restrict__ X, LnParams post, LnParams head_ln, const float* __restrict__ wh,
+                  const float* __restrict__ bh, DdimStep s, float* __restrict__ y, const float* __restrict__ noise,
+                  float* __restrict__ out3, float* __restrict__ trace_y, float* __restrict__ trace_x0,
+                  int trace_stride, int trace_idx, int64_t T) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5)) * 2;
+  if (t >= T) return;
+  const bool two = t + 1 < T;
+  float x0[16], x1[16], z0[16], z1[16], w[16];
+  load_row(X + t * kC, lane, x0);
+  load_row(X + (two ? t + 1 : t) * kC, lane, x1);
+  layernorm_2rows(x0, x1, post.gamma, post.beta, nullptr, 1e-6f, lane, z0, z1);
+  layernorm_2rows(z0, z1, head_ln.gamma, head_ln.beta, nullptr, 1e-5f, lane, x0, x1);
+  float o0[3], o1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    load_row_ldg(wh + k * kC, lane, w);
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { d0 = fmaf(x0[i], w[i], d0); d1 = fmaf(x1[i], w[i], d1); }
+    const float bk = __ldg(bh + k);
+    o0[k] = warp_sum(d0) + bk;
+    o1[k] = warp_sum(d1) + bk;
+  }
+  head_finish(o0[0], o0[1], o0[2], lane, t, s, y, noise, out3, trace_y, trace_x0, trace_stride, trace_idx);
+  if (two) head_finish(o1[0], o1[1], o1[2], lane, t + 1, s, y, noise, out3, trace_y, trace_x0, trace_stride, trace_idx);
 }
 
 __global__ void tta_merge_kernel(const float* __restrict__ y, const float* __restrict__ yf,
@@ -461,6 +650,11 @@ __global__ void merge_kernel(const __half* __restrict__ hi, const __half* __rest
   }
 }
 
+// D3D_LN_ROWS = 1: the one-row-per-warp forms of ln_split / postnorm_add_ln (A/B; read when the launch sequence is built)
+inline int rows_per_warp() {
+  const char* v = getenv("D3D_LN_ROWS");
+  return (v && *v == '1') ? 1 : 2;
+}
 inline unsigned row_grid(int64_t T) { return static_cast<unsigned>((T + kWarpsPerCta - 1) / kWarpsPerCta); }
 inline unsigned flat_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
@@ -502,6 +696,11 @@ cudaError_t launch_lift_ln(const float* x2d, const float* y, const float* x5, co
                            cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
   if (T > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if ((!tvec || tvec_stride == 0) && rows_per_warp() == 2) {
+    auto k2 = fmt == FMT_F4C ? lift_ln2_kernel<FMT_F4C> : fmt == FMT_F8C ? lift_ln2_kernel<FMT_F8C> : lift_ln2_kernel<FMT_SPLIT16>;
+    k2<<<row_grid((T + 1) / 2), kWarpsPerCta * 32, 0, st>>>(x2d, y, x5, wf_t, bf, spos, tvec, ln1, X, a_hi, a_lo, a_sf, T, J);
+    return cudaGetLastError();
+  }
   auto kern = fmt == FMT_F4C ? lift_ln_kernel<FMT_F4C> : fmt == FMT_F8C ? lift_ln_kernel<FMT_F8C> : lift_ln_kernel<FMT_SPLIT16>;
   kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(x2d, y, x5, wf_t, bf, spos, tvec, tvec_stride, ln1, X, a_hi, a_lo, a_sf, T,
                                                  J, tokens_per_clip);
@@ -512,6 +711,12 @@ cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos, c
                                    int64_t T, int J, int F, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
   if (T > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if (!tpos && (!tvec || tvec_stride == 0) && rows_per_warp() == 2) {       // eval: no per-row additive term
+    auto k2 = fmt == FMT_F4C ? postnorm_add_ln2_kernel<FMT_F4C>
+            : fmt == FMT_F8C ? postnorm_add_ln2_kernel<FMT_F8C> : postnorm_add_ln2_kernel<FMT_SPLIT16>;
+    k2<<<row_grid((T + 1) / 2), kWarpsPerCta * 32, 0, st>>>(X, post, tvec, ln1, a_hi, a_lo, a_sf, T);
+    return cudaGetLastError();
+  }
   auto kern = fmt == FMT_F4C ? postnorm_add_ln_kernel<FMT_F4C>
             : fmt == FMT_F8C ? postnorm_add_ln_kernel<FMT_F8C> : postnorm_add_ln_kernel<FMT_SPLIT16>;
   kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, tpos, tvec, tvec_stride, ln1, a_hi, a_lo, a_sf, T, J, F);
@@ -520,6 +725,11 @@ cudaError_t launch_postnorm_add_ln(float* X, LnParams post, const float* tpos, c
 cudaError_t launch_ln_split(const float* X, LnParams ln, float eps, __half* a_hi, __half* a_lo, uint8_t* a_sf, int fmt,
                             int64_t T, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
+  if (rows_per_warp() == 2) {
+    auto k2 = fmt == FMT_F4C ? ln_split2_kernel<FMT_F4C> : fmt == FMT_F8C ? ln_split2_kernel<FMT_F8C> : ln_split2_kernel<FMT_SPLIT16>;
+    k2<<<row_grid((T + 1) / 2), kWarpsPerCta * 32, 0, st>>>(X, ln, eps, a_hi, a_lo, a_sf, T);
+    return cudaGetLastError();
+  }
   auto kern = fmt == FMT_F4C ? ln_split_kernel<FMT_F4C> : fmt == FMT_F8C ? ln_split_kernel<FMT_F8C> : ln_split_kernel<FMT_SPLIT16>;
   kern<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, ln, eps, a_hi, a_lo, a_sf, T);
   return cudaGetLastError();
@@ -533,8 +743,12 @@ cudaError_t launch_head_ddim(const float* X, LnParams post, LnParams head_ln, co
                              DdimStep s, float* y, const float* noise, float* out3, float* trace_y, float* trace_x0,
                              int trace_stride, int trace_idx, int64_t T, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
-  head_ddim_kernel<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, head_ln, wh, bh, s, y, noise, out3, trace_y,
-                                                             trace_x0, trace_stride, trace_idx, T);
+  if (rows_per_warp() == 2)
+    head_ddim2_kernel<<<row_grid((T + 1) / 2), kWarpsPerCta * 32, 0, st>>>(X, post, head_ln, wh, bh, s, y, noise, out3, trace_y,
+                                                                          trace_x0, trace_stride, trace_idx, T);
+  else
+    head_ddim_kernel<<<row_grid(T), kWarpsPerCta * 32, 0, st>>>(X, post, head_ln, wh, bh, s, y, noise, out3, trace_y,
+                                                               trace_x0, trace_stride, trace_idx, T);
   return cudaGetLastError();
 }
 cudaError_t launch_tta_merge(const float* y, const float* yf, const int32_t* perm, float scale, float* out,

@@ -204,6 +204,24 @@ def test_deferred_norm2_pair(eng27, monkeypatch, M, ew_emit, ew_gelu):
     assert (hid.cpu().double() - h_ref).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("F", [81, 100, 243, 256, 65, 129])
+def test_attention_two_warpgroups_per_slot(monkeypatch, F):
+    """attn_temporal_tc2_kernel (D3D_ATTN_WG2=1; measured slower, ships off): a row's columns and channels split over two
+    warpgroups, P in two TMEM column ranges, row maximum / sum exchanged through shared memory.  Same reference and
+    tolerance as test_attention_core; F covers 3 chunks (2 + 1 split), 4, 8, the full 256 and the smallest sizes of the
+    one- and two-tile paths."""
+    monkeypatch.setenv("D3D_ATTN_WG2", "1")
+    B, J, C = 2, 17, 512
+    eng = Engine(F, max_clips=B)
+    qkv = _rand((B * F * J, 3 * C), 20 + F, 1.5)
+    qkv[:, :2 * C] = qkv[:, :2 * C].half().float()
+    x = qkv.view(B, F, J, 3 * C)
+    ref = oracle.attention_core(x.permute(0, 2, 1, 3).reshape(B * J, F, 3 * C), 8).reshape(B, J, F, C).permute(0, 2, 1, 3)
+    out = eng.op_attention(qkv.cuda(), B, False, _lib.ATTN_DEFAULT).cpu().view(B, F, J, C)
+    eng.close()
+    assert (out - ref).abs().max().item() < 4e-3
+
+
 def test_tc_matches_simt_elementwise(eng27):
     """Same split operands in, so tensor-core and CUDA-core results differ only by accumulation order and the
     dropped lo*lo term (2^-22 relative)."""
