@@ -333,12 +333,17 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
     if (epi == EPI_F32_RED) m.out = *out_map;
     const int passes = mode == D3D_GEMM_TC_FP16 ? 1 : (mode == D3D_GEMM_TC_F8C ? 2 : (mode == D3D_GEMM_TC_F4C ? 4 : 3));
     // epilogue warps per CTA: 16 pays where the epilogue, not the mainloop, sets the tile time
+    // GELU epilogue: 16 warps.  After the epilogue diet 8 warps (one more ring stage) are 2 % faster on the isolated fc1
+    // launch (r02r) but 1 % slower in the step (r02s: GEMM class 2157 vs 2139 ms on one box)
     const int ew = (epi == EPI_GELU_SPLIT || epi == EPI_GELU_DLN) ? env_int("D3D_GEMM_EW_GELU", 16)
                  : epi == EPI_QKV16    ? env_int("D3D_GEMM_EW_QKV", 8)
                  : epi == EPI_F32_EMIT ? env_int("D3D_GEMM_EW_EMIT", 8)
                  : epi == EPI_F32_RED  ? 8
                                         : env_int("D3D_GEMM_EW_F32", 8);
-    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), pick_cs(M), ew, h->num_sms, st));
+    // D3D_GEMM_SMS: run the persistent GEMM on fewer SMs (diagnostic: is the operand feed limited per SM or chip-wide?)
+    const int sms = env_int("D3D_GEMM_SMS", h->num_sms);
+    KLP(D3D_PROF_GEMM, st, launch_gemm_tc(m, p, epi, passes, pick_bn(h, M, w.N), pick_cg(w.N), pick_cs(M), ew,
+                                           sms > 0 && sms < h->num_sms ? sms : h->num_sms, st));
   }
   return 0;
 }
