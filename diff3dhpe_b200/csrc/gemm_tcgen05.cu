@@ -401,6 +401,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int q_ = 0, tile; (tile = tile_of(q_)) >= 0; ++q_) {
         const int m0 = ((tile / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
         const int n0 = (tile % n_tiles_n) * BN + static_cast<int>(rank) * C::kBRows;
+        int m0_next = -1;                      // first row of this CTA in the unit's next m-tile (n-inner order only)
+        if (PASSES == 4 && p.n_inner) {
+          const int tn = tile_of(q_ + n_tiles_n);
+          if (tn >= 0) m0_next = ((tn / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
+          if (m0_next >= p.M) m0_next = -1;
+        }
         for (int kb = 0; kb < n_steps; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* s = smem + stage * C::kStageBytes;
@@ -408,6 +414,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             // fp16 (hi) stages first, then e2m1 (c4) stages with their scale-factor atoms; all bytes of both CTAs complete
             // on the leader's full barrier
             const bool f4 = kb >= n_kb;
+            if (p.prefetch_a && m0_next >= 0 && tile % n_tiles_n == 0) {
+              // The A rows of this unit's NEXT m-tile still sit in HBM (an activation operand is 3.3 GB, the L2 126 MB); its
+              // first n-tile would wait for them with only the ring's depth of cover.  Pull stage kb of it into L2 now,
+              // one whole m-tile ahead (the other n-tiles re-read the rows from L2 anyway).
+              const int pc0 = f4 ? (kb - n_kb) * 128 : kb * BK;
+              ptx::tma_prefetch_l2_2d(f4 ? &tm_a_lo : &tm_a_hi, pc0, m0_next);
+              if (f4) ptx::tma_prefetch_l2_2d(&tm_a_sf, 0, 2 * ((m0_next >> 7) * (p.K / 64) + 2 * (kb - n_kb)));
+            }
             const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), leader);
             if (rank == 0)
               ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * (kTileBytesA + C::kTileBytesB + (f4 ? C::kSfBytes : 0)));

@@ -56,6 +56,7 @@ struct GemmParams {
   __half* ln_hi;          // A operand of the next GEMM (FMT_F8C: hi fp16 [M,512] + c8 bytes [M,1024])
   __half* ln_second;
   int n_inner;            // tile order of the persistent tcgen05 kernel: 1 = all n-tiles of an m-tile on the same CTA pair
+  int prefetch_a;         // FMT_F4C, n-inner: L2-prefetch the A rows of the unit's next m-tile while the current one runs
   __half* emit_hi;        // EPI_F32_EMIT: x as a FMT_F4C operand [M,N] (hi fp16, c4 bytes, scale-factor atoms)
   uint8_t* emit_c4;
   uint8_t* emit_sf;

@@ -339,6 +339,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// L2 prefetch of a tiled box (no shared-memory destination, no completion): HBM -> L2 ahead of the TMA load that needs it
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // shared-space accesses with 32-bit addresses (a generic pointer costs a 64-bit add and a generic-space LD / ST per access)
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
