@@ -323,8 +323,9 @@ int run_gemm(d3d_handle* h, const OperandBuf& a, const Lin& w, int64_t M, int ep
   p.stream_out = env_int("D3D_GEMM_STREAM_OUT", 1);
   // measured (profiles/r01q_*): DRAM reads of the qkv GEMM 2.9x -> 1.1x its algorithmic bytes, step time -1.7 %
   p.n_inner = env_int("D3D_GEMM_N_INNER", 1);
-  // OFF: measured SLOWER (profiles/r02t_gemm_pf.log: qkv +8 %, fc2 +29 %, step 3184 -> 3420 ms) -- an m-tile ahead is ~40 us
-  // of streaming writes ahead, the prefetched rows are evicted again before the loads arrive and HBM reads them twice
+  // OFF: measured SLOWER at both distances -- 1 = a whole m-tile ahead (profiles/r02t_gemm_pf.log: qkv +8 %, fc2 +29 %, step
+  // 3184 -> 3420 ms), 2 = during the last n-tile of the current m-tile (r02u: qkv +3 %, fc2 +20 %): the prefetch requests
+  // ride the same saturated TMA / L2 path as the operand loads they are meant to help
   p.prefetch_a = env_int("D3D_GEMM_PREFETCH_A", 0);
   if (mode == D3D_GEMM_SIMT_FP32 || mode == D3D_GEMM_SIMT_F8C || mode == D3D_GEMM_SIMT_F4C) {
     KLP(D3D_PROF_GEMM, st, launch_gemm_simt(a.hi, a.lo, a.sf, w.hi, w.lo, w.sf, p, epi, mode_fmt(mode), st));

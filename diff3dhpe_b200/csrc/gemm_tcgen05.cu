@@ -403,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int n0 = (tile % n_tiles_n) * BN + static_cast<int>(rank) * C::kBRows;
         int m0_next = -1;                      // first row of this CTA in the unit's next m-tile (n-inner order only)
         if (PASSES == 4 && p.n_inner) {
-          const int tn = tile_of(q_ + n_tiles_n);
+          const int tn = tile_of(q_ + n_tiles_n - tile % n_tiles_n);      // first tile of the unit's next m-tile
           if (tn >= 0) m0_next = ((tn / n_tiles_n) * CS + static_cast<int>(pair)) * TM + static_cast<int>(rank) * BM;
           if (m0_next >= p.M) m0_next = -1;
         }
@@ -414,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             // fp16 (hi) stages first, then e2m1 (c4) stages with their scale-factor atoms; all bytes of both CTAs complete
             // on the leader's full barrier
             const bool f4 = kb >= n_kb;
-            if (p.prefetch_a && m0_next >= 0 && tile % n_tiles_n == 0) {
+            if (p.prefetch_a && m0_next >= 0 && tile % n_tiles_n == (p.prefetch_a == 2 ? n_tiles_n - 1 : 0)) {
               // The A rows of this unit's NEXT m-tile still sit in HBM (an activation operand is 3.3 GB, the L2 126 MB); its
               // first n-tile would wait for them with only the ring's depth of cover.  Pull stage kb of it into L2 now,
               // one whole m-tile ahead (the other n-tiles re-read the rows from L2 anyway).
