@@ -52,6 +52,7 @@ PROTOTYPES = {
     "d3d_pose_metrics_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                               C.c_void_p]),
     "d3d_launch_count": (C.c_int64, [C.c_void_p]),
+    "d3d_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "d3d_profile_begin": (C.c_int, [C.c_void_p]),
     "d3d_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "d3d_op_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -116,6 +116,7 @@ struct d3d_handle {
   float* absmax_dev = nullptr;         // load-time |w| maximum of the last split weight (range guard)
   double* vel_tmp = nullptr;           // per-call (sum, count) of the velocity error (d3d_pose_metrics_accumulate)
   std::vector<void*> allocs;
+  int64_t alloc_bytes = 0;             // device bytes owned by the handle (d3d_workspace_bytes)
 };
 
 namespace {
@@ -173,6 +174,7 @@ int dev_alloc(d3d_handle* h, T** p, int64_t n, bool zero = true) {
   CK(cudaMalloc(&q, static_cast<size_t>(n) * sizeof(T)));
   if (zero) CK(cudaMemset(q, 0, static_cast<size_t>(n) * sizeof(T)));
   h->allocs.push_back(q);
+  h->alloc_bytes += static_cast<int64_t>(n) * static_cast<int64_t>(sizeof(T));
   *p = static_cast<T*>(q);
   return 0;
 }
@@ -568,6 +570,8 @@ int d3d_abi_version(void) { return D3D_ABI_VERSION; }
 const char* d3d_last_error(const d3d_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int64_t d3d_launch_count(const d3d_handle* h) { return h ? h->launches : 0; }
+
+int64_t d3d_workspace_bytes(const d3d_handle* h) { return h ? h->alloc_bytes : 0; }
 
 int d3d_create(const d3d_config* cfg, d3d_handle** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return -1; }

@@ -235,6 +235,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.d3d_launch_count(self.h))
 
+    def workspace_bytes(self) -> int:
+        """Device bytes owned by the handle (weights + workspace + tables; nothing is allocated on the hot path)."""
+        return int(self.lib.d3d_workspace_bytes(self.h))
+
     # ------------------------------------------------------------------ kernel-level entry points (tests / bench)
     def op_linear(self, a, w, bias, residual=None, act=0, gemm_mode=_lib.GEMM_TC_SPLIT3):
         M, K = a.shape

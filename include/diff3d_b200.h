@@ -168,6 +168,11 @@ D3D_API int d3d_mpjpe_accumulate(d3d_handle* h, const float* pred_dev, const flo
 /* Number of kernels launched (or replayed through graphs) by this handle since creation. */
 D3D_API int64_t d3d_launch_count(const d3d_handle* h);
 
+/* Device bytes the handle owns (packed weights, activation workspace, time tables, sampler state): everything is
+ * allocated in d3d_create / d3d_set_schedule, nothing on the hot path (SURVEY.md 8b `d3d_workspace_bytes`).  16 KB per
+ * token of max_clips * num_frame * num_joints + ~100 MB of weights: 34 GB for 512 clips of 243 frames. */
+D3D_API int64_t d3d_workspace_bytes(const d3d_handle* h);
+
 /* Per-kernel-class device timing.  Between d3d_profile_begin and d3d_profile_end every kernel of the sampler /
  * denoiser is launched un-graphed and bracketed by CUDA events on the launch stream; d3d_profile_end
  * synchronises and returns the summed durations (ms) and launch counts per class. */

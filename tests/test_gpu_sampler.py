@@ -107,6 +107,23 @@ def test_sampler_golden_alternative_epilogues(golden, monkeypatch, name, env):
         assert torch.equal(pred, pred2)
 
 
+def test_workspace_bytes_and_no_hot_path_allocation():
+    """d3d_workspace_bytes: the handle's device footprint is fixed after create / set_schedule -- 16 KB per
+    token of the largest batch plus the packed weights -- and a sampler call allocates nothing (graph replay needs that)."""
+    F, B, S = 27, 3, 2
+    diff = _diffusion(F, S, max_clips=B)
+    x2d, _ = synthetic.make_inputs(B, F)
+    y_T, _ = synthetic.make_noise(B, F, S)
+    diff.ddim_sample_loop(x2d.cuda(), [B, F, 17, 3], noise=(y_T.cuda(), None))
+    eng = diff.model.engine(B)
+    before = eng.workspace_bytes()
+    tokens = (B * F * 17 + 511) // 512 * 512
+    assert before >= tokens * 14 * 1024 and before < tokens * 17 * 1024 + 400 * 2 ** 20
+    diff.ddim_sample_loop(x2d.cuda(), [B, F, 17, 3], noise=(y_T.cuda(), None))
+    diff.ddim_sample_loop(x2d[:2].cuda(), [2, F, 17, 3], noise=(y_T[:2].cuda(), None))
+    assert eng.workspace_bytes() == before
+
+
 def test_fp16_fast_mode_is_within_maxabs_bar(golden):
     g = golden("sampler_f27_b2_s3_clip")
     diff = _diffusion(27, 3, gemm_mode=_lib.GEMM_TC_FP16, max_clips=2)
