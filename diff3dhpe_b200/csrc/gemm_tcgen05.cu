@@ -27,9 +27,14 @@
 //     mainloop of tile i+1.  Eight epilogue warps per CTA read TMEM with tcgen05.ld (32 lanes x 32 columns);
 //     the residual rows of chunk c+1 are prefetched while chunk c is in flight (the un-prefetched version was
 //     latency-bound: 26 % tensor-pipe on the proj GEMM).
+//   * epilogues (kernels.cuh GemmEpi): fp32 (+ residual) through a swizzled transpose buffer; the SHIPPED in-place residual
+//     update of proj / fc2 as a TMA reduction (EPI_F32_RED: the L2 adds, X never enters the SM -- the L2 -> SM operand
+//     feed is what bounds all four GEMMs); q | k | v_hi | v_lo fp16 pack; GELU -> block-scaled operand (1-MUFU
+//     GELU, bias from shared memory, per-lane store addressing); the deferred-LayerNorm pair EPI_F32_EMIT / EPI_GELU_DLN
+//     (measured, off by default).
 //
 // Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA), 2 = TMEM allocator, 3 = idle,
-// 4..11 = epilogue.
+// 4..11 = epilogue (EW = 16: 640 threads, epilogue warps 4..19, setmaxnreg 32 / 112).
 #include "kernels.cuh"
 #include "operand.cuh"
 #include "ptx.cuh"
@@ -654,7 +659,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       // (read + write) and, with the F4C mainloop at ~5 us per tile, sets the tile time of proj / fc2: ncu had them at
       // 55-58 % of DRAM with ONE 4 KB chunk per warp in flight (32 KB per SM, below bandwidth x latency ~ 44 B/ns x 0.8 us);
       // two chunks per warp double the bytes in flight (profiles/r02d_full_gemm.md -> r02e).
-      constexpr int kResDepth = (EPI == EPI_F32 && EW == 8) ? D3D_GEMM_RES_DEPTH : 1;      // EMIT keeps x in registers too      // EW = 16: 104 registers, no room
+      constexpr int kResDepth = (EPI == EPI_F32 && EW == 8) ? D3D_GEMM_RES_DEPTH : 1;      // EMIT / 16 warps: no registers to spare
       // 16 warps at 104 registers: x (32 registers) stays live through the operand emission, so the next residual chunk is
       // requested only after it (four warps per scheduler cover the exposed latency)
       constexpr bool kLateRes = EPI == EPI_F32_EMIT && EW == 16;
