@@ -62,8 +62,18 @@ struct TcBars {
   uint64_t o_full[NSLOT];       // O = P V complete                                         (MMA -> epilogue)
   uint64_t tmem_free[NSLOT];    // O read out: the columns may receive the next S           (epilogue -> MMA)
   uint64_t vlo_full[NSLOT];     // v_lo rows of the tile landed in the (dead) Q tile        (TMA -> epilogue)
+  uint64_t staged[NSLOT];       // the tile's output rows are staged in shared memory       (epilogue -> store warp)
+  uint64_t stg_free[NSLOT];     // the TMA stores have read the slot's staging buffer       (store warp -> epilogue)
   uint32_t tmem_base;
 };
+
+// D3D_ATTN_STORE_WARP = 1: the TMA stores of a tile and the wait for them to have read shared memory are issued by an
+// otherwise idle warp of the control warpgroup (one per slot) instead of by row 0 of the slot's softmax warps, whose warp
+// would sit in cp.async.bulk.wait_group.read while the next S of the slot is already complete (the slot's four warps
+// arrive on p_full together, so the wait was on every tile's critical path).
+#ifndef D3D_ATTN_STORE_WARP
+#define D3D_ATTN_STORE_WARP 1
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -357,6 +367,8 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       ptx::mbar_init(&bars->o_full[s], 1);
       ptx::mbar_init(&bars->tmem_free[s], 128);
       ptx::mbar_init(&bars->vlo_full[s], 1);
+      ptx::mbar_init(&bars->staged[s], 1);
+      ptx::mbar_init(&bars->stg_free[s], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -431,6 +443,38 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     }
   } else if (warp > kMmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
+    // ------------------------------------------------------------------ store warps: one per slot (D3D_ATTN_STORE_WARP)
+    const int slot = warp - (kMmaWarp + 1);
+    if (D3D_ATTN_STORE_WARP && slot < NSLOT && ptx::elect_one()) {
+      uint8_t* Stg = StgAll + slot * kTile;
+      for (int w = slot; w < W; w += NSLOT) {
+        const int n = w / n_mt, m = w - n * n_mt;
+        const int i = w / NSLOT, stage = n % n_stage;
+        const int unit = blockIdx.x + n * gridDim.x;
+        const int seq = unit >> 3, h = unit & 7;
+        int b = seq / J, j = seq - b * J;
+        const bool tail = SPATIAL && j == J - 1 && F % 7 != 0;
+        if (SPATIAL) { j = (b * F + 7 * j) * 17; b = 0; }
+        if (PACKED) j *= pk_g;
+        uint8_t* Qs = smem + stage * stage_bytes;
+        ptx::mbar_wait(&bars->staged[slot], i & 1);
+        const CUtensorMap* mh = tail ? &tm_hi_tail : &tm_hi;
+        const CUtensorMap* ms = tail ? &tm_second_tail : &tm_second;
+        ptx::tma_store_4d(mh, Qs + m * kTile, h * kHd, j, m * 128, b);
+        if (FMT == FMT_F4C) {
+          ptx::tma_store_4d(ms, Stg, h * 32, j, m * 128, b);
+          ptx::tma_store_4d(ms, Stg + 4096, (kC >> 1) + h * 32, j, m * 128, b);
+        } else {
+          ptx::tma_store_4d(ms, Stg, h * kHd, j, m * 128, b);
+          if (FMT != FMT_SPLIT16) ptx::tma_store_4d(ms, Stg + 8192, kC + h * kHd, j, m * 128, b);
+        }
+        ptx::bulk_commit();
+        ptx::bulk_wait_read_all();           // Stg / Q_m have been read: the tile has left shared memory
+        ptx::mbar_arrive(&bars->stage_free[stage]);
+        ptx::mbar_arrive(&bars->stg_free[slot]);
+      }
+      ptx::bulk_wait_all();
+    }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue: thread = query row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSoftmaxRegs));
@@ -507,7 +551,11 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       ptx::mbar_arrive(&bars->tmem_free[slot]);
 
       // ---- epilogue: out = O / l - (v_hi + v_lo), packed as the proj GEMM's A operand, staged for the TMA stores
-      ptx::bar_sync(1 + slot, 128);          // the issuer is past the read-wait of the previous tile's stores: Stg is free
+      if (D3D_ATTN_STORE_WARP) {             // the previous tile's stores have read the slot's staging buffer
+        if (i > 0) ptx::mbar_wait(&bars->stg_free[slot], (i - 1) & 1);
+      } else {
+        ptx::bar_sync(1 + slot, 128);        // the issuer is past the read-wait of the previous tile's stores: Stg is free
+      }
       const ptx::f32x2 inv2 = ptx::splat2(inv);
       if (FMT == FMT_F4C) {
         // block-scaled operand (operand.cuh): the row's 64 channels are two 32-element scale blocks of each part.
@@ -608,7 +656,9 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       }
       ptx::fence_proxy_async();
       ptx::bar_sync(1 + slot, 128);          // every row is staged, and nobody still reads v_hi rows of this tile
-      if (issuer) {
+      if (D3D_ATTN_STORE_WARP) {
+        if (issuer) ptx::mbar_arrive(&bars->staged[slot]);
+      } else if (issuer) {
         const CUtensorMap* mh = tail ? &tm_hi_tail : &tm_hi;
         const CUtensorMap* ms = tail ? &tm_second_tail : &tm_second;
         ptx::tma_store_4d(mh, Qs + m * kTile, h * kHd, j, m * 128, b);
@@ -624,7 +674,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         ptx::mbar_arrive(&bars->stage_free[stage]);
       }
     }
-    if (issuer) ptx::bulk_wait_all();
+    if (!D3D_ATTN_STORE_WARP && issuer) ptx::bulk_wait_all();
   }
 
   ptx::tc_fence_before();
