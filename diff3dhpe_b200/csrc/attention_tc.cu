@@ -26,6 +26,7 @@
 //
 // Warp roles (384 threads): 0..3 softmax + epilogue of slot 0 (TMEM lane quadrant = warp & 3), 4..7 of slot 1,
 // 8 = TMA producer, 9 = MMA issuer and TMEM allocator, 10..11 idle (they complete the control warpgroup).
+#include <cstdlib>
 #include "kernels.cuh"
 #include "operand.cuh"
 // The barrier waits of this kernel sit on a per-item latency chain (MMA -> softmax -> MMA -> epilogue): the sleeping
@@ -335,17 +336,26 @@ __device__ __forceinline__ float softmax_row_packed(uint32_t taddr, int F, int G
 // boxes, the *_tail maps (F % 7) * 17-row boxes.  J carries the groups per clip.
 // PACKED: G = `pk_g` joints per tile (softmax_row_packed); J then counts the joint GROUPS per clip and `j_tok` the joints.
 template <int FMT, int NSLOT, int NCH, bool SPATIAL, bool PACKED = false>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__((4 * NSLOT + 4) * 32, 1)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_hi,
                         const __grid_constant__ CUtensorMap tm_second, const __grid_constant__ CUtensorMap tm_hi_tail,
                         const __grid_constant__ CUtensorMap tm_second_tail, uint8_t* __restrict__ sf_out, int F, int J,
                         int n_units, int n_mt, int NKp, int n_stage, int pk_g = 1, int j_tok = 0) {
   static_assert(!PACKED || (!SPATIAL && NCH == 0), "the packed mode is a temporal mode with a runtime chunk count");
+  // NSLOT == 3 (single-tile modes, S only 128 columns wide, FMT_F4C): three 128-column slots, three softmax warpgroups
+  // (512 threads, 128 registers at launch, control 40 / softmax 152), P aliases [0, 64), O [64, 128), 8 KB of staging per slot
+  static_assert(NSLOT == 2 || (NSLOT == 3 && FMT == FMT_F4C && (SPATIAL || PACKED)), "three slots: single-tile F4C modes only");
+  constexpr int kSC = NSLOT == 2 ? kSlotCols : 128;            // TMEM columns per slot
+  constexpr int kOC = NSLOT == 2 ? kOCol : 64;                 // O accumulator inside the slot
+  constexpr int kStgSlot = NSLOT == 2 ? kTile : 8192;          // staging bytes per slot
+  constexpr int kTmemCols = NSLOT == 2 ? 512 : 512;            // power of two >= NSLOT * kSC
+  constexpr int kSmxRegs = NSLOT == 2 ? kSoftmaxRegs : 152;
+  static_assert(NSLOT != 3 || 3 * 128 * (152 - 128) <= 128 * (128 - kCtrlRegs), "setmaxnreg pool overdrawn");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = 3 * n_mt * kTile;          // Q tiles | K tiles | V tiles of one unit
   uint8_t* StgAll = smem + n_stage * stage_bytes;    // 16 KB per slot: second-part staging of one 128-row output tile
-  TcBars<NSLOT>* bars = reinterpret_cast<TcBars<NSLOT>*>(StgAll + NSLOT * kTile);
+  TcBars<NSLOT>* bars = reinterpret_cast<TcBars<NSLOT>*>(StgAll + NSLOT * kStgSlot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kTmaWarp = 4 * NSLOT, kMmaWarp = 4 * NSLOT + 1;
@@ -372,7 +382,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     }
     ptx::fence_barrier_init();
   }
-  if (warp == kMmaWarp) ptx::tmem_alloc<kSlotCols * NSLOT>(&bars->tmem_base);
+  if (warp == kMmaWarp) ptx::tmem_alloc<kTmemCols>(&bars->tmem_base);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -412,11 +422,11 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       auto issue_pv = [&](int w) {           // O[128, 64] = P[128, NKp] (TMEM) . V[NKp, 64], 16 keys per MMA
         const int slot = w % NSLOT, i = w / NSLOT, stage = (w / n_mt) % n_stage;
         const uint32_t sV = s0 + stage * stage_bytes + 2 * n_mt * kTile;
-        const uint32_t tcol = tmem_base + slot * kSlotCols;
+        const uint32_t tcol = tmem_base + slot * kSC;
         ptx::mbar_wait(&bars->p_full[slot], i & 1);
         ptx::tc_fence_after();
         for (int ks = 0; ks < n_ks; ++ks)
-          ptx::mma_f16_ts(tcol + kOCol, tcol + ks * 8, make_desc_mn_sw128(sV + ks * 2048), idesc_pv, ks != 0 ? 1u : 0u);
+          ptx::mma_f16_ts(tcol + kOC, tcol + ks * 8, make_desc_mn_sw128(sV + ks * 2048), idesc_pv, ks != 0 ? 1u : 0u);
         ptx::mma_commit(&bars->o_full[slot]);
       };
       for (int w = 0; w < W; ++w) {
@@ -431,7 +441,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)            // S[128, NKp] = Q_m[128, 64] . K[NKp, 64]^T, 16 channels per MMA
-          ptx::mma_f16_ss(tmem_base + slot * kSlotCols, ptx::make_desc_k_sw128(sQ + m * kTile + k * 32),
+          ptx::mma_f16_ss(tmem_base + slot * kSC, ptx::make_desc_k_sw128(sQ + m * kTile + k * 32),
                           ptx::make_desc_k_sw128(sK + k * 32), idesc_qk, k != 0 ? 1u : 0u);
         ptx::mma_commit(&bars->s_full[slot]);
         // the P.V of the item NSLOT-1 back: with two slots, S of this item is already being computed while the other
@@ -444,10 +454,12 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   } else if (warp > kMmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
     // ------------------------------------------------------------------ store warps: one per slot (D3D_ATTN_STORE_WARP)
-    const int slot = warp - (kMmaWarp + 1);
-    if (D3D_ATTN_STORE_WARP && slot < NSLOT && ptx::elect_one()) {
-      uint8_t* Stg = StgAll + slot * kTile;
-      for (int w = slot; w < W; w += NSLOT) {
+    const int sidx = warp - (kMmaWarp + 1);          // store warp 0 serves the even slots, store warp 1 the odd ones
+    if (D3D_ATTN_STORE_WARP && ptx::elect_one()) {
+      for (int w = 0; w < W; ++w) {
+        const int slot = w % NSLOT;
+        if ((slot & 1) != sidx) continue;
+        uint8_t* Stg = StgAll + slot * kStgSlot;
         const int n = w / n_mt, m = w - n * n_mt;
         const int i = w / NSLOT, stage = n % n_stage;
         const int unit = blockIdx.x + n * gridDim.x;
@@ -477,16 +489,16 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue: thread = query row
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSoftmaxRegs));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSmxRegs));
     const int slot = warp >> 2;
     const int row_l = (warp & 3) * 32 + lane;                             // row inside the 128-query tile
-    const uint32_t taddr = tmem_base + slot * kSlotCols + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t taddr = tmem_base + slot * kSC + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const int n_chunks = (NKp + 31) >> 5;
     if (!SPATIAL && NCH > 0 && (n_chunks != NCH || F <= 32 * (NCH - 1))) __trap();    // launcher / instantiation mismatch
     if ((SPATIAL || PACKED) && (n_mt != 1 || NKp != 128)) __trap();
     const int sw = (row_l & 7) << 4;                                      // swizzle XOR of this row (bytes)
     const bool issuer = row_l == 0;                                       // issues the slot's TMA stores
-    uint8_t* Stg = StgAll + slot * kTile;
+    uint8_t* Stg = StgAll + slot * kStgSlot;
     for (int w = slot; w < W; w += NSLOT) {
       const int n = w / n_mt, m = w - n * n_mt;
       const int i = w / NSLOT, stage = n % n_stage;
@@ -544,8 +556,8 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       ptx::mbar_wait(&bars->o_full[slot], i & 1);
       ptx::tc_fence_after();
       uint32_t o0[32], o1[32];
-      ptx::tmem_ld_32x32(taddr + kOCol, o0);
-      ptx::tmem_ld_32x32(taddr + kOCol + 32, o1);
+      ptx::tmem_ld_32x32(taddr + kOC, o0);
+      ptx::tmem_ld_32x32(taddr + kOC + 32, o1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->tmem_free[slot]);
@@ -681,7 +693,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   __syncthreads();
   if (warp == kMmaWarp) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<kSlotCols * NSLOT>(tmem_base);
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -1084,11 +1096,17 @@ int encode_tokens_2d(CUtensorMap* out, void* base, CUtensorMapDataType dt, int e
 inline int tc_stages(int n_mt) { return n_mt == 1 ? 4 : 2; }
 template <int NSLOT>
 int tc_smem_bytes(int n_mt) {
-  return (tc_stages(n_mt) * 3 * n_mt + NSLOT) * kTile + static_cast<int>(sizeof(TcBars<NSLOT>)) + 1024 /*alignment slack*/;
+  return tc_stages(n_mt) * 3 * n_mt * kTile + NSLOT * (NSLOT == 2 ? kTile : 8192) + static_cast<int>(sizeof(TcBars<NSLOT>)) +
+         1024 /*alignment slack*/;
 }
 
 }  // namespace
 
+// D3D_ATTN_SLOTS = 3: three 128-column TMEM slots / softmax warpgroups in the single-tile modes (spatial, packed temporal)
+inline bool three_slots() {
+  const char* v = getenv("D3D_ATTN_SLOTS");
+  return v && *v == '3';
+}
 inline int packed_group(int F) { return F <= 32 ? 4 : (F <= 64 ? 2 : 1); }     // joints per 128-row tile
 
 int make_attn_tc_maps(AttnTcMaps* maps, const __half* qkv, __half* o_hi, __half* o_second, int fmt, int F, int J,
@@ -1151,6 +1169,12 @@ cudaError_t configure_attention_tc() {
   D3D_CFG_TC(FMT_SPLIT16, 0, true) D3D_CFG_TC(FMT_F8C, 0, true)
   D3D_CFG_TC(FMT_F4C, 0, false) D3D_CFG_TC(FMT_F4C, 3, false) D3D_CFG_TC(FMT_F4C, 8, false) D3D_CFG_TC(FMT_F4C, 0, true)
 #undef D3D_CFG_TC
+  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_F4C, 3, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                tc_smem_bytes<3>(1))) != cudaSuccess)
+    return e;
+  if ((e = cudaFuncSetAttribute(attn_temporal_tc_kernel<FMT_F4C, 3, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                tc_smem_bytes<3>(1))) != cudaSuccess)
+    return e;
   for (auto kern : {attn_temporal_tc2_kernel<8>, attn_temporal_tc2_kernel<3>, attn_temporal_tc2_kernel<0>})
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<2>(2))) != cudaSuccess) return e;
 #define D3D_CFG_PK(FMT_)                                                                                                     \
@@ -1178,7 +1202,10 @@ cudaError_t launch_attn_temporal_tc(const AttnTcMaps& maps, const __half* qkv, u
 #define D3D_LAUNCH_PK(FMT_)                                                                   \
   attn_temporal_tc_kernel<FMT_, 2, 0, false, true><<<grid, kTcThreads, smem, st>>>(           \
       maps.qkv, maps.o_hi, maps.o_second, maps.o_hi, maps.o_second, o_sf, F, JG, n_units, 1, 128, tc_stages(1), G, J)
-    if (fmt == FMT_F4C) D3D_LAUNCH_PK(FMT_F4C);
+    if (fmt == FMT_F4C && three_slots())
+      attn_temporal_tc_kernel<FMT_F4C, 3, 0, false, true><<<grid, 512, tc_smem_bytes<3>(1), st>>>(
+          maps.qkv, maps.o_hi, maps.o_second, maps.o_hi, maps.o_second, o_sf, F, JG, n_units, 1, 128, tc_stages(1), G, J);
+    else if (fmt == FMT_F4C) D3D_LAUNCH_PK(FMT_F4C);
     else if (fmt == FMT_F8C) D3D_LAUNCH_PK(FMT_F8C);
     else D3D_LAUNCH_PK(FMT_SPLIT16);
 #undef D3D_LAUNCH_PK
@@ -1224,7 +1251,11 @@ cudaError_t launch_attn_spatial_tc(const AttnTcMaps& maps, uint8_t* o_sf, int fm
   const int n_units = static_cast<int>(units64);
   const int grid = n_units < num_sms ? n_units : num_sms;
   const int smem = tc_smem_bytes<2>(1);
-  if (fmt == FMT_F4C) {
+  if (fmt == FMT_F4C && three_slots()) {
+    if (!o_sf) return cudaErrorInvalidValue;
+    attn_temporal_tc_kernel<FMT_F4C, 3, 0, true><<<grid, 512, tc_smem_bytes<3>(1), st>>>(
+        maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, o_sf, F, G, n_units, 1, 128, tc_stages(1));
+  } else if (fmt == FMT_F4C) {
     if (!o_sf) return cudaErrorInvalidValue;
     attn_temporal_tc_kernel<FMT_F4C, 2, 0, true><<<grid, kTcThreads, smem, st>>>(
         maps.qkv, maps.o_hi, maps.o_second, maps.o_hi_tail, maps.o_second_tail, o_sf, F, G, n_units, 1, 128, tc_stages(1));

@@ -222,6 +222,26 @@ def test_attention_two_warpgroups_per_slot(monkeypatch, F):
     assert (out - ref).abs().max().item() < 4e-3
 
 
+@pytest.mark.parametrize("F,spatial", [(27, True), (243, True), (9, True), (100, True), (1, True), (9, False), (27, False),
+                                       (33, False), (64, False)])
+def test_attention_three_slots(monkeypatch, F, spatial):
+    """D3D_ATTN_SLOTS=3: the single-tile modes (spatial; packed temporal, F <= 64) with three 128-column TMEM slots and three
+    softmax warpgroups per CTA (512 threads) instead of two 256-column slots.  Same reference and tolerance as
+    test_attention_core."""
+    monkeypatch.setenv("D3D_ATTN_SLOTS", "3")
+    B, J, C = 2, 17, 512
+    eng = Engine(F, max_clips=B)
+    qkv = _rand((B * F * J, 3 * C), 20 + F, 1.5)
+    qkv[:, :2 * C] = qkv[:, :2 * C].half().float()
+    x = qkv.view(B, F, J, 3 * C)
+    seqs = x.reshape(B * F, J, 3 * C) if spatial else x.permute(0, 2, 1, 3).reshape(B * J, F, 3 * C)
+    ref = oracle.attention_core(seqs, 8)
+    ref = ref.reshape(B, F, J, C) if spatial else ref.reshape(B, J, F, C).permute(0, 2, 1, 3)
+    out = eng.op_attention(qkv.cuda(), B, spatial, _lib.ATTN_DEFAULT).cpu().view(B, F, J, C)
+    eng.close()
+    assert (out - ref).abs().max().item() < 4e-3
+
+
 def test_tc_matches_simt_elementwise(eng27):
     """Same split operands in, so tensor-core and CUDA-core results differ only by accumulation order and the
     dropped lo*lo term (2^-22 relative)."""
