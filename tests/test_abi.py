@@ -29,7 +29,9 @@ def test_library_builds_and_exports_header_symbols():
 
 
 def test_sass_is_blackwell_native():
-    """The GEMM must be tcgen05 + TMA + TMEM (UTCHMMA / UTMALDG / LDTM in SASS), not a legacy-only path."""
+    """The GEMM must be tcgen05 + TMA + TMEM (UTCHMMA / UTMALDG / LDTM in SASS), not a legacy-only path; the shipped
+    precision mode needs the block-scaled MMA (UTCOMMA, kind::mxf4) with scale factors copied into TMEM (UTCCP), and the
+    in-place residual update of proj / fc2 the TMA reduction (UTMAREDG)."""
     import shutil
     import subprocess
     if shutil.which("cuobjdump") is None and not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
@@ -37,7 +39,7 @@ def test_sass_is_blackwell_native():
     exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     build.build()
     sass = subprocess.run([exe, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCOMMA", "UTCCP", "UTMAREDG", "UTMASTG"):
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
 
 
