@@ -16,6 +16,11 @@ namespace d3d {
 namespace {
 
 constexpr int kWarpsPerCta = 8;
+// the two-row kernels are capped at 64 registers (4 CTAs = 32 warps per SM instead of 24): LayerNorm class 498 -> 480 ms per
+// cfg3 step (profiles/r02y3_*); D3D_ROWS2_MIN_CTAS=1 builds the uncapped forms
+#ifndef D3D_ROWS2_MIN_CTAS
+#define D3D_ROWS2_MIN_CTAS 4
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -233,7 +238,7 @@ lift_ln_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, cons
 // lift_ln on two rows per warp: the five fusion_layer weight rows, its bias, the time vector and the norm1 parameters are
 // loaded once for both tokens (only the Spatial_pos_embed row differs); eval only (one time vector for every clip).
 template <int FMT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, D3D_ROWS2_MIN_CTAS)
 lift_ln2_kernel(const float* __restrict__ x2d, const float* __restrict__ y3, const float* __restrict__ x5,
                 const float* __restrict__ wf_t, const float* __restrict__ bf, const float* __restrict__ spos,
                 const float* __restrict__ tvec, LnParams ln1, float* __restrict__ X, __half* __restrict__ a_hi,
@@ -326,7 +331,7 @@ ln_split_kernel(const float* __restrict__ X, LnParams ln, float eps, __half* __r
 // Two rows per warp (rows 2 w, 2 w + 1 of the launch): the production forms of ln_split / postnorm_add_ln when no
 // per-row additive term is needed (eval: one time vector for every clip; Temporal_pos_embed only after block 0).
 template <int FMT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, D3D_ROWS2_MIN_CTAS)
 ln_split2_kernel(const float* __restrict__ X, LnParams ln, float eps, __half* __restrict__ a_hi, __half* __restrict__ a_lo,
                  uint8_t* __restrict__ a_sf, int64_t T) {
   const int lane = threadIdx.x & 31;
@@ -342,7 +347,7 @@ ln_split2_kernel(const float* __restrict__ X, LnParams ln, float eps, __half* __
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, D3D_ROWS2_MIN_CTAS)
 postnorm_add_ln2_kernel(float* __restrict__ X, LnParams post, const float* __restrict__ tvec, LnParams ln1,
                         __half* __restrict__ a_hi, __half* __restrict__ a_lo, uint8_t* __restrict__ a_sf, int64_t T) {
   const int lane = threadIdx.x & 31;
@@ -445,7 +450,7 @@ __device__ __forceinline__ void head_finish(float o0, float o1, float o2, int la
   }
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, D3D_ROWS2_MIN_CTAS)
 head_ddim2_kernel(const float* __restrict__ X, LnParams post, LnParams head_ln, const float* __restrict__ wh,
                   const float* __restrict__ bh, DdimStep s, float* __restrict__ y, const float* __restrict__ noise,
                   float* __restrict__ out3, float* __restrict__ trace_y, float* __restrict__ trace_x0,
